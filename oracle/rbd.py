@@ -95,8 +95,8 @@ def local_ext_forces(model, kin, ee_frames, forces):
 def rnea(model, kin, v, a, fext):
     """pin.rnea(model, data, q, v, a, fext) -> tau (appendix A.3)."""
     n = model.njoints
-    batch = np.broadcast(v[..., 0], a[..., 0]).shape
-    dt = np.result_type(v.dtype, a.dtype, kin.oR[1].dtype)
+    batch = np.broadcast(v[..., 0], a[..., 0], kin.oR[1][..., 0, 0], *[f_[..., 0] for f_ in fext.values()]).shape
+    dt = np.result_type(v.dtype, a.dtype, kin.oR[1].dtype, *[f_.dtype for f_ in fext.values()])
     vel, acc, f = [None] * n, [None] * n, [None] * n
     vel[0] = np.zeros(batch + (6,), dtype=dt)
     acc[0] = np.zeros(batch + (6,), dtype=dt) + np.concatenate([-model.gravity, np.zeros(3)])
@@ -123,8 +123,8 @@ def rnea(model, kin, v, a, fext):
 def aba(model, kin, v, tau, fext):
     """pin.aba(model, data, q, v, tau, fext) -> a (Featherstone ABA, appendix A.4)."""
     n = model.njoints
-    batch = np.broadcast(v[..., 0], tau[..., 0]).shape
-    dt = np.result_type(v.dtype, tau.dtype, kin.oR[1].dtype)
+    batch = np.broadcast(v[..., 0], tau[..., 0], kin.oR[1][..., 0, 0], *[f_[..., 0] for f_ in fext.values()]).shape
+    dt = np.result_type(v.dtype, tau.dtype, kin.oR[1].dtype, *[f_.dtype for f_ in fext.values()])
     vel, c, IA, pA = [None] * n, [None] * n, [None] * n, [None] * n
     vel[0] = np.zeros(batch + (6,), dtype=dt)
     for i in range(1, n):

@@ -1,0 +1,53 @@
+// Library-internal handle: host tables, device copies, workspaces.  One handle per (GPU, stream).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/pino_locoman_b200.h"
+#include "plm_host.h"
+#include "plm_types.h"
+#include "plm_qp_types.h"
+
+struct plm_handle {
+  plm::HostTables host;
+  plm_ocp_desc ocp;
+  int max_batch = 0;
+  std::string error;
+  PlmModel* d_model = nullptr;
+  PlmLayout* d_layout = nullptr;
+  int16_t* d_lut = nullptr;
+  PlmConstEntry* d_consts = nullptr;
+  plm::DeviceTables tab;
+  double* d_tgt = nullptr;   // [max_batch][tgt_ld] dx_des | u_des
+  int tgt_ld = 0;
+  int node_ws_doubles = 0;
+  size_t node_smem = 0;
+  long long launches = 0;
+  // QP workspaces (plm_qp.cu)
+  plm::QpWork qp;
+  int qp_factor_doubles = 0;
+  // SQP step workspaces / timing
+  double* d_sqp = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+int plm_setup_node_kernels(plm_handle* h);
+int plm_launch_node_eval(plm_handle* h, const double* x, const double* p, int batch, double* g, double* J, int want_jac, cudaStream_t s);
+int plm_launch_bounds(plm_handle* h, const double* p, int batch, double* lbg, double* ubg, cudaStream_t s);
+int plm_launch_targets(plm_handle* h, const double* p, int batch, cudaStream_t s);
+int plm_launch_objective(plm_handle* h, const double* x, const double* dx, const double* alphas, int ntrial, const double* p,
+                         int batch, double* f, double* grad, cudaStream_t s);
+int plm_launch_hess_diag(plm_handle* h, const double* p, int batch, double* hess, cudaStream_t s);
+int plm_qp_alloc(plm_handle* h);
+void plm_qp_free(plm_handle* h);
+
+#define PLM_LAUNCH_CHECK(h)                                                    \
+  do {                                                                         \
+    cudaError_t _e = cudaGetLastError();                                       \
+    (h)->launches++;                                                           \
+    if (_e != cudaSuccess) {                                                   \
+      (h)->error = std::string("kernel launch: ") + cudaGetErrorString(_e);    \
+      return 5;                                                                \
+    }                                                                          \
+  } while (0)

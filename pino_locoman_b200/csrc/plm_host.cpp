@@ -1,0 +1,349 @@
+// Host table builder (see plm_host.h).  Row order and canonical forms follow optimization/ocp.py:103-198 and the
+// setup_dynamics_constraints of each optimization/ocp_*.py; x / p layouts follow setup_variables / setup_parameters.
+#include "plm_host.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace plm {
+
+namespace {
+
+struct Entry {
+  int col;       // local column in [dx_i | u_i | dx_{i+1}]
+  int kind;      // 0: lut source, 1: constant, 2: direct (written by a lane at a recorded position)
+  int src, idx;  // kind 0: source block and index;  kind 1: code/arg
+};
+
+struct RowBuilder {
+  std::vector<std::vector<Entry>> rows;
+  int new_row() { rows.emplace_back(); return (int)rows.size() - 1; }
+  void add(int row, int col, int kind, int src, int idx) { rows[row].push_back({col, kind, src, idx}); }
+};
+
+bool is_anc_or_self(const PlmModel& M, int a, int b) {   // body a is an ancestor-or-self of body b
+  while (b >= 0) {
+    if (a == b) return true;
+    b = M.parent[b];
+  }
+  return false;
+}
+
+}  // namespace
+
+static bool build_model(const plm_robot_desc& r, PlmModel& M, std::string& err) {
+  memset(&M, 0, sizeof(M));
+  if (r.nbody < 1 || r.nbody > PLM_MAXB) { err = "nbody out of range"; return false; }
+  M.nbody = r.nbody;
+  M.nv = 6 + r.nbody - 1;
+  M.nq = 7 + r.nbody - 1;
+  M.nj = r.nbody - 1;
+  if (M.nv > PLM_MAXCOL) { err = "nv exceeds one warp"; return false; }
+  M.nfeet = r.nfeet;
+  M.has_ext = r.has_ext_force ? 1 : 0;
+  M.ncontact = r.nfeet + M.has_ext;
+  if (r.nfeet != 4 || M.ncontact > PLM_MAXC) { err = "expected 4 feet"; return false; }
+  M.arm_body = r.arm_body;
+  for (int i = 0; i < 3; ++i) M.arm_off[i] = r.arm_offset[i];
+  M.gravity_z = 9.81;
+  double total = 0;
+  for (int b = 0; b < M.nbody; ++b) {
+    M.parent[b] = r.parent[b];
+    if (b == 0 ? r.parent[b] != -1 : (r.parent[b] < 0 || r.parent[b] >= b)) { err = "bodies must be in topological order"; return false; }
+    const double* pl = r.placement + 12 * b;
+    bool rot = false;
+    for (int i = 0; i < 9; ++i) {
+      M.place_R[b][i] = pl[i];
+      double id = (i % 4 == 0) ? 1.0 : 0.0;
+      if (fabs(pl[i] - id) > 0) rot = true;
+    }
+    M.has_rot[b] = rot;
+    for (int i = 0; i < 3; ++i) M.place_p[b][i] = pl[9 + i];
+    const double* ax = r.axis + 3 * b;
+    double n = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    M.axtype[b] = 3;
+    for (int i = 0; i < 3; ++i) M.axis[b][i] = (b > 0 && n > 0) ? ax[i] / n : 0.0;
+    if (b > 0) {
+      for (int i = 0; i < 3; ++i)
+        if (M.axis[b][i] == 1.0 && M.axis[b][(i + 1) % 3] == 0.0 && M.axis[b][(i + 2) % 3] == 0.0) M.axtype[b] = i;
+    }
+    const double* in = r.inertia + 10 * b;
+    M.mass[b] = in[0];
+    total += in[0];
+    for (int i = 0; i < 3; ++i) M.com[b][i] = in[1 + i];
+    for (int i = 0; i < 6; ++i) M.Ic[b][i] = in[4 + i];
+  }
+  M.total_mass = total;
+  for (int k = 0; k < M.ncontact; ++k) {
+    M.contact_body[k] = r.contact_body[k];
+    for (int i = 0; i < 3; ++i) M.contact_off[k][i] = r.contact_offset[3 * k + i];
+    for (int k2 = 0; k2 < k; ++k2)
+      if (M.contact_body[k2] == M.contact_body[k]) { err = "at most one contact frame per body"; return false; }
+  }
+  for (int d = 0; d < M.nv; ++d) {
+    int body = d < 6 ? 0 : d - 5;
+    M.col_body[d] = body;
+    int chain[PLM_MAXB], len = 0;
+    for (int b = body; b > 0; b = M.parent[b]) chain[len++] = b;
+    if (len > PLM_MAXDEPTH) { err = "kinematic chain too deep"; return false; }
+    M.chain_len[d] = len;
+    for (int l = 0; l < len; ++l) M.chain[d][l] = chain[len - 1 - l];
+    uint32_t mask = 0;
+    for (int k = 0; k < M.ncontact; ++k)
+      if (is_anc_or_self(M, body, M.contact_body[k])) mask |= 1u << k;
+    M.col_contacts[d] = mask;
+    if (M.arm_body >= 0 && is_anc_or_self(M, body, M.arm_body)) M.col_arm |= 1u << d;
+  }
+  int n = 0;
+  for (int b = M.nbody - 1; b >= 1; --b) M.body_order[n++] = b;   // topological order => reverse is leaves first
+  for (int j = 0; j < M.nj; ++j) {
+    M.joint_pos_min[j] = r.joint_pos_min[j];
+    M.joint_pos_max[j] = r.joint_pos_max[j];
+    M.joint_vel_max[j] = r.joint_vel_max[j];
+    M.joint_torque_max[j] = r.joint_torque_max[j];
+  }
+  for (int i = 0; i < M.nq; ++i) M.q0[i] = r.q0[i];
+  return true;
+}
+
+bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTables& out) {
+  PlmModel& M = out.model;
+  PlmLayout& L = out.layout;
+  if (!build_model(robot, M, out.error)) return false;
+  memset(&L, 0, sizeof(L));
+  const int kind = ocp.dynamics;
+  if (kind < 0 || kind > PLM_WHOLE_BODY_RNEA) { out.error = "Unknown dynamics type"; return false; }
+  const int N = ocp.nodes;
+  if (N < 2 || N > PLM_MAXNODES) { out.error = "nodes out of range"; return false; }
+  const int nv = M.nv, nq = M.nq, nj = M.nj, nfeet = M.nfeet;
+  const int nf = 3 * M.ncontact;
+  L.dynamics = kind;
+  L.nodes = N;
+  L.tau_nodes = (kind == PLM_WHOLE_BODY_RNEA) ? std::min(ocp.tau_nodes, N) : 0;
+  L.mu = ocp.mu;
+  L.nf = nf;
+  const bool cvel = kind == PLM_CENTROIDAL_VEL;
+  L.nx = cvel ? 6 + nq : nq + nv;
+  L.ndx = cvel ? 6 + nv : 2 * nv;
+  const int ndx = L.ndx;
+  L.lead = (kind == PLM_WHOLE_BODY_ABA) ? nj : nv;
+  L.f_idx = L.lead;
+  L.tau_idx = L.lead + nf;
+  // stage offsets
+  std::vector<int> nu(N);
+  for (int i = 0; i < N; ++i) nu[i] = L.lead + nf + ((kind == PLM_WHOLE_BODY_RNEA && i < L.tau_nodes) ? nj : 0);
+  L.x_off[0] = 0;
+  for (int i = 0; i < N; ++i) L.x_off[i + 1] = L.x_off[i] + ndx + nu[i];
+  L.n = L.x_off[N] + ndx;
+  // parameter offsets
+  int off = 0;
+  auto take = [&](int32_t& dst, int sz) { dst = off; off += sz; };
+  take(L.p_x_init, L.nx); take(L.p_dt_min, 1); take(L.p_dt_max, 1); take(L.p_contact, 4 * N); take(L.p_swing, 4 * N);
+  take(L.p_n_contacts, 1); take(L.p_swing_period, 1); take(L.p_swing_height, 1); take(L.p_swing_vel, 2);
+  take(L.p_Q, ndx); take(L.p_R, nu[0]); take(L.p_base_vel, 6); take(L.p_ext_force, 3); take(L.p_arm_vel, 3);
+  L.p_tau_prev = L.p_W = -1;
+  if (kind == PLM_WHOLE_BODY_RNEA) { take(L.p_tau_prev, nj); take(L.p_W, nj); }
+  L.np = off;
+
+  // local column helpers
+  const int dq0 = cvel ? 6 : 0;           // dq block inside dx
+  auto col_dq = [&](int c) { return dq0 + c; };
+  auto col_v = [&](int c, int nu_i) { (void)nu_i; return cvel ? ndx + c : nv + c; };   // dv (state) or U velocity
+  auto col_lead = [&](int c) { return ndx + c; };
+  auto col_f = [&](int k, int t) { return ndx + L.f_idx + 3 * k + t; };
+  auto col_tau = [&](int j) { return ndx + L.tau_idx + j; };
+  auto col_next = [&](int c, int nu_i) { return ndx + nu_i + c; };
+
+  // node types: (first-node skip?, torque rows?)
+  const bool first_skip = !cvel;
+  L.ntypes = 0;
+  int type_of[2][2] = {{-1, -1}, {-1, -1}};
+  std::vector<std::vector<std::vector<Entry>>> type_rows;
+  for (int i = 0; i < N; ++i) {
+    const int skip = (i == 0 && first_skip) ? 1 : 0;
+    const int jr = (kind == PLM_WHOLE_BODY_RNEA && i < L.tau_nodes) ? 1 : 0;
+    if (type_of[skip][jr] >= 0) { L.node_type[i] = type_of[skip][jr]; continue; }
+    if (L.ntypes >= 4) { out.error = "too many node types"; return false; }
+    const int t = L.ntypes++;
+    type_of[skip][jr] = t;
+    L.node_type[i] = t;
+    PlmNodeType& T = L.types[t];
+    memset(&T, 0, sizeof(T));
+    T.nu = nu[i];
+    T.joint_rows = jr;
+    T.state_rows = !skip;
+    T.row_int = T.row_dyn = T.row_tauj = T.row_taub = T.row_ext = T.row_arm = T.row_qj = T.row_vj = -1;
+    const int nu_i = nu[i];
+    // lut source offsets
+    const int sizes[PLM_SRC_COUNT] = {nv * nv, nv * nv, nv * nv, nv * nf, nfeet * 3 * nv, nfeet * 3 * nv, 3 * nv, 3 * nv, 6 * nv, 6 * nf};
+    int lo = 0;
+    for (int s = 0; s < PLM_SRC_COUNT; ++s) { T.src_off[s] = lo; lo += sizes[s]; }
+    T.lut_size = lo;
+    RowBuilder rb;
+    auto q_cols_ok = [&](int c) { return c >= 3; };   // no row depends on the base translation increment
+    // ---- 1. dynamics rows
+    T.row_int = 0;
+    if (cvel) {
+      for (int r = 0; r < 6; ++r) {   // dh_next - (dh + h_dot dt)
+        int row = rb.new_row();
+        rb.add(row, r, 1, 1, 0);
+        if (r >= 3) for (int c = 3; c < nv; ++c) rb.add(row, col_dq(c), 0, PLM_SRC_XQ, r * nv + c);
+        for (int k = 0; k < M.ncontact; ++k)
+          for (int tt = 0; tt < 3; ++tt)
+            if (r >= 3 || tt == r) rb.add(row, col_f(k, tt), 0, PLM_SRC_XF, r * nf + 3 * k + tt);
+        rb.add(row, col_next(r, nu_i), 1, 0, 0);
+      }
+      for (int c = 0; c < nv; ++c) {  // dq_next - (dq + v dt)
+        int row = rb.new_row();
+        rb.add(row, col_dq(c), 1, 1, 0);
+        rb.add(row, col_v(c, nu_i), 1, 2, 0);
+        rb.add(row, col_next(6 + c, nu_i), 1, 0, 0);
+      }
+      T.row_dyn = (int)rb.rows.size();
+      for (int r = 0; r < 6; ++r) {   // A v - m h
+        int row = rb.new_row();
+        rb.add(row, r, 1, 3, 0);
+        for (int c = 3; c < nv; ++c) rb.add(row, col_dq(c), 0, PLM_SRC_TQ, r * nv + c);
+        for (int c = 0; c < nv; ++c) rb.add(row, col_v(c, nu_i), 0, PLM_SRC_TV, r * nv + c);
+      }
+    } else {
+      for (int c = 0; c < nv; ++c) {  // dq_next - (dq + v dt)
+        int row = rb.new_row();
+        rb.add(row, col_dq(c), 1, 1, 0);
+        rb.add(row, col_v(c, nu_i), 1, 2, 0);
+        rb.add(row, col_next(c, nu_i), 1, 0, 0);
+      }
+      for (int c = 0; c < nv; ++c) {  // dv_next - (dv + a dt)
+        int row = rb.new_row();
+        if (kind == PLM_WHOLE_BODY_ABA) {
+          for (int d = 3; d < nv; ++d) rb.add(row, col_dq(d), 0, PLM_SRC_TQ, c * nv + d);
+          for (int d = 0; d < nv; ++d) rb.add(row, col_v(d, nu_i), 0, PLM_SRC_TV, c * nv + d);
+          for (int j = 0; j < nj; ++j) rb.add(row, col_lead(j), 0, PLM_SRC_TA, c * nv + j);
+          for (int k = 0; k < M.ncontact; ++k)
+            for (int tt = 0; tt < 3; ++tt) rb.add(row, col_f(k, tt), 0, PLM_SRC_TF, c * nf + 3 * k + tt);
+        } else {
+          rb.add(row, col_v(c, nu_i), 1, 1, 0);
+          rb.add(row, col_lead(c), 1, 2, 0);
+        }
+        rb.add(row, col_next(nv + c, nu_i), 1, 0, 0);
+      }
+      if (kind == PLM_WHOLE_BODY_RNEA || kind == PLM_WHOLE_BODY_ACC || kind == PLM_CENTROIDAL_ACC) {
+        T.row_dyn = (int)rb.rows.size();
+        const bool centroidal = kind == PLM_CENTROIDAL_ACC;
+        const int nrow_t = 6 + (jr ? nj : 0);
+        for (int r = 0; r < nrow_t; ++r) {
+          if (r == 6) T.row_tauj = (int)rb.rows.size();
+          int row = rb.new_row();
+          const int rbody = M.col_body[r];
+          for (int c = 0; c < nv; ++c) {
+            const int cbody = M.col_body[c];
+            const bool rel = is_anc_or_self(M, rbody, cbody) || is_anc_or_self(M, cbody, rbody);
+            if (!rel) continue;
+            if (q_cols_ok(c)) rb.add(row, col_dq(c), 0, PLM_SRC_TQ, r * nv + c);
+            rb.add(row, col_v(c, nu_i), 0, PLM_SRC_TV, r * nv + c);
+            rb.add(row, col_lead(c), 0, PLM_SRC_TA, r * nv + c);
+          }
+          for (int k = 0; k < M.ncontact; ++k) {
+            if (!is_anc_or_self(M, rbody, M.contact_body[k])) continue;
+            for (int tt = 0; tt < 3; ++tt)
+              if (!centroidal || r >= 3 || tt == r) rb.add(row, col_f(k, tt), 0, PLM_SRC_TF, r * nf + 3 * k + tt);
+          }
+          if (r >= 6) rb.add(row, col_tau(r - 6), 1, 1, 0);
+        }
+        if (jr) {
+          T.row_taub = (int)rb.rows.size();
+          for (int j = 0; j < nj; ++j) { int row = rb.new_row(); rb.add(row, col_tau(j), 1, 0, 0); }
+        }
+      }
+    }
+    // ---- 2. contact / swing rows per foot
+    for (int k = 0; k < nfeet; ++k) {
+      T.row_foot[k] = (int)rb.rows.size();
+      int row = rb.new_row(); rb.add(row, col_f(k, 2), 2, k, 0);                       // c f_z >= 0
+      row = rb.new_row(); for (int tt = 0; tt < 3; ++tt) rb.add(row, col_f(k, tt), 2, k, 1 + tt);   // cone
+      for (int tt = 0; tt < 3; ++tt) { row = rb.new_row(); rb.add(row, col_f(k, tt), 2, k, 4 + tt); }  // (1-c) f = 0
+      if (!skip) {
+        for (int r = 0; r < 3; ++r) {   // c v_xy = 0 ; c v_z + (1-c)(v_z - v_des) = 0
+          row = rb.new_row();
+          for (int c = 0; c < nv; ++c) {
+            if (!((M.col_contacts[c] >> k) & 1u)) continue;
+            if (q_cols_ok(c)) rb.add(row, col_dq(c), 0, PLM_SRC_FQ, (k * 3 + r) * nv + c);
+            rb.add(row, col_v(c, nu_i), 0, PLM_SRC_FV, (k * 3 + r) * nv + c);
+          }
+        }
+      }
+    }
+    // ---- 3. external force rows
+    if (M.has_ext) {
+      T.row_ext = (int)rb.rows.size();
+      for (int tt = 0; tt < 3; ++tt) { int row = rb.new_row(); rb.add(row, col_f(nfeet, tt), 1, 0, 0); }
+    }
+    // ---- 4. arm task and joint limits
+    if (!skip) {
+      if (M.arm_body >= 0) {
+        T.row_arm = (int)rb.rows.size();
+        for (int r = 0; r < 3; ++r) {
+          int row = rb.new_row();
+          for (int c = 0; c < nv; ++c) {
+            if (!((M.col_arm >> c) & 1u)) continue;
+            if (r < 2 && M.col_body[c] == 0) continue;
+            if (q_cols_ok(c)) rb.add(row, col_dq(c), 0, PLM_SRC_AQ, r * nv + c);
+            rb.add(row, col_v(c, nu_i), 0, PLM_SRC_AV, r * nv + c);
+          }
+        }
+      }
+      T.row_qj = (int)rb.rows.size();
+      for (int j = 0; j < nj; ++j) { int row = rb.new_row(); rb.add(row, col_dq(6 + j), 1, 0, 0); }
+      T.row_vj = (int)rb.rows.size();
+      for (int j = 0; j < nj; ++j) { int row = rb.new_row(); rb.add(row, col_v(6 + j, nu_i), 1, 0, 0); }
+    }
+    // ---- assign positions (row-major, columns ascending)
+    T.nrows = (int)rb.rows.size();
+    T.lut_off = (int)out.lut.size();
+    out.lut.resize(out.lut.size() + T.lut_size, (int16_t)-1);
+    T.const_off = (int)out.consts.size();
+    int16_t* lut = out.lut.data() + T.lut_off;
+    int pos = 0;
+    for (int k = 0; k < 4; ++k) T.pos_foot[k] = -1;
+    for (auto& row : rb.rows) {
+      std::stable_sort(row.begin(), row.end(), [](const Entry& a, const Entry& b) { return a.col < b.col; });
+      for (const Entry& e : row) {
+        if (e.kind == 0) lut[T.src_off[e.src] + e.idx] = (int16_t)pos;
+        else if (e.kind == 1) out.consts.push_back({pos, e.src, e.idx});
+        else if (e.idx == 0) T.pos_foot[e.src] = pos;
+        ++pos;
+      }
+    }
+    if (pos > 32000) { out.error = "node block too large for int16 lut"; return false; }
+    T.nnz = pos;
+    T.nconst = (int)out.consts.size() - T.const_off;
+    type_rows.push_back(rb.rows);
+  }
+  // constant codes 4/5 (contact-scaled) are not used by row groups above: foot force rows are direct entries.
+
+  // ---- global offsets and COO pattern
+  L.row_off[0] = ndx;
+  L.nnz_off[0] = ndx;
+  L.max_rows = L.max_nnz = 0;
+  for (int c = 0; c < ndx; ++c) { out.pat_rows.push_back(c); out.pat_cols.push_back(c); }   // DX_0 == 0
+  for (int i = 0; i < N; ++i) {
+    const PlmNodeType& T = L.types[L.node_type[i]];
+    L.row_off[i + 1] = L.row_off[i] + T.nrows;
+    L.nnz_off[i + 1] = L.nnz_off[i] + T.nnz;
+    L.max_rows = std::max(L.max_rows, T.nrows);
+    L.max_nnz = std::max(L.max_nnz, T.nnz);
+    const auto& rows = type_rows[L.node_type[i]];
+    for (size_t r = 0; r < rows.size(); ++r)
+      for (const Entry& e : rows[r]) {
+        out.pat_rows.push_back(L.row_off[i] + (int)r);
+        out.pat_cols.push_back(L.x_off[i] + e.col);
+      }
+  }
+  L.m = L.row_off[N];
+  L.nnz = L.nnz_off[N];
+  return true;
+}
+
+}  // namespace plm

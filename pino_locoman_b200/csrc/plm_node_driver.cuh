@@ -1,0 +1,75 @@
+// Phase sequencing of one node evaluation, shared by the CUDA kernel (one warp, phases separated by
+// __syncwarp) and by the host emulation used in the CPU tests (lanes of a phase run in a loop).
+#pragma once
+#include "plm_node.cuh"
+
+namespace plm {
+
+PLM_HD size_t aba_ws_doubles(int nv, int nf) { return (size_t)4 * 32 * nv + (size_t)nv * nf; }
+
+#if defined(__CUDACC__)
+struct WarpExec {
+  int lane;
+  LaneState st;
+  template <class F>
+  __device__ __forceinline__ void run(F f) {
+    f(lane, st);
+    __syncwarp();
+  }
+};
+#endif
+
+struct HostExec {
+  LaneState st[32];
+  template <class F>
+  void run(F f) {
+    for (int l = 0; l < 32; ++l) f(l, st[l]);
+  }
+};
+
+// Bytes of shared workspace one warp needs for a layout.
+PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf) {
+  size_t base = (sizeof(NodeWs) + 7) / 8;
+  size_t extra = (size_t)L.max_rows + (size_t)L.max_nnz;
+  if (L.dynamics == PLM_WHOLE_BODY_ABA) extra += aba_ws_doubles(nv, nf);
+  return base + extra + 2;
+}
+
+// ws.g / ws.J / aba scratch are carved from `tail` (doubles following the NodeWs struct).
+PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, double* tail) {
+  ws.g = tail;
+  ws.J = tail + L.max_rows;
+  ws.aba = tail + L.max_rows + L.max_nnz;
+}
+
+}  // namespace plm
+#include "plm_node_aba.cuh"
+namespace plm {
+
+template <int KIND, class Exec>
+PLM_HD void node_eval_body(Exec& ex, NodeWs& ws, const NodeArgs& A) {
+  const PlmModel& M = *A.M;
+  const PlmNodeType& T = *A.T;
+  if (A.want_jac) {
+    ex.run([&](int lane, LaneState&) {
+      for (int e = lane; e < T.nnz; e += 32) ws.J[e] = 0.0;
+      node_phase_a<KIND>(ws, A, lane);
+    });
+  } else {
+    ex.run([&](int lane, LaneState&) { node_phase_a<KIND>(ws, A, lane); });
+  }
+  ex.run([&](int lane, LaneState& st) { node_phase_b<KIND>(ws, A, st, lane); });
+  for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
+  if (KIND == PLM_WHOLE_BODY_ABA) {
+    aba_solve_and_derivatives<Exec>(ex, ws, A);
+  } else {
+    ex.run([&](int lane, LaneState& st) { node_phase_d<KIND>(ws, A, st, lane); });
+    ex.run([&](int lane, LaneState& st) { node_phase_e<KIND>(ws, A, st, lane); });
+  }
+  ex.run([&](int lane, LaneState& st) {
+    node_phase_f<KIND>(ws, A, st, lane);
+    if (A.want_jac) node_phase_consts(ws, A, lane, 32);
+  });
+}
+
+}  // namespace plm

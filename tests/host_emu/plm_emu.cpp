@@ -1,0 +1,80 @@
+// Host emulation of the node-evaluation kernel for CPU tests: the device code of
+// pino_locoman_b200/csrc/plm_node*.cuh compiled with g++, the 32 lanes of a warp run in a loop per phase.
+// TEST INFRASTRUCTURE: validates the kernel mathematics against the oracle without a GPU; it is not a product path
+// (the product library refuses to run without a CUDA device).
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../pino_locoman_b200/csrc/plm_host.h"
+#include "../../pino_locoman_b200/csrc/plm_node_driver.cuh"
+
+using namespace plm;
+
+struct Emu {
+  HostTables t;
+};
+
+template <int KIND>
+static void run_node(const HostTables& t, const double* x, const double* p, int b, int node, double* g, double* Jv, int want_jac) {
+  const PlmLayout& L = t.layout;
+  std::vector<double> buf(node_ws_doubles(L, t.model.nv, L.nf) + 8, 0.0);
+  NodeWs& ws = *reinterpret_cast<NodeWs*>(buf.data());
+  node_ws_bind(ws, L, buf.data() + (sizeof(NodeWs) + 7) / 8);
+  NodeArgs A;
+  A.M = &t.model;
+  A.L = &L;
+  A.T = &L.types[L.node_type[node]];
+  A.lut = t.lut.data() + A.T->lut_off;
+  A.consts = t.consts.data() + A.T->const_off;
+  A.xs = x + (size_t)b * L.n + L.x_off[node];
+  A.p = p + (size_t)b * L.np;
+  A.node = node;
+  A.dt = node_dt(L, A.p, node);
+  A.want_jac = want_jac;
+  HostExec ex;
+  memset(&ex, 0, sizeof(ex));
+  node_eval_body<KIND>(ex, ws, A);
+  const PlmNodeType& T = *A.T;
+  for (int r = 0; r < T.nrows; ++r) g[(size_t)b * L.m + L.row_off[node] + r] = ws.g[r];
+  if (node == 0) for (int r = 0; r < L.ndx; ++r) g[(size_t)b * L.m + r] = A.xs[r];
+  if (want_jac) {
+    for (int e = 0; e < T.nnz; ++e) Jv[(size_t)b * L.nnz + L.nnz_off[node] + e] = ws.J[e];
+    if (node == 0) for (int e = 0; e < L.ndx; ++e) Jv[(size_t)b * L.nnz + e] = 1.0;
+  }
+}
+
+extern "C" {
+
+Emu* emu_create(const plm_robot_desc* r, const plm_ocp_desc* o, char* err, int errlen) {
+  Emu* e = new Emu();
+  if (!build_tables(*r, *o, e->t)) {
+    strncpy(err, e->t.error.c_str(), errlen - 1);
+    delete e;
+    return nullptr;
+  }
+  return e;
+}
+void emu_destroy(Emu* e) { delete e; }
+void emu_dims(const Emu* e, int* out) {
+  const PlmLayout& L = e->t.layout;
+  int v[8] = {L.n, L.m, L.np, L.nnz, L.ndx, L.nx, L.nf, L.nodes};
+  memcpy(out, v, sizeof(v));
+}
+void emu_pattern(const Emu* e, int* rows, int* cols) {
+  memcpy(rows, e->t.pat_rows.data(), e->t.pat_rows.size() * sizeof(int));
+  memcpy(cols, e->t.pat_cols.data(), e->t.pat_cols.size() * sizeof(int));
+}
+void emu_node_eval(const Emu* e, const double* x, const double* p, int batch, double* g, double* Jv, int want_jac) {
+  const PlmLayout& L = e->t.layout;
+  for (int b = 0; b < batch; ++b)
+    for (int i = 0; i < L.nodes; ++i) switch (L.dynamics) {
+        case PLM_CENTROIDAL_VEL: run_node<PLM_CENTROIDAL_VEL>(e->t, x, p, b, i, g, Jv, want_jac); break;
+        case PLM_CENTROIDAL_ACC: run_node<PLM_CENTROIDAL_ACC>(e->t, x, p, b, i, g, Jv, want_jac); break;
+        case PLM_WHOLE_BODY_ACC: run_node<PLM_WHOLE_BODY_ACC>(e->t, x, p, b, i, g, Jv, want_jac); break;
+        case PLM_WHOLE_BODY_ABA: run_node<PLM_WHOLE_BODY_ABA>(e->t, x, p, b, i, g, Jv, want_jac); break;
+        default: run_node<PLM_WHOLE_BODY_RNEA>(e->t, x, p, b, i, g, Jv, want_jac); break;
+      }
+}
+}

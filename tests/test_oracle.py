@@ -1,0 +1,171 @@
+"""Oracle pinned against the reference's own gait code (golden vectors) and against algebraic identities."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rbd, spatial as sp
+from oracle.dynamics import DynamicsCentroidalAcc, DynamicsWholeBodyTorque
+from oracle.gait import GaitSequence, get_spline_vel_z, opti_dts
+from oracle.model import OracleRobot
+from oracle.ocp import OracleOCP
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gait_golden.json")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+def _check_schedules(gold, make_seq, make_dts):
+    for case in gold["schedules"]:
+        dts = make_dts(case["dt_min"], case["dt_max"], case["nodes"])
+        assert [float(d).hex() for d in dts] == case["dts"]
+        seq = make_seq(case["gait"], case["period"])
+        assert seq.n_contacts == case["n_contacts"] and float(seq.swing_period).hex() == case["swing_period"]
+        contact, swing = seq.get_gait_schedule(case["k"] * case["dt_min"], dts, case["nodes"])
+        assert contact.astype(int).tolist() == case["contact"]
+        assert [[float(s).hex() for s in row] for row in swing] == case["swing"]
+
+
+def test_oracle_gait_bit_exact_vs_reference(gold):
+    _check_schedules(gold, GaitSequence, opti_dts)
+
+
+def test_product_gait_bit_exact_vs_reference(gold):
+    from pino_locoman_b200.utils.gait_sequence import GaitSequence as G, horizon_dts
+    _check_schedules(gold, G, horizon_dts)
+    # batched start times give the same bits as one call per start time
+    seq = G("trot", 0.8)
+    dts = horizon_dts(0.01, 0.08, 20)
+    ks = np.arange(0, 80)
+    cb, sb = seq.get_gait_schedule(ks * 0.01, dts, 20)
+    for k in ks:
+        c1, s1 = seq.get_gait_schedule(k * 0.01, dts, 20)
+        assert np.array_equal(cb[k], c1) and np.array_equal(sb[k], s1)
+
+
+def test_spline_bit_exact_vs_reference(gold):
+    from pino_locoman_b200.utils.gait_sequence import get_spline_vel_z as prod_spline
+    for s in gold["splines"]:
+        args = (s["phase"], s["swing_period"], s["h_max"], s["v_liftoff"], s["v_touchdown"])
+        assert float(get_spline_vel_z(*args)).hex() == s["vel_z"]
+        assert float(prod_spline(*args)).hex() == s["vel_z"]
+
+
+def test_unknown_gait_raises():
+    from pino_locoman_b200.utils.gait_sequence import GaitSequence as G
+    with pytest.raises(ValueError):
+        GaitSequence("gallop", 0.5)
+    with pytest.raises(ValueError):
+        G("gallop", 0.5)
+
+
+@pytest.mark.parametrize("name,mass,root_mass,nq,nv,nf", [("go2", 16.087, 7.279, 19, 18, 12), ("b2", 72.5803, 39.4371, 19, 18, 12),
+                                                          ("b2g", 77.26826983, 40.210575, 25, 24, 15)])
+def test_model_constants(name, mass, root_mass, nq, nv, nf):
+    """Published constants of SURVEY.md 2.4 (total / merged root mass, dims, joint order)."""
+    r = OracleRobot(name)
+    m = r.model
+    assert (m.nq, m.nv, r.nf) == (nq, nv, nf)
+    assert abs(m.total_mass - mass) < 1e-6 and abs(m.mass[1] - root_mass) < 1e-6
+    legs = [f"{l}_{j}_joint" for l in ("FL", "FR", "RL", "RR") for j in ("hip", "thigh", "calf")]
+    arm = [f"joint{i}" for i in range(1, 7)] if name == "b2g" else []
+    assert m.names[2:] == legs + arm
+    assert [m.frames[f].name for f in r.foot_frames] == ["FR_foot", "FL_foot", "RR_foot", "RL_foot"]
+
+
+def test_product_loader_matches_oracle_model(robots):
+    prod, ora = robots
+    for name in prod:
+        t, m = prod[name].tables(), ora[name].model
+        ine = np.array([[m.mass[i], *m.com[i], m.Ic[i][0, 0], m.Ic[i][0, 1], m.Ic[i][0, 2], m.Ic[i][1, 1], m.Ic[i][1, 2],
+                         m.Ic[i][2, 2]] for i in range(1, m.njoints)])
+        assert np.abs(ine - t["inertia"]).max() < 1e-12
+        assert np.array_equal(t["parent"][1:], np.array(m.parents[2:]) - 1)
+        assert np.abs(prod[name].q0 - ora[name].q0).max() == 0
+
+
+def _random_state(r, rng):
+    m = r.model
+    q = r.q0.copy()
+    q[7:] += rng.normal(0, 0.3, m.nq - 7)
+    quat = rng.normal(size=4)
+    q[3:7] = quat / np.linalg.norm(quat)
+    q[:3] = rng.normal(size=3)
+    return q, rng.normal(size=m.nv), rng.normal(size=m.nv), rng.normal(size=r.nf) * 20
+
+
+@pytest.mark.parametrize("name", ["go2", "b2g"])
+def test_rigid_body_identities(name):
+    """EOM identity of run_ocp.py:106-161, ABA o RNEA = id, centroidal identities, integrate/difference."""
+    r = OracleRobot(name)
+    m = r.model
+    rng = np.random.default_rng(3)
+    q, v, a, f = _random_state(r, rng)
+    dyn = DynamicsWholeBodyTorque(m, r.mass, r.foot_frames)
+    ee = dyn._ee(r.ext_force_frame)
+    kin = rbd.Kin(m, q)
+    tau = dyn.rnea_dynamics(r.ext_force_frame)(q, v, a, f)
+    fext = rbd.local_ext_forces(m, kin, ee, f)
+    assert np.abs(rbd.aba(m, kin, v, tau, fext) - a).max() < 1e-10
+    z = np.zeros(m.nv)
+    nle = rbd.rnea(m, kin, v, z, {})
+    M = np.stack([rbd.rnea(m, kin, z, e, {}) - rbd.rnea(m, kin, z, z, {}) for e in np.eye(m.nv)], -1)
+    tau_ext = sum(np.stack([dyn.get_frame_velocity(fid)(q, e)[:3] for e in np.eye(m.nv)], -1).T @ f[3 * i:3 * i + 3]
+                  for i, fid in enumerate(ee))
+    assert np.abs(M @ a + nle - tau_ext - tau).max() < 1e-9
+    assert np.abs(M - M.T).max() < 1e-10
+    A = rbd.centroidal_map(m, kin)
+    assert np.abs(A[:3, :3] / r.mass - kin.oR[1]).max() < 1e-12
+    assert np.abs(A @ v - rbd.centroidal_momentum(m, kin, v)).max() < 1e-10
+    gaps = DynamicsCentroidalAcc(m, r.mass, r.foot_frames).dynamics_gaps(r.ext_force_frame)(q, v, a, f)
+    com = rbd.center_of_mass(m, kin)
+    fw = sp.act_force(kin.oR[1], kin.op[1], tau[:6])
+    assert np.abs(gaps - np.concatenate([fw[:3], fw[3:] - np.cross(com, fw[:3])])).max() < 1e-9
+    x0 = np.concatenate([q, v])
+    dx = rng.normal(size=2 * m.nv) * 0.3
+    x1 = dyn.state_integrate()(x0, dx)
+    assert np.abs(dyn.state_difference()(x0, x1) - dx).max() < 1e-12
+    # d/dt (A v) along the motion
+    eps = 1e-6
+
+    def h(t):
+        qq = rbd.integrate(m, q, v * t + 0.5 * a * t * t)
+        return rbd.centroidal_momentum(m, rbd.Kin(m, qq), v + a * t)
+    assert np.abs((h(eps) - h(-eps)) / (2 * eps) - rbd.centroidal_momentum_rate(m, kin, v, a)).max() < 1e-5
+
+
+@pytest.mark.parametrize("rn,kind,n,m,np_", [("go2", "centroidal_vel", 1104, 1744, 258), ("b2", "whole_body_rnea", 1392, 2032, 318),
+                                              ("b2g", "whole_body_aba", 1668, 2437, 309), ("b2", "centroidal_acc", 1356, 1960, 282),
+                                              ("b2g", "whole_body_rnea", 1842, 2665, 369)])
+def test_problem_sizes(robots, rn, kind, n, m, np_):
+    """(n, m, np) of SURVEY.md 8(a) row 13 / row 15 at N=20."""
+    o = OracleOCP(robots[1][rn], kind, 20)
+    assert (o.n, o.m, o.np_) == (n, m, np_)
+
+
+def test_unknown_dynamics_raises(robots):
+    with pytest.raises(ValueError):
+        OracleOCP(robots[1]["b2"], "whole_body_foo", 5)
+
+
+def test_oracle_jacobian_vs_finite_differences(robots):
+    from emu_util import random_problem
+    rng = np.random.default_rng(7)
+    o = OracleOCP(robots[1]["b2g"], "whole_body_rnea", 4)
+    x, p = random_problem(o, rng)
+    J = o.jac_g(x, p)
+    d = rng.normal(size=x.size)
+    eps = 1e-6
+    gp, _, _ = o.g_data(x + eps * d, p)
+    gm, _, _ = o.g_data(x - eps * d, p)
+    assert np.abs((gp - gm) / (2 * eps) - J @ d).max() < 1e-6 * np.abs(J @ d).max()
+    f0, grad = o.f_data(x, p)
+    fp, _ = o.f_data(x + eps * d, p)
+    fm, _ = o.f_data(x - eps * d, p)
+    assert abs((fp - fm) / (2 * eps) - grad @ d) < 1e-6 * abs(grad @ d)
+    assert np.allclose(np.diag(np.diag(o.hess_diag(p))) @ d * 0 + o.hess_diag(p) * d, (o.f_data(x + d, p)[1] - grad), rtol=1e-9, atol=1e-6)
