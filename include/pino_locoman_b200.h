@@ -129,8 +129,10 @@ int plm_frame_vel(plm_handle* h, int32_t contact, int32_t relative_to_base, cons
                   int32_t batch, double* d_vel, void* stream);
 
 /* ---- OSQP equivalents (optimization/ocp.py:312-313,395,401) -------------------------------------- */
-/* Reset the persistent ADMM iterates (x, z, y) of the first `batch` instances to zero (osqp setup state). */
-int plm_qp_reset(plm_handle* h, int32_t batch, void* stream);
+/* setup(P, q=1, A=ones(pattern), l=-1, u=1) of optimization/ocp.py:305-313: zero the persistent ADMM iterates
+ * (x, z, y) of the first `batch` instances and record the setup-time row scaling that osqp still has in force
+ * when the first update() classifies the constraint rows.  d_hess is the diagonal P [batch][n]. */
+int plm_qp_setup(plm_handle* h, int32_t batch, const double* d_hess, void* stream);
 /* update(q=, Ax=, l=, u=): scale (Ruiz), classify rows, build and factor the per-instance stage-structured system.
  * d_hess is the diagonal P. */
 int plm_qp_update(plm_handle* h, int32_t batch, const double* d_hess, const double* d_q, const double* d_J,
@@ -140,6 +142,8 @@ int plm_qp_solve(plm_handle* h, int32_t batch, double* d_dx, int32_t* d_iters, i
 /* Read / write the persistent scaled iterates: x [batch][n], z [batch][m], y [batch][m]. */
 int plm_qp_get_iterates(plm_handle* h, int32_t batch, double* d_x, double* d_z, double* d_y, void* stream);
 int plm_qp_set_iterates(plm_handle* h, int32_t batch, const double* d_x, const double* d_z, const double* d_y, void* stream);
+/* Scaling of the last plm_qp_update: D [batch][n], E [batch][m], c [batch] (diagnostics / tests). */
+int plm_qp_get_scaling(plm_handle* h, int32_t batch, double* d_D, double* d_E, double* d_c, void* stream);
 
 /* ---- Armijo line search (optimization/ocp.py:430-480) --------------------------------------------- */
 /* d_info: [batch][4] = accepted (0/1), accepted step size, trials used, constraint-violation metric of the result */

@@ -54,11 +54,12 @@ SIGNATURES = {
     "plm_centroidal_vel_gaps": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int32, vp, vp]),
     "plm_com_dyn": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, vp, vp]),
     "plm_frame_vel": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp]),
-    "plm_qp_reset": (ctypes.c_int, [vp, ctypes.c_int32, vp]),
+    "plm_qp_setup": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp]),
     "plm_qp_update": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp, vp, vp]),
     "plm_qp_solve": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp]),
     "plm_qp_get_iterates": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp]),
     "plm_qp_set_iterates": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp]),
+    "plm_qp_get_scaling": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp]),
     "plm_line_search": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int32, vp, vp, vp]),
     "plm_sqp_step": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, vp, vp, vp]),
     "plm_last_phase_ms": (ctypes.c_int, [vp, c_double_p]),

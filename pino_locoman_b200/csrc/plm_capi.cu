@@ -76,7 +76,20 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
   h->tgt_ld = L.ndx + L.types[L.node_type[0]].nu;
   PLM_CHECK_CUDA(h, cudaMalloc(&h->d_tgt, (size_t)max_batch * h->tgt_ld * sizeof(double)));
   h->node_ws_doubles = (int)node_ws_doubles(L, h->host.model.nv, L.nf);
-  h->node_smem = ((sizeof(PlmModel) + 7) / 8 + (sizeof(PlmLayout) + 7) / 8 + (size_t)PLM_NODE_WARPS * h->node_ws_doubles) * 8;
+  {
+    const size_t tables = ((sizeof(PlmModel) + 7) / 8 + (sizeof(PlmLayout) + 7) / 8) * 8;
+    const size_t per_warp = (size_t)h->node_ws_doubles * 8, cap = 227 * 1024;
+    int best_w = 0, best = 0;
+    for (int w = 1; w <= PLM_NODE_WARPS; ++w) {
+      const size_t need = tables + w * per_warp + 1024;   // + per-CTA reservation
+      if (need > cap) break;
+      const int resident = (int)(cap / need) * w;
+      if (resident >= best) { best = resident; best_w = w; }
+    }
+    if (best_w == 0) { h->error = "node workspace exceeds shared memory"; return 6; }
+    h->node_warps = best_w;
+    h->node_smem = tables + best_w * per_warp;
+  }
   int rc = plm_setup_node_kernels(h);
   if (rc) return rc;
   rc = plm_qp_alloc(h);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/pino_locoman_b200.h"
 #include "plm_host.h"
@@ -22,11 +23,14 @@ struct plm_handle {
   double* d_tgt = nullptr;   // [max_batch][tgt_ld] dx_des | u_des
   int tgt_ld = 0;
   int node_ws_doubles = 0;
+  int node_warps = PLM_NODE_WARPS;   // warps (= node evaluations) per CTA, chosen to maximise resident warps per SM
   size_t node_smem = 0;
   long long launches = 0;
   // QP workspaces (plm_qp.cu)
   plm::QpWork qp;
   int qp_factor_doubles = 0;
+  int* d_qp_fail = nullptr;   // [max_batch] stage index (+1) of a non-positive Cholesky pivot, 0 = ok
+  size_t smem_scale = 0, smem_factor = 0, smem_admm = 0;
   // SQP step workspaces / timing
   double* d_sqp = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -40,6 +44,9 @@ int plm_launch_objective(plm_handle* h, const double* x, const double* dx, const
                          int batch, double* f, double* grad, cudaStream_t s);
 int plm_launch_hess_diag(plm_handle* h, const double* p, int batch, double* hess, cudaStream_t s);
 int plm_qp_alloc(plm_handle* h);
+int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream_t s);
+int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J, const double* d_l, const double* d_u, cudaStream_t s);
+int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int* d_status, cudaStream_t s);
 void plm_qp_free(plm_handle* h);
 
 #define PLM_LAUNCH_CHECK(h)                                                    \

@@ -320,6 +320,11 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     T.nnz = pos;
     T.nconst = (int)out.consts.size() - T.const_off;
     type_rows.push_back(rb.rows);
+    {
+      std::vector<std::vector<int>> rc;
+      for (auto& row : rb.rows) { std::vector<int> cols; for (const Entry& e : row) cols.push_back(e.col); rc.push_back(cols); }
+      out.type_rowcols.push_back(rc);
+    }
   }
   // constant codes 4/5 (contact-scaled) are not used by row groups above: foot force rows are direct entries.
 
@@ -343,6 +348,52 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   }
   L.m = L.row_off[N];
   L.nnz = L.nnz_off[N];
+
+  // ---- QP solver tables: per-type CSR/CSC of the node blocks, factor offsets, OSQP settings
+  QpLayout& Q = out.qp;
+  memset(&Q, 0, sizeof(Q));
+  auto push = [&](const std::vector<int>& v) {
+    int o = (int)out.qp_idx.size();
+    for (int x : v) out.qp_idx.push_back((int16_t)x);
+    return o;
+  };
+  for (int t = 0; t < L.ntypes; ++t) {
+    const auto& rows = out.type_rowcols[t];
+    const int s = ndx + L.types[t].nu, ncols = s + ndx;
+    std::vector<int> rptr(1, 0), ccol;
+    for (const auto& r : rows) { for (int c : r) ccol.push_back(c); rptr.push_back((int)ccol.size()); }
+    std::vector<int> cptr(ncols + 1, 0), cpos(ccol.size()), crow(ccol.size());
+    for (int c : ccol) cptr[c + 1]++;
+    for (int c = 0; c < ncols; ++c) cptr[c + 1] += cptr[c];
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (size_t r = 0; r < rows.size(); ++r)
+      for (int e = rptr[r]; e < rptr[r + 1]; ++e) { int c = ccol[e]; cpos[fill[c]] = e; crow[fill[c]] = (int)r; fill[c]++; }
+    QpTypeIdx& I = Q.type[t];
+    I.rptr = push(rptr); I.ccol = push(ccol); I.cptr = push(cptr); I.cpos = push(cpos); I.crow = push(crow);
+    I.ncols = ncols; I.s = s;
+    // structural assumptions of the stage solver: the first ndx rows are the integrator rows, each with
+    // exactly one entry in DX_{i+1} (its last entry, at next-column r); no other row touches DX_{i+1}
+    for (size_t r = 0; r < rows.size(); ++r) {
+      int nnext = 0;
+      for (int c : rows[r]) if (c >= s) nnext++;
+      const bool integ = (int)r < ndx;
+      if (integ ? (nnext != 1 || rows[r].back() != s + (int)r) : nnext != 0) { out.error = "unexpected stage coupling pattern"; return false; }
+    }
+  }
+  Q.smax = 0;
+  int fo = 0;
+  for (int i = 0; i <= N; ++i) {
+    const int s = (i < N) ? ndx + nu[i] : ndx;
+    Q.fac_off[i] = fo;
+    fo += s * (s + 1) / 2;
+    Q.smax = std::max(Q.smax, s);
+  }
+  Q.fac_off[N + 1] = fo;
+  Q.fac_total = fo;
+  Q.max_iter = ocp.osqp_max_iter; Q.check_termination = ocp.osqp_check_termination; Q.scaling = ocp.osqp_scaling;
+  Q.rho = ocp.osqp_rho; Q.sigma = ocp.osqp_sigma; Q.alpha = ocp.osqp_alpha;
+  Q.eps_abs = ocp.osqp_eps_abs; Q.eps_rel = ocp.osqp_eps_rel;
+  Q.eps_prim_inf = ocp.osqp_eps_prim_inf; Q.eps_dual_inf = ocp.osqp_eps_dual_inf;
   return true;
 }
 

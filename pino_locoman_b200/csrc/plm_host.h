@@ -8,6 +8,7 @@
 
 #include "../../include/pino_locoman_b200.h"
 #include "plm_types.h"
+#include "plm_qp_types.h"
 
 namespace plm {
 
@@ -17,6 +18,9 @@ struct HostTables {
   std::vector<int16_t> lut;             // pool of per-type luts
   std::vector<PlmConstEntry> consts;    // pool of per-type constant entries
   std::vector<int32_t> pat_rows, pat_cols;   // COO pattern of J_g in value order
+  std::vector<std::vector<std::vector<int>>> type_rowcols;   // [type][row] -> local columns (ascending)
+  QpLayout qp;                          // QP solver layout
+  std::vector<int16_t> qp_idx;          // pool of the per-type CSR/CSC index tables
   std::string error;
 };
 

@@ -27,7 +27,7 @@ node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* _
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const PlmLayout& L = *sL;
-  const long long item = (long long)blockIdx.x * PLM_NODE_WARPS + warp;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (item >= (long long)batch * L.nodes) return;
   const int b = (int)(item / L.nodes), node = (int)(item % L.nodes);
   NodeWs& ws = *reinterpret_cast<NodeWs*>(wsbase + (size_t)warp * ws_doubles);

@@ -25,8 +25,8 @@ int plm_setup_node_kernels(plm_handle* h) {
 int plm_launch_node_eval(plm_handle* h, const double* x, const double* p, int batch, double* g, double* J, int want_jac, cudaStream_t s) {
   const PlmLayout& L = h->host.layout;
   const long long items = (long long)batch * L.nodes;
-  const int blocks = (int)((items + PLM_NODE_WARPS - 1) / PLM_NODE_WARPS);
-  const dim3 grid(blocks), block(PLM_NODE_WARPS * 32);
+  const int blocks = (int)((items + h->node_warps - 1) / h->node_warps);
+  const dim3 grid(blocks), block(h->node_warps * 32);
   switch (L.dynamics) {
     case PLM_CENTROIDAL_VEL: node_eval_kernel<PLM_CENTROIDAL_VEL><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles); break;
     case PLM_CENTROIDAL_ACC: node_eval_kernel<PLM_CENTROIDAL_ACC><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles); break;

@@ -1,4 +1,813 @@
-// Batched OSQP-style QP solver (placeholder until the ADMM kernels land).
+// Batched OSQP-style ADMM QP solver: one CTA per MPC instance.
+//
+// Replaces osqp.OSQP.setup / update / solve as called at optimization/ocp.py:312-313, :395, :401
+// (third-party osqp 0.6.x semantics restated in SURVEY.md appendix A.8):
+//   qp_scale_kernel   Ruiz equilibration (scale_data), cost scaling, rho_vec classification
+//   qp_factor_kernel  reduced KKT  H = P + sigma I + A^T diag(rho) A  is block tridiagonal over the shooting
+//                     stages (only the integrator rows couple stage i with DX_{i+1}); block Cholesky, the inverse
+//                     of every stage factor is stored packed (Linv_i), so the ADMM sweeps are plain mat-vecs
+//   qp_admm_kernel    x~ = H^-1 (sigma x - q + A^T(rho z - y)), z~ = A x~, relaxation, projection on [l,u],
+//                     dual update, termination tests every check_termination iterations (unscaled residuals,
+//                     primal / dual infeasibility certificates), persistent warm-started iterates.
+#include <math.h>
+
 #include "plm_handle.cuh"
-int plm_qp_alloc(plm_handle* h) { (void)h; return 0; }
-void plm_qp_free(plm_handle* h) { (void)h; }
+
+using namespace plm;
+
+#define OSQP_INFTY 1e30
+#define MIN_SCALING 1e-4
+#define MAX_SCALING 1e4
+#define RHO_MIN 1e-6
+#define RHO_TOL 1e-4
+#define RHO_EQ_OVER_RHO_INEQ 1e3
+#define QP_THREADS 256
+
+__device__ __forceinline__ double limit_scaling(double v) {
+  v = v < MIN_SCALING ? 1.0 : v;
+  return v > MAX_SCALING ? MAX_SCALING : v;
+}
+
+// deterministic block reductions (fixed tree)
+__device__ __forceinline__ double block_reduce(double v, double* red, bool is_max) {
+  for (int o = 16; o > 0; o >>= 1) {
+    double t = __shfl_down_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, t) : v + t;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = is_max ? fmax(r, red[w]) : r + red[w];
+  __syncthreads();
+  return r;
+}
+
+struct StageView {
+  const int16_t *rptr, *ccol, *cptr, *cpos, *crow;
+  int nrows, ncols, s;
+};
+
+__device__ __forceinline__ StageView stage_view(const PlmLayout& L, const QpLayout& Q, const int16_t* idx, int node) {
+  const int t = L.node_type[node];
+  const QpTypeIdx& I = Q.type[t];
+  StageView v;
+  v.rptr = idx + I.rptr; v.ccol = idx + I.ccol; v.cptr = idx + I.cptr; v.cpos = idx + I.cpos; v.crow = idx + I.crow;
+  v.nrows = L.types[t].nrows; v.ncols = I.ncols; v.s = I.s;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Scaling.  mode 0: data update (A = J values, q, l, u given).  mode 1: setup-time scaling with the dummy data of
+// optimization/ocp.py:305-310 (A = ones on the pattern, q = 1, l = -1, u = 1); only E is kept (as Eprev).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(QP_THREADS)
+qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, int mode,
+                const double* __restrict__ hess, const double* __restrict__ qin, const double* __restrict__ Jv,
+                const double* __restrict__ lin, const double* __restrict__ uin, QpWork W) {
+  extern __shared__ double sm[];
+  const PlmLayout& L = *tab.layout;
+  const QpLayout& Q = *Qp;
+  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes;
+  double* D = sm;            // [n]
+  double* E = D + n;         // [m]
+  double* Dt = E + m;        // [n]
+  double* Et = Dt + n;       // [m]
+  double* red = Et + m;      // [32]
+  const double* P = hess + (size_t)b * n;
+  const double* A = Jv ? Jv + (size_t)b * L.nnz : nullptr;
+  const double* q = qin ? qin + (size_t)b * n : nullptr;
+  for (int j = tid; j < n; j += nth) D[j] = 1.0;
+  for (int r = tid; r < m; r += nth) E[r] = 1.0;
+  double c = 1.0;
+  __syncthreads();
+  for (int pass = 0; pass < Q.scaling; ++pass) {
+    // row norms of the current scaled A: E_r * max_k |A_rk| D_col
+    for (int r = tid; r < m; r += nth) {
+      double v = 0.0;
+      if (r < ndx) v = ((A ? fabs(A[r]) : 1.0)) * D[r];
+      else {
+        // locate node by linear scan over row offsets (N <= 64)
+        int node = 0;
+        while (node + 1 < N && r >= L.row_off[node + 1]) ++node;
+        const StageView sv = stage_view(L, Q, idx, node);
+        const int lr = r - L.row_off[node];
+        const double* An = A ? A + L.nnz_off[node] : nullptr;
+        const int xo = L.x_off[node];
+        for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) v = fmax(v, (An ? fabs(An[e]) : 1.0) * D[xo + sv.ccol[e]]);
+      }
+      Et[r] = 1.0 / sqrt(limit_scaling(E[r] * v));
+    }
+    // column norms: max(|P^_jj|, D_j * max_r E_r |A_rj|)
+    for (int j = tid; j < n; j += nth) {
+      int node = 0;
+      while (node < N && j >= L.x_off[node + 1]) ++node;     // node == N: terminal DX block
+      double v = 0.0;
+      const int lc = j - L.x_off[node];
+      if (node < N) {
+        const StageView sv = stage_view(L, Q, idx, node);
+        const double* An = A ? A + L.nnz_off[node] : nullptr;
+        const int ro = L.row_off[node];
+        for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) v = fmax(v, (An ? fabs(An[sv.cpos[e]]) : 1.0) * E[ro + sv.crow[e]]);
+      }
+      if (lc < ndx) {
+        if (node == 0) v = fmax(v, (A ? fabs(A[lc]) : 1.0) * E[lc]);      // DX_0 == 0 rows
+        else {
+          const StageView sp = stage_view(L, Q, idx, node - 1);
+          const double* Ap = A ? A + L.nnz_off[node - 1] : nullptr;
+          const int ro = L.row_off[node - 1];
+          const int pc = sp.s + lc;
+          for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) v = fmax(v, (Ap ? fabs(Ap[sp.cpos[e]]) : 1.0) * E[ro + sp.crow[e]]);
+        }
+      }
+      v = fmax(D[j] * v, c * D[j] * D[j] * fabs(P[j]));
+      Dt[j] = 1.0 / sqrt(limit_scaling(v));
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += nth) D[j] *= Dt[j];
+    for (int r = tid; r < m; r += nth) E[r] *= Et[r];
+    __syncthreads();
+    // cost scaling: c_temp = 1 / limit(max(mean_j |P^_jj|, limit(||q^||_inf)))
+    double sp_ = 0.0, mq = 0.0;
+    for (int j = tid; j < n; j += nth) {
+      sp_ += c * D[j] * D[j] * fabs(P[j]);
+      mq = fmax(mq, fabs(c * D[j] * (q ? q[j] : 1.0)));
+    }
+    const double psum = block_reduce(sp_, red, false);
+    const double qmax = block_reduce(mq, red, true);
+    const double ct = 1.0 / limit_scaling(fmax(psum / (double)n, limit_scaling(qmax)));
+    c *= ct;
+  }
+  if (mode == 1) {
+    for (int r = tid; r < m; r += nth) W.Eprev[(size_t)b * m + r] = E[r];
+    return;
+  }
+  // scaled data
+  double* Ah = W.Ahat + (size_t)b * L.nnz;
+  for (int e = tid; e < ndx; e += nth) Ah[e] = E[e] * A[e] * D[e];
+  for (int node = 0; node < N; ++node) {
+    const StageView sv = stage_view(L, Q, idx, node);
+    const int ro = L.row_off[node], xo = L.x_off[node], no = L.nnz_off[node];
+    for (int lr = tid; lr < sv.nrows; lr += nth)
+      for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) Ah[no + e] = E[ro + lr] * A[no + e] * D[xo + sv.ccol[e]];
+  }
+  for (int j = tid; j < n; j += nth) {
+    W.D[(size_t)b * n + j] = D[j];
+    W.Ph[(size_t)b * n + j] = c * D[j] * D[j] * P[j];
+    W.qh[(size_t)b * n + j] = c * D[j] * q[j];
+  }
+  if (tid == 0) W.cscale[b] = c;
+  const double* l = lin + (size_t)b * m;
+  const double* u = uin + (size_t)b * m;
+  for (int r = tid; r < m; r += nth) {
+    const double lc = fmax(l[r], -OSQP_INFTY), uc = fmin(u[r], OSQP_INFTY);
+    // osqp_update_bounds runs before osqp_update_A: rows are classified with the previous row scaling
+    const double ep = W.Eprev[(size_t)b * m + r];
+    const double lp = ep * lc, up = ep * uc;
+    double rho;
+    if (lp < -OSQP_INFTY * MIN_SCALING && up > OSQP_INFTY * MIN_SCALING) rho = RHO_MIN;
+    else if (up - lp < RHO_TOL) rho = RHO_EQ_OVER_RHO_INEQ * Q.rho;
+    else rho = Q.rho;
+    W.rho[(size_t)b * m + r] = rho;
+    W.lh[(size_t)b * m + r] = E[r] * lc;
+    W.uh[(size_t)b * m + r] = E[r] * uc;
+    W.E[(size_t)b * m + r] = E[r];
+    W.Eprev[(size_t)b * m + r] = E[r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Factorisation.  Packed lower-triangular storage: element (i, j <= i) at i(i+1)/2 + j.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+__global__ void __launch_bounds__(QP_THREADS)
+qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, QpWork W, int* __restrict__ fail) {
+  extern __shared__ double sm[];
+  const PlmLayout& L = *tab.layout;
+  const QpLayout& Q = *Qp;
+  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
+  const int tsz = smax * (smax + 1) / 2;
+  double* H = sm;                      // [tsz]  stage block -> Cholesky factor (packed lower)
+  double* Li = H + tsz;                // [tsz]  inverse of the factor (packed lower)
+  double* Wm = Li + tsz;               // [smax][ndx]  W = Linv G^T
+  double* K = Wm + smax * ndx;         // [ndx][ndx]   Schur term for the next stage
+  double* gsc = K + ndx * ndx;         // [ndx]  rho_r * (next entry) of the integrator rows
+  const double* Ah = W.Ahat + (size_t)b * L.nnz;
+  const double* Ph = W.Ph + (size_t)b * n;
+  const double* rho = W.rho + (size_t)b * m;
+  double* Lout = W.Linv + (size_t)b * Q.fac_total;
+
+  for (int i = 0; i <= N; ++i) {
+    const bool last = (i == N);
+    StageView sv;
+    if (!last) sv = stage_view(L, Q, idx, i);
+    const int s = last ? ndx : sv.s;
+    const int xo = L.x_off[i];
+    const double* An = last ? nullptr : Ah + L.nnz_off[i];
+    const double* rh = last ? nullptr : rho + L.row_off[i];
+    // ---- H_ii (lower triangle): thread j owns row j
+    for (int j = tid; j < s; j += nth) {
+      double* Hj = H + tri(j, 0);
+      for (int k = 0; k <= j; ++k) Hj[k] = 0.0;
+      Hj[j] = Ph[xo + j] + Q.sigma;
+      if (j < ndx) {
+        if (i == 0) Hj[j] += rho[j] * Ah[j] * Ah[j];           // DX_0 == 0 rows
+        else {
+          for (int k = 0; k <= j; ++k) Hj[k] -= K[j * ndx + k];  // Schur complement of stage i-1
+          Hj[j] += gsc[j];                                       // rho_r n_r^2 of the integrator row feeding DX_i[j]
+        }
+      }
+      if (!last) {
+        for (int e = sv.cptr[j]; e < sv.cptr[j + 1]; ++e) {
+          const int r = sv.crow[e];
+          const double w = rh[r] * An[sv.cpos[e]];
+          for (int e2 = sv.rptr[r]; e2 < sv.rptr[r + 1]; ++e2) {
+            const int k = sv.ccol[e2];
+            if (k <= j) Hj[k] += w * An[e2];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- in-place Cholesky (right-looking)
+    for (int k = 0; k < s; ++k) {
+      const double piv = H[tri(k, k)];
+      if (!(piv > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
+      const double d = sqrt(piv > 0.0 ? piv : 1.0);
+      __syncthreads();
+      for (int r = k + tid; r < s; r += nth) H[tri(r, k)] = (r == k) ? d : H[tri(r, k)] / d;
+      __syncthreads();
+      // trailing update: rows k+1.., 8 column lanes per row
+      const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
+      for (int r = k + 1 + slot; r < s; r += nslot) {
+        const double lrk = H[tri(r, k)];
+        double* Hr = H + tri(r, 0);
+        for (int c2 = k + 1 + lane8; c2 <= r; c2 += 8) Hr[c2] -= lrk * H[tri(c2, k)];
+      }
+      __syncthreads();
+    }
+    // ---- Linv: column j by forward substitution (thread per column)
+    for (int j = tid; j < s; j += nth) {
+      for (int r = j; r < s; ++r) {
+        double acc = (r == j) ? 1.0 : 0.0;
+        const double* Hr = H + tri(r, 0);
+        for (int k = j; k < r; ++k) acc -= Hr[k] * Li[tri(k, j)];
+        Li[tri(r, j)] = acc / Hr[r];
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < s * (s + 1) / 2; e += nth) Lout[Q.fac_off[i] + e] = Li[e];
+    if (last) break;
+    // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = Linv G^T ; K = W^T W
+    for (int c2 = tid; c2 < ndx; c2 += nth) {
+      const int elast = sv.rptr[c2 + 1] - 1;              // next entry of integrator row c2
+      const double nn = An[elast];
+      gsc[c2] = rh[c2] * nn * nn;
+    }
+    for (int o = tid; o < s * ndx; o += nth) {
+      const int t = o / ndx, c2 = o % ndx;
+      const int e0 = sv.rptr[c2], e1 = sv.rptr[c2 + 1] - 1;
+      const double g = rh[c2] * An[e1];
+      double acc = 0.0;
+      const double* Lt = Li + tri(t, 0);
+      for (int e = e0; e < e1; ++e) {
+        const int k = sv.ccol[e];
+        if (k <= t) acc += An[e] * Lt[k];
+      }
+      Wm[o] = g * acc;
+    }
+    __syncthreads();
+    for (int o = tid; o < ndx * ndx; o += nth) {
+      const int r = o / ndx, c2 = o % ndx;
+      if (c2 > r) continue;
+      double acc = 0.0;
+      for (int t = 0; t < s; ++t) acc += Wm[t * ndx + r] * Wm[t * ndx + c2];
+      K[o] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ADMM iterations.
+// ------------------------------------------------------------------------------------------------------------
+struct AdmmVec {
+  double *x, *z, *y, *xt, *w, *t, *yv;   // shared-memory vectors
+};
+
+// out[r] = sum_k A_rk v[col]  for all rows (CSR), v indexed by global column
+__device__ void spmv_rows(const PlmLayout& L, const QpLayout& Q, const int16_t* idx, const double* Ah, const double* v, double* out) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int r = tid; r < L.ndx; r += nth) out[r] = Ah[r] * v[r];
+  for (int node = 0; node < L.nodes; ++node) {
+    const StageView sv = stage_view(L, Q, idx, node);
+    const double* An = Ah + L.nnz_off[node];
+    const double* vn = v + L.x_off[node];
+    double* on = out + L.row_off[node];
+    for (int lr = tid; lr < sv.nrows; lr += nth) {
+      double acc = 0.0;
+      for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) acc += An[e] * vn[sv.ccol[e]];
+      on[lr] = acc;
+    }
+  }
+}
+
+// out[j] = sum_r A_rj w[r]  for all columns (CSC gather)
+__device__ void spmv_cols(const PlmLayout& L, const QpLayout& Q, const int16_t* idx, const double* Ah, const double* w, double* out) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int N = L.nodes, ndx = L.ndx;
+  for (int node = 0; node <= N; ++node) {
+    const int s = (node < N) ? Q.type[L.node_type[node]].s : ndx;
+    const int xo = L.x_off[node];
+    for (int lc = tid; lc < s; lc += nth) {
+      double acc = 0.0;
+      if (node < N) {
+        const StageView sv = stage_view(L, Q, idx, node);
+        const double* An = Ah + L.nnz_off[node];
+        const double* wn = w + L.row_off[node];
+        for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) acc += An[sv.cpos[e]] * wn[sv.crow[e]];
+      }
+      if (lc < ndx) {
+        if (node == 0) acc += Ah[lc] * w[lc];
+        else {
+          const StageView sp = stage_view(L, Q, idx, node - 1);
+          const double* Ap = Ah + L.nnz_off[node - 1];
+          const double* wp = w + L.row_off[node - 1];
+          const int pc = sp.s + lc;
+          for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) acc += Ap[sp.cpos[e]] * wp[sp.crow[e]];
+        }
+      }
+      out[xo + lc] = acc;
+    }
+  }
+}
+
+// y = Linv r (lower-triangular mat-vec): warp per row, lanes over columns
+__device__ __forceinline__ void tri_matvec(const double* __restrict__ Lp, int s, const double* r, double* y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = warp; t < s; t += nw) {
+    const double* row = Lp + tri(t, 0);
+    double acc = 0.0;
+    for (int k = lane; k <= t; k += 32) acc += row[k] * r[k];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[t] = acc;
+  }
+}
+// x = Linv^T y: thread per column, rows t >= j
+__device__ __forceinline__ void tri_matvec_t(const double* __restrict__ Lp, int s, const double* y, double* x) {
+  for (int j = threadIdx.x; j < s; j += blockDim.x) {
+    double acc = 0.0;
+    for (int t = j; t < s; ++t) acc += Lp[tri(t, j)] * y[t];
+    x[j] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(QP_THREADS)
+qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, QpWork W,
+               double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out) {
+  extern __shared__ double sm[];
+  const PlmLayout& L = *tab.layout;
+  const QpLayout& Q = *Qp;
+  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
+  double* x = sm;              // [n]
+  double* xt = x + n;          // [n]  rhs -> forward solution y -> x~
+  double* z = xt + n;          // [m]
+  double* y = z + m;           // [m]
+  double* w = y + m;           // [m]  rho z - y, then z~ = A x~
+  double* tv = w + m;          // [smax] Linv^T y of the previous stage / G^T x of the next stage
+  double* rv = tv + smax;      // [smax] stage right-hand side
+  double* red = rv + smax;     // [32]
+  const double* Ah = W.Ahat + (size_t)b * L.nnz;
+  const double* Ph = W.Ph + (size_t)b * n;
+  const double* qh = W.qh + (size_t)b * n;
+  const double* lh = W.lh + (size_t)b * m;
+  const double* uh = W.uh + (size_t)b * m;
+  const double* rho = W.rho + (size_t)b * m;
+  const double* Dv = W.D + (size_t)b * n;
+  const double* Ev = W.E + (size_t)b * m;
+  const double* Lf = W.Linv + (size_t)b * Q.fac_total;
+  const double cs = W.cscale[b];
+  double* xg = W.x + (size_t)b * n;
+  double* zg = W.z + (size_t)b * m;
+  double* yg = W.y + (size_t)b * m;
+  const double alpha = Q.alpha, sigma = Q.sigma;
+  for (int j = tid; j < n; j += nth) x[j] = xg[j];
+  for (int r = tid; r < m; r += nth) { z[r] = zg[r]; y[r] = yg[r]; }
+  __syncthreads();
+  int status = 0, it = 0;
+  double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
+  for (it = 1; it <= Q.max_iter; ++it) {
+    // ---- rhs = sigma x - q + A^T (rho z - y)
+    for (int r = tid; r < m; r += nth) w[r] = rho[r] * z[r] - y[r];
+    __syncthreads();
+    spmv_cols(L, Q, idx, Ah, w, xt);
+    __syncthreads();
+    for (int j = tid; j < n; j += nth) xt[j] += sigma * x[j] - qh[j];
+    __syncthreads();
+    // ---- forward sweep: y_i = Linv_i (b_i - G_{i-1} Linv_{i-1}^T y_{i-1})
+    for (int i = 0; i <= N; ++i) {
+      const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
+      double* bi = xt + L.x_off[i];
+      if (i > 0) {
+        const StageView sp = stage_view(L, Q, idx, i - 1);
+        const double* Ap = Ah + L.nnz_off[i - 1];
+        const double* rp = rho + L.row_off[i - 1];
+        for (int c2 = tid; c2 < ndx; c2 += nth) {
+          const int e1 = sp.rptr[c2 + 1] - 1;
+          double acc = 0.0;
+          for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tv[sp.ccol[e]];
+          bi[c2] -= rp[c2] * Ap[e1] * acc;
+        }
+        __syncthreads();
+      }
+      for (int k = tid; k < s; k += nth) rv[k] = bi[k];
+      __syncthreads();
+      const double* Lp = Lf + Q.fac_off[i];
+      tri_matvec(Lp, s, rv, bi);
+      __syncthreads();
+      if (i < N) {
+        tri_matvec_t(Lp, s, bi, tv);
+        __syncthreads();
+      }
+    }
+    // ---- backward sweep: x_i = Linv_i^T (y_i - Linv_i G_i^T x_{i+1})
+    for (int i = N; i >= 0; --i) {
+      const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
+      double* yi = xt + L.x_off[i];
+      const double* Lp = Lf + Q.fac_off[i];
+      if (i < N) {
+        const StageView sv = stage_view(L, Q, idx, i);
+        const double* An = Ah + L.nnz_off[i];
+        const double* rh = rho + L.row_off[i];
+        const double* xn = xt + L.x_off[i + 1];
+        // tv = G_i^T x_{i+1}: column gather over the integrator rows (rows < ndx come first in every column)
+        for (int k = tid; k < s; k += nth) {
+          double acc = 0.0;
+          for (int e = sv.cptr[k]; e < sv.cptr[k + 1]; ++e) {
+            const int r = sv.crow[e];
+            if (r >= ndx) break;
+            const int e1 = sv.rptr[r + 1] - 1;
+            acc += An[sv.cpos[e]] * rh[r] * An[e1] * xn[r];
+          }
+          tv[k] = acc;
+        }
+        __syncthreads();
+        tri_matvec(Lp, s, tv, rv);
+        __syncthreads();
+        for (int k = tid; k < s; k += nth) rv[k] = yi[k] - rv[k];
+      } else {
+        for (int k = tid; k < s; k += nth) rv[k] = yi[k];
+      }
+      __syncthreads();
+      tri_matvec_t(Lp, s, rv, yi);
+      __syncthreads();
+    }
+    // ---- z~ = A x~ ; relaxation, projection, dual update
+    spmv_rows(L, Q, idx, Ah, xt, w);
+    __syncthreads();
+    double mdx = 0.0;
+    for (int j = tid; j < n; j += nth) {
+      const double xn = alpha * xt[j] + (1.0 - alpha) * x[j];
+      mdx = fmax(mdx, fabs(Dv[j] * (xn - x[j])));
+      xt[j] = xn - x[j];          // delta_x (kept for the dual infeasibility test)
+      x[j] = xn;
+    }
+    for (int r = tid; r < m; r += nth) {
+      const double zr = alpha * w[r] + (1.0 - alpha) * z[r];
+      double zn = zr + y[r] / rho[r];
+      zn = fmin(fmax(zn, lh[r]), uh[r]);
+      const double dy = rho[r] * (zr - zn);
+      y[r] += dy;
+      z[r] = zn;
+      w[r] = dy;                  // delta_y (kept for the primal infeasibility test)
+    }
+    __syncthreads();
+    const bool check = (Q.check_termination > 0 && it % Q.check_termination == 0) || it == Q.max_iter;
+    if (!check) continue;
+    const bool approx = !(Q.check_termination > 0 && it % Q.check_termination == 0);
+    ndx_max = block_reduce(mdx, red, true);
+    // two passes when the last iteration is also a regular check: exact first, then approximate
+    for (int pass = 0; pass < 2 && status == 0; ++pass) {
+      const bool apx = approx || pass == 1;
+      if (pass == 1 && it != Q.max_iter) break;
+      const double kk = apx ? 10.0 : 1.0;
+      const double eps_abs = Q.eps_abs * kk, eps_rel = Q.eps_rel * kk, eps_pinf = Q.eps_prim_inf * kk, eps_dinf = Q.eps_dual_inf * kk;
+      // primal residual: ||E^-1 (A x - z)||, norms of E^-1 z and E^-1 A x       (tv/rv/… are free: use global scratch-free passes)
+      double pr = 0.0, nz = 0.0, nax = 0.0;
+      {
+        // A x row by row (no storage)
+        for (int r = tid; r < m; r += nth) {
+          double ax;
+          if (r < ndx) ax = Ah[r] * x[r];
+          else {
+            int node = 0;
+            while (node + 1 < N && r >= L.row_off[node + 1]) ++node;
+            const StageView sv = stage_view(L, Q, idx, node);
+            const int lr = r - L.row_off[node];
+            const double* An = Ah + L.nnz_off[node];
+            const double* vn = x + L.x_off[node];
+            ax = 0.0;
+            for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) ax += An[e] * vn[sv.ccol[e]];
+          }
+          const double ei = 1.0 / Ev[r];
+          pr = fmax(pr, fabs((ax - z[r]) * ei));
+          nz = fmax(nz, fabs(z[r] * ei));
+          nax = fmax(nax, fabs(ax * ei));
+        }
+      }
+      pr = block_reduce(pr, red, true);
+      nz = block_reduce(nz, red, true);
+      nax = block_reduce(nax, red, true);
+      // dual residual: ||D^-1 (P x + q + A^T y)|| / c
+      double dr = 0.0, nq = 0.0, naty = 0.0, npx = 0.0;
+      {
+        const int NN = L.nodes;
+        for (int node = 0; node <= NN; ++node) {
+          const int s = (node < NN) ? Q.type[L.node_type[node]].s : ndx;
+          const int xo = L.x_off[node];
+          for (int lc = tid; lc < s; lc += nth) {
+            double acc = 0.0;
+            if (node < NN) {
+              const StageView sv = stage_view(L, Q, idx, node);
+              const double* An = Ah + L.nnz_off[node];
+              const double* wn = y + L.row_off[node];
+              for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) acc += An[sv.cpos[e]] * wn[sv.crow[e]];
+            }
+            if (lc < ndx) {
+              if (node == 0) acc += Ah[lc] * y[lc];
+              else {
+                const StageView sp = stage_view(L, Q, idx, node - 1);
+                const double* Ap = Ah + L.nnz_off[node - 1];
+                const double* wp = y + L.row_off[node - 1];
+                const int pc = sp.s + lc;
+                for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) acc += Ap[sp.cpos[e]] * wp[sp.crow[e]];
+              }
+            }
+            const int j = xo + lc;
+            const double di = 1.0 / Dv[j];
+            const double px = Ph[j] * x[j];
+            dr = fmax(dr, fabs((px + qh[j] + acc) * di));
+            nq = fmax(nq, fabs(qh[j] * di));
+            naty = fmax(naty, fabs(acc * di));
+            npx = fmax(npx, fabs(px * di));
+          }
+        }
+      }
+      dr = block_reduce(dr, red, true) / cs;
+      nq = block_reduce(nq, red, true);
+      naty = block_reduce(naty, red, true);
+      npx = block_reduce(npx, red, true);
+      const double eps_pri = eps_abs + eps_rel * fmax(nz, nax);
+      const double eps_dua = eps_abs + eps_rel * fmax(nq, fmax(naty, npx)) / cs;
+      const bool prim_ok = pr < eps_pri, dual_ok = dr < eps_dua;
+      bool prim_inf = false, dual_inf = false;
+      if (!prim_ok) {
+        // primal infeasibility certificate on delta_y (w): project on the polar of the recession cone of [l,u]
+        double ndy = 0.0, lhs = 0.0;
+        for (int r = tid; r < m; r += nth) {
+          double dy = w[r];
+          const bool up = uh[r] > OSQP_INFTY * MIN_SCALING, lo = lh[r] < -OSQP_INFTY * MIN_SCALING;
+          if (up && lo) dy = 0.0;
+          else if (up) dy = fmin(dy, 0.0);
+          else if (lo) dy = fmax(dy, 0.0);
+          ndy = fmax(ndy, fabs(Ev[r] * dy));
+          lhs += uh[r] * fmax(dy, 0.0) + lh[r] * fmin(dy, 0.0);
+        }
+        ndy = block_reduce(ndy, red, true);
+        lhs = block_reduce(lhs, red, false);
+        if (ndy > eps_pinf && lhs < -eps_pinf * ndy) {
+          // ||D^-1 A^T dy_proj|| < eps ||dy||
+          for (int r = tid; r < m; r += nth) {
+            double dy = w[r];
+            const bool up = uh[r] > OSQP_INFTY * MIN_SCALING, lo = lh[r] < -OSQP_INFTY * MIN_SCALING;
+            if (up && lo) dy = 0.0;
+            else if (up) dy = fmin(dy, 0.0);
+            else if (lo) dy = fmax(dy, 0.0);
+            zg[r] = dy;     // global scratch (rewritten with z at exit)
+          }
+          __syncthreads();
+          double na = 0.0;
+          const int NN = L.nodes;
+          for (int node = 0; node <= NN; ++node) {
+            const int s = (node < NN) ? Q.type[L.node_type[node]].s : ndx;
+            for (int lc = tid; lc < s; lc += nth) {
+              double acc = 0.0;
+              if (node < NN) {
+                const StageView sv = stage_view(L, Q, idx, node);
+                const double* An = Ah + L.nnz_off[node];
+                const double* wn = zg + L.row_off[node];
+                for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) acc += An[sv.cpos[e]] * wn[sv.crow[e]];
+              }
+              if (lc < ndx) {
+                if (node == 0) acc += Ah[lc] * zg[lc];
+                else {
+                  const StageView sp = stage_view(L, Q, idx, node - 1);
+                  const double* Ap = Ah + L.nnz_off[node - 1];
+                  const double* wp = zg + L.row_off[node - 1];
+                  const int pc = sp.s + lc;
+                  for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) acc += Ap[sp.cpos[e]] * wp[sp.crow[e]];
+                }
+              }
+              na = fmax(na, fabs(acc / Dv[L.x_off[node] + lc]));
+            }
+          }
+          na = block_reduce(na, red, true);
+          prim_inf = na < eps_pinf * ndy;
+        }
+      }
+      if (!dual_ok && !prim_inf) {
+        // dual infeasibility certificate on delta_x (xt)
+        if (ndx_max > eps_dinf) {
+          double qd = 0.0, npd = 0.0;
+          for (int j = tid; j < n; j += nth) {
+            qd += qh[j] * xt[j];
+            npd = fmax(npd, fabs(Ph[j] * xt[j] / Dv[j]));
+          }
+          qd = block_reduce(qd, red, false);
+          npd = block_reduce(npd, red, true);
+          if (qd < -cs * eps_dinf * ndx_max && npd < cs * eps_dinf * ndx_max) {
+            double bad = 0.0;
+            for (int r = tid; r < m; r += nth) {
+              double ax;
+              if (r < ndx) ax = Ah[r] * xt[r];
+              else {
+                int node = 0;
+                while (node + 1 < N && r >= L.row_off[node + 1]) ++node;
+                const StageView sv = stage_view(L, Q, idx, node);
+                const int lr = r - L.row_off[node];
+                const double* An = Ah + L.nnz_off[node];
+                const double* vn = xt + L.x_off[node];
+                ax = 0.0;
+                for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) ax += An[e] * vn[sv.ccol[e]];
+              }
+              ax /= Ev[r];
+              if ((uh[r] < OSQP_INFTY * MIN_SCALING && ax > eps_dinf * ndx_max) ||
+                  (lh[r] > -OSQP_INFTY * MIN_SCALING && ax < -eps_dinf * ndx_max)) bad = 1.0;
+            }
+            bad = block_reduce(bad, red, true);
+            dual_inf = bad == 0.0;
+          }
+        }
+      }
+      if (prim_ok && dual_ok) status = apx ? 2 : 1;
+      else if (prim_inf) status = apx ? 3 : -3;
+      else if (dual_inf) status = apx ? 4 : -4;
+    }
+    if (status != 0) break;
+  }
+  if (it > Q.max_iter) it = Q.max_iter;
+  if (status == 0) status = -2;   // maximum iterations reached
+  const bool no_solution = (status == 3 || status == -3 || status == 4 || status == -4);
+  __syncthreads();
+  for (int j = tid; j < n; j += nth) {
+    xg[j] = no_solution ? 0.0 : x[j];
+    if (dx_out) dx_out[(size_t)b * n + j] = no_solution ? nan("") : Dv[j] * x[j];
+  }
+  for (int r = tid; r < m; r += nth) {
+    zg[r] = no_solution ? 0.0 : z[r];
+    yg[r] = no_solution ? 0.0 : y[r];
+  }
+  if (tid == 0) {
+    if (iters_out) iters_out[b] = it;
+    if (status_out) status_out[b] = status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+#define QP_CUDA(h, expr)                                                               \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      (h)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+      return 7;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+int plm_qp_alloc(plm_handle* h) {
+  const PlmLayout& L = h->host.layout;
+  const QpLayout& Q = h->host.qp;
+  QpWork& W = h->qp;
+  const size_t B = (size_t)h->max_batch;
+  QP_CUDA(h, cudaMalloc(&W.d_ql, sizeof(QpLayout)));
+  QP_CUDA(h, cudaMemcpy(W.d_ql, &Q, sizeof(QpLayout), cudaMemcpyHostToDevice));
+  QP_CUDA(h, cudaMalloc(&W.d_idx, h->host.qp_idx.size() * sizeof(int16_t)));
+  QP_CUDA(h, cudaMemcpy(W.d_idx, h->host.qp_idx.data(), h->host.qp_idx.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+  auto al = [&](double** p, size_t per) { return cudaMalloc(p, B * per * sizeof(double)); };
+  QP_CUDA(h, al(&W.Ahat, L.nnz)); QP_CUDA(h, al(&W.D, L.n)); QP_CUDA(h, al(&W.E, L.m)); QP_CUDA(h, al(&W.Eprev, L.m));
+  QP_CUDA(h, al(&W.cscale, 1)); QP_CUDA(h, al(&W.Ph, L.n)); QP_CUDA(h, al(&W.qh, L.n)); QP_CUDA(h, al(&W.lh, L.m));
+  QP_CUDA(h, al(&W.uh, L.m)); QP_CUDA(h, al(&W.rho, L.m)); QP_CUDA(h, al(&W.Linv, Q.fac_total));
+  QP_CUDA(h, al(&W.x, L.n)); QP_CUDA(h, al(&W.z, L.m)); QP_CUDA(h, al(&W.y, L.m));
+  QP_CUDA(h, cudaMalloc(&h->d_qp_fail, B * sizeof(int)));
+  QP_CUDA(h, cudaMemset(W.x, 0, B * L.n * sizeof(double)));
+  QP_CUDA(h, cudaMemset(W.z, 0, B * L.m * sizeof(double)));
+  QP_CUDA(h, cudaMemset(W.y, 0, B * L.m * sizeof(double)));
+  QP_CUDA(h, cudaMemset(h->d_qp_fail, 0, B * sizeof(int)));
+  {
+    // Eprev = 1 until plm_qp_setup computes the setup-time scaling
+    std::vector<double> ones(B * L.m, 1.0);
+    QP_CUDA(h, cudaMemcpy(W.Eprev, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  W.allocated = 1;
+  h->qp_factor_doubles = Q.fac_total;
+  const int smax = Q.smax, ndx = L.ndx;
+  h->smem_scale = (size_t)(2 * L.n + 2 * L.m + 32) * 8;
+  h->smem_factor = (size_t)(smax * (smax + 1) + smax * ndx + ndx * ndx + ndx) * 8;
+  h->smem_admm = (size_t)(2 * L.n + 3 * L.m + 2 * smax + 32) * 8;
+  if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
+    h->error = "QP workspace exceeds shared memory";
+    return 7;
+  }
+  QP_CUDA(h, cudaFuncSetAttribute(qp_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_scale));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_factor));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_admm));
+  return 0;
+}
+
+void plm_qp_free(plm_handle* h) {
+  QpWork& W = h->qp;
+  cudaFree(W.d_ql); cudaFree(W.d_idx); cudaFree(W.Ahat); cudaFree(W.D); cudaFree(W.E); cudaFree(W.Eprev);
+  cudaFree(W.cscale); cudaFree(W.Ph); cudaFree(W.qh); cudaFree(W.lh); cudaFree(W.uh); cudaFree(W.rho); cudaFree(W.Linv);
+  cudaFree(W.x); cudaFree(W.z); cudaFree(W.y); cudaFree(h->d_qp_fail);
+}
+
+int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream_t s) {
+  const PlmLayout& L = h->host.layout;
+  QpWork& W = h->qp;
+  QP_CUDA(h, cudaMemsetAsync(W.x, 0, (size_t)batch * L.n * sizeof(double), s));
+  QP_CUDA(h, cudaMemsetAsync(W.z, 0, (size_t)batch * L.m * sizeof(double), s));
+  QP_CUDA(h, cudaMemsetAsync(W.y, 0, (size_t)batch * L.m * sizeof(double), s));
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J,
+                       const double* d_l, const double* d_u, cudaStream_t s) {
+  QpWork& W = h->qp;
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, 0, d_hess, d_q, d_J, d_l, d_u, W);
+  PLM_LAUNCH_CHECK(h);
+  qp_factor_kernel<<<batch, QP_THREADS, h->smem_factor, s>>>(h->tab, W.d_ql, W.d_idx, W, h->d_qp_fail);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int* d_status, cudaStream_t s) {
+  QpWork& W = h->qp;
+  qp_admm_kernel<<<batch, QP_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W, d_dx, d_iters, d_status);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+extern "C" {
+
+int plm_qp_setup(plm_handle* h, int32_t batch, const double* d_hess, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  return plm_qp_setup_impl(h, batch, d_hess, (cudaStream_t)stream);
+}
+
+int plm_qp_update(plm_handle* h, int32_t batch, const double* d_hess, const double* d_q, const double* d_J,
+                  const double* d_l, const double* d_u, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  return plm_qp_update_impl(h, batch, d_hess, d_q, d_J, d_l, d_u, (cudaStream_t)stream);
+}
+
+int plm_qp_solve(plm_handle* h, int32_t batch, double* d_dx, int32_t* d_iters, int32_t* d_status, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  return plm_qp_solve_impl(h, batch, d_dx, d_iters, d_status, (cudaStream_t)stream);
+}
+
+int plm_qp_get_iterates(plm_handle* h, int32_t batch, double* d_x, double* d_z, double* d_y, void* stream) {
+  const PlmLayout& L = h->host.layout;
+  cudaStream_t s = (cudaStream_t)stream;
+  QP_CUDA(h, cudaMemcpyAsync(d_x, h->qp.x, (size_t)batch * L.n * 8, cudaMemcpyDeviceToDevice, s));
+  QP_CUDA(h, cudaMemcpyAsync(d_z, h->qp.z, (size_t)batch * L.m * 8, cudaMemcpyDeviceToDevice, s));
+  QP_CUDA(h, cudaMemcpyAsync(d_y, h->qp.y, (size_t)batch * L.m * 8, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int plm_qp_set_iterates(plm_handle* h, int32_t batch, const double* d_x, const double* d_z, const double* d_y, void* stream) {
+  const PlmLayout& L = h->host.layout;
+  cudaStream_t s = (cudaStream_t)stream;
+  QP_CUDA(h, cudaMemcpyAsync(h->qp.x, d_x, (size_t)batch * L.n * 8, cudaMemcpyDeviceToDevice, s));
+  QP_CUDA(h, cudaMemcpyAsync(h->qp.z, d_z, (size_t)batch * L.m * 8, cudaMemcpyDeviceToDevice, s));
+  QP_CUDA(h, cudaMemcpyAsync(h->qp.y, d_y, (size_t)batch * L.m * 8, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+/* Debug / test access to the scaling of the last plm_qp_update: D [batch][n], E [batch][m], c [batch]. */
+int plm_qp_get_scaling(plm_handle* h, int32_t batch, double* d_D, double* d_E, double* d_c, void* stream) {
+  const PlmLayout& L = h->host.layout;
+  cudaStream_t s = (cudaStream_t)stream;
+  QP_CUDA(h, cudaMemcpyAsync(d_D, h->qp.D, (size_t)batch * L.n * 8, cudaMemcpyDeviceToDevice, s));
+  QP_CUDA(h, cudaMemcpyAsync(d_E, h->qp.E, (size_t)batch * L.m * 8, cudaMemcpyDeviceToDevice, s));
+  QP_CUDA(h, cudaMemcpyAsync(d_c, h->qp.cscale, (size_t)batch * 8, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+}  // extern "C"

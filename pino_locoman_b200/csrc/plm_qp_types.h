@@ -1,7 +1,52 @@
-// Workspaces of the batched OSQP-style QP solver (filled in by plm_qp.cu).
+// Tables and workspaces of the batched OSQP-style QP solver.
 #pragma once
+#include <stdint.h>
+
+#include "plm_types.h"
+
 namespace plm {
+
+// Per node-type local sparsity tables (offsets into one int16 pool).  Local columns of a node block are
+// [0, s) = this stage (DX_i | U_i) and [s, s + ndx) = DX_{i+1}; local rows are the node's rows in g order.
+struct QpTypeIdx {
+  int32_t rptr;   // [nrows+1]  CSR row pointers (positions in the node's value block)
+  int32_t ccol;   // [nnz]      local column of each value
+  int32_t cptr;   // [ncols+1]  CSC column pointers
+  int32_t cpos;   // [nnz]      value position of each CSC entry
+  int32_t crow;   // [nnz]      local row of each CSC entry
+  int32_t ncols;  // s + ndx
+  int32_t s;      // stage size ndx + nu
+};
+
+struct QpLayout {
+  QpTypeIdx type[4];
+  int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
+  int32_t fac_total;
+  int32_t smax;                        // largest stage size
+  // OSQP settings
+  int32_t max_iter, check_termination, scaling;
+  double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+};
+
 struct QpWork {
   int allocated = 0;
+  QpLayout* d_ql = nullptr;
+  int16_t* d_idx = nullptr;
+  // per instance, [max_batch][...]
+  double* Ahat = nullptr;    // [nnz]   E A D
+  double* D = nullptr;       // [n]
+  double* E = nullptr;       // [m]
+  double* Eprev = nullptr;   // [m]     row scaling in force when the bounds are classified (osqp update order)
+  double* cscale = nullptr;  // [1]
+  double* Ph = nullptr;      // [n]     c D P D
+  double* qh = nullptr;      // [n]     c D q
+  double* lh = nullptr;      // [m]     E l
+  double* uh = nullptr;      // [m]     E u
+  double* rho = nullptr;     // [m]     rho_vec
+  double* Linv = nullptr;    // [fac_total] packed lower-triangular inverses of the stage Cholesky factors
+  double* x = nullptr;       // [n]     persistent scaled ADMM iterates
+  double* z = nullptr;       // [m]
+  double* y = nullptr;       // [m]
 };
+
 }  // namespace plm

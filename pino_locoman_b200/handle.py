@@ -138,8 +138,15 @@ class Handle:
         return D
 
     # ------------------------------------------------------------------ OSQP equivalents
-    def qp_reset(self, batch):
-        self._rc(self.lib.plm_qp_reset(self._h, batch, self._stream()))
+    def qp_setup(self, hess):
+        """osqp setup(): zero iterates, record the setup-time row scaling (optimization/ocp.py:305-313)."""
+        B = _check_in(hess, (self.n,), "hess").shape[0]
+        self._rc(self.lib.plm_qp_setup(self._h, B, _ptr(hess), self._stream()))
+
+    def qp_get_scaling(self, batch):
+        D, E, c = self._new(batch, self.n), self._new(batch, self.m), self._new(batch)
+        self._rc(self.lib.plm_qp_get_scaling(self._h, batch, _ptr(D), _ptr(E), _ptr(c), self._stream()))
+        return D, E, c
 
     def qp_update(self, hess, q, J, l, u):
         B = _check_in(q, (self.n,), "q").shape[0]
