@@ -21,6 +21,8 @@ using namespace plm;
     }                                                                                     \
   } while (0)
 
+void plm_sqp_free(plm_handle* h);
+
 extern "C" {
 
 void plm_fill_default_ocp_desc(plm_ocp_desc* d, int32_t dynamics, int32_t nodes) {
@@ -100,6 +102,7 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
 void plm_destroy(plm_handle* h) {
   if (!h) return;
   plm_qp_free(h);
+  plm_sqp_free(h);
   cudaFree(h->d_model);
   cudaFree(h->d_layout);
   cudaFree(h->d_lut);

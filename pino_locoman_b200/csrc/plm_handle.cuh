@@ -10,6 +10,25 @@
 #include "plm_types.h"
 #include "plm_qp_types.h"
 
+#define PLM_LS_TRIALS 14   // a = 1, 1/2, ... while a > 1e-4 (optimization/ocp.py:433-435,448)
+
+namespace plm {
+// Line-search and SQP-step workspaces (device), sized for max_batch.
+struct LsWork {
+  double* alphas = nullptr;   // [PLM_LS_TRIALS]
+  double* ftr = nullptr;      // [B][PLM_LS_TRIALS] objective at the trials
+  double* part = nullptr;     // [B][PLM_LS_TRIALS][nodes][2] violation partials
+  double* state = nullptr;    // [B][8]
+  double* viol = nullptr;     // [B][2]
+  double* f0 = nullptr;       // [B]
+  double* gdot = nullptr;     // [B]
+  int* accepted = nullptr;    // [B]
+  // plm_sqp_step buffers
+  double *grad = nullptr, *J = nullptr, *g = nullptr, *lbg = nullptr, *ubg = nullptr, *l = nullptr, *u = nullptr, *hess = nullptr, *dx = nullptr;
+  int *iters = nullptr, *status = nullptr;
+};
+}  // namespace plm
+
 struct plm_handle {
   plm::HostTables host;
   plm_ocp_desc ocp;
@@ -31,8 +50,10 @@ struct plm_handle {
   int qp_factor_doubles = 0;
   int* d_qp_fail = nullptr;   // [max_batch] stage index (+1) of a non-positive Cholesky pivot, 0 = ok
   size_t smem_scale = 0, smem_factor = 0, smem_admm = 0;
-  // SQP step workspaces / timing
-  double* d_sqp = nullptr;
+  // line search / SQP step workspaces, timing
+  plm::LsWork ls;
+  int qp_setup_done = 0;
+  int sqp_alloc_done = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -43,6 +64,12 @@ int plm_launch_targets(plm_handle* h, const double* p, int batch, cudaStream_t s
 int plm_launch_objective(plm_handle* h, const double* x, const double* dx, const double* alphas, int ntrial, const double* p,
                          int batch, double* f, double* grad, cudaStream_t s);
 int plm_launch_hess_diag(plm_handle* h, const double* p, int batch, double* hess, cudaStream_t s);
+int plm_launch_node_trials(plm_handle* h, const double* x, const double* p, int batch, double* g, double* J, int want_jac,
+                           const void* trial_args, cudaStream_t s);
+int plm_line_search_impl(plm_handle* h, const double* x, const double* p, const double* dx, int batch, const double* g,
+                         const double* lbg, const double* ubg, double* x_new, cudaStream_t s);
+int plm_launch_bounds_shift(plm_handle* h, int batch, const double* g, const double* lbg, const double* ubg, double* l, double* u, cudaStream_t s);
+int plm_launch_stats(plm_handle* h, int batch, const int* iters, const int* status, double* stats, cudaStream_t s);
 int plm_qp_alloc(plm_handle* h);
 int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream_t s);
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J, const double* d_l, const double* d_u, cudaStream_t s);

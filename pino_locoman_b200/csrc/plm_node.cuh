@@ -49,6 +49,7 @@ struct NodeWs {
   double* g;     // [max_rows]
   double* J;     // [max_nnz]
   double* aba;   // ABA scratch: M/L, Minv, GQ, GV (nv x 32 each), GF (nv x nf)
+  double* xbuf;  // [2 ndx + nu] staged x + alpha dx of this node (line-search trials)
 };
 
 struct NodeArgs {

@@ -30,7 +30,7 @@ struct HostExec {
 // Bytes of shared workspace one warp needs for a layout.
 PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf) {
   size_t base = (sizeof(NodeWs) + 7) / 8;
-  size_t extra = (size_t)L.max_rows + (size_t)L.max_nnz;
+  size_t extra = (size_t)L.max_rows + (size_t)L.max_nnz + (size_t)(2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
   if (L.dynamics == PLM_WHOLE_BODY_ABA) extra += aba_ws_doubles(nv, nf);
   return base + extra + 2;
 }
@@ -39,7 +39,8 @@ PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf) {
 PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, double* tail) {
   ws.g = tail;
   ws.J = tail + L.max_rows;
-  ws.aba = tail + L.max_rows + L.max_nnz;
+  ws.xbuf = tail + L.max_rows + L.max_nnz;
+  ws.aba = ws.xbuf + (2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
 }
 
 }  // namespace plm

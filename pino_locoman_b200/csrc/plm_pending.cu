@@ -16,7 +16,4 @@ int plm_dyn_gaps(plm_handle* h, int32_t, const double*, const double*, const dou
 int plm_centroidal_vel_gaps(plm_handle* h, const double*, const double*, const double*, int32_t, double*, void*) { PLM_PENDING(h, "plm_centroidal_vel_gaps"); }
 int plm_com_dyn(plm_handle* h, const double*, const double*, int32_t, double*, void*) { PLM_PENDING(h, "plm_com_dyn"); }
 int plm_frame_vel(plm_handle* h, int32_t, int32_t, const double*, const double*, int32_t, double*, void*) { PLM_PENDING(h, "plm_frame_vel"); }
-int plm_line_search(plm_handle* h, const double*, const double*, const double*, int32_t, double*, double*, void*) { PLM_PENDING(h, "plm_line_search"); }
-int plm_sqp_step(plm_handle* h, const double*, const double*, int32_t, double*, double*, void*) { PLM_PENDING(h, "plm_sqp_step"); }
-int plm_last_phase_ms(plm_handle* h, double*) { PLM_PENDING(h, "plm_last_phase_ms"); }
 }

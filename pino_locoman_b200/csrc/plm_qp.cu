@@ -768,6 +768,7 @@ extern "C" {
 
 int plm_qp_setup(plm_handle* h, int32_t batch, const double* d_hess, void* stream) {
   if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  h->qp_setup_done = 1;
   return plm_qp_setup_impl(h, batch, d_hess, (cudaStream_t)stream);
 }
 
