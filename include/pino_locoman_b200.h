@@ -81,7 +81,9 @@ void plm_fill_default_ocp_desc(plm_ocp_desc* desc, int32_t dynamics, int32_t nod
 /* sizeof(plm_robot_desc), sizeof(plm_ocp_desc), sizeof(plm_dims): lets a binding verify its struct images. */
 void plm_abi_struct_sizes(int32_t out[3]);
 
-/* Create / destroy.  max_batch sizes the workspaces owned by the handle (QP factor, ADMM iterates). */
+/* Create / destroy.  max_batch sizes the workspaces owned by the handle (QP factor, ADMM iterates).
+ * max_batch == 0 gives a layout-only handle (dims / offsets / pattern queries work without a GPU; every
+ * compute entry point fails).  With max_batch > 0 a CUDA device is required: there is no CPU path. */
 int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max_batch, plm_handle** out);
 void plm_destroy(plm_handle* h);
 const char* plm_last_error(const plm_handle* h);

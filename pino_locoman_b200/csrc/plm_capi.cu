@@ -56,6 +56,7 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
   h->max_batch = max_batch;
   *out = h;
   if (!build_tables(*robot, *ocp, h->host)) { h->error = h->host.error; return 2; }
+  if (max_batch == 0) return 0;   // layout-only handle: tables and layout queries, no device work
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     h->error = "no CUDA device: pino_locoman_b200 has no CPU path";
@@ -101,6 +102,7 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
 
 void plm_destroy(plm_handle* h) {
   if (!h) return;
+  if (h->max_batch == 0) { delete h; return; }
   plm_qp_free(h);
   plm_sqp_free(h);
   cudaFree(h->d_model);

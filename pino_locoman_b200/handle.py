@@ -30,11 +30,15 @@ class Handle:
     def __init__(self, robot, dynamics, nodes, max_batch, tau_nodes=3, device=None, **osqp_opts):
         if dynamics not in _lib.DYNAMICS_ID:
             raise ValueError(f"Unknown dynamics type: {dynamics}")
-        if not torch.cuda.is_available():
+        self.layout_only = int(max_batch) == 0     # layout queries only (host-logic tests); no compute
+        if not self.layout_only and not torch.cuda.is_available():
             raise RuntimeError("pino_locoman_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        torch.cuda.set_device(self.device)
+        if self.layout_only:
+            self.device = torch.device("cpu")
+        else:
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+            torch.cuda.set_device(self.device)
         self._rd = robot_desc(robot)
         od = _lib.OcpDesc()
         self.lib.plm_fill_default_ocp_desc(ctypes.byref(od), _lib.DYNAMICS_ID[dynamics], nodes)

@@ -1,0 +1,82 @@
+"""Host logic of the plugin surface (no GPU): parameter-vector assembly, initial guess and warm start of the batched
+OCP classes against the oracle's restatement of the reference, factory / error behaviour."""
+import numpy as np
+import pytest
+
+from oracle.ocp import OracleOCP
+from pino_locoman_b200 import OCP_ARGS
+from pino_locoman_b200.optimization import make_ocp
+
+CASES = [("go2", "centroidal_vel"), ("b2", "whole_body_rnea"), ("b2g", "whole_body_aba"), ("b2", "centroidal_acc"),
+         ("b2g", "whole_body_rnea"), ("b2g", "whole_body_acc")]
+
+
+def _configure(ocp, x_init, t, ext, arm):
+    ocp.set_time_params(0.01, 0.08)
+    ocp.set_swing_params(0.07, [0.1, -0.2])
+    ocp.set_tracking_targets(np.array([0.2, 0, 0, 0, 0, 0]), ext, arm)
+    ocp.update_initial_state(x_init)
+    ocp.update_gait_sequence(t)
+
+
+@pytest.mark.parametrize("rn,kind", CASES)
+def test_parameter_vector_and_guess_match_oracle(robots, rn, kind):
+    prod, ora = robots
+    N, B = 20, 3
+    ocp = make_ocp(dynamics=kind, default_args=OCP_ARGS[kind], robot=prod[rn], nodes=N, solver="osqp", batch=B, device="layout")
+    rng = np.random.default_rng(0)
+    ts = np.array([0.0, 0.17, 0.79])
+    x_inits = np.stack([ocp.x_nom + 0.01 * rng.normal(size=ocp.x_nom.size) for _ in range(B)])
+    ext, arm = np.array([1.0, -2.0, 3.0]), np.array([0.05, 0.0, -0.02])
+    _configure(ocp, x_inits, ts, ext, arm)
+    if kind == "whole_body_rnea":
+        ocp.update_previous_torques(np.arange(ocp.nj) * 0.1)
+    for b in range(B):
+        o = OracleOCP(ora[rn], kind, N)
+        assert (ocp.n, ocp.m, ocp.handle.np) == (o.n, o.m, o.np_)
+        _configure(o, x_inits[b], ts[b], ext, arm)
+        if kind == "whole_body_rnea":
+            o.update_previous_torques(np.arange(o.nj) * 0.1)
+        assert np.array_equal(ocp._p[b], o.p_vector())            # bit-exact, incl. the gait schedules
+        # forces in the guess carry the total mass: the two independent loaders sum link masses in different orders
+        assert np.allclose(ocp.initial_guess()[b], o.initial_guess(), rtol=1e-14, atol=0)
+        assert np.array_equal(np.asarray(ocp.dts), np.asarray(o.dts()))
+    # warm start from a fake previous solution
+    sol = rng.normal(size=(B, ocp.n))
+    ocp.retract_stacked_sol(sol, retract_all=False)
+    ocp.warm_start()
+    for b in range(B):
+        o = OracleOCP(ora[rn], kind, N)
+        _configure(o, x_inits[b], ts[b], ext, arm)
+        o.retract_stacked_sol(sol[b])
+        assert np.allclose(ocp._x0[b], o.warm_start(), rtol=1e-14, atol=0)
+    assert len(ocp.q_sol) == 1 and ocp.q_sol[0].shape == (B, ocp.nq)
+
+
+def test_factory_errors(robots):
+    prod, _ = robots
+    with pytest.raises(ValueError, match="Unknown dynamics type"):
+        make_ocp(dynamics="whole_body_foo", default_args={}, robot=prod["b2"], nodes=10, solver="osqp")
+    ocp = make_ocp(dynamics="centroidal_acc", default_args=OCP_ARGS["centroidal_acc"], robot=prod["b2"], nodes=10, solver="ipopt",
+                   device="layout")
+    with pytest.raises(ValueError, match="not supported"):
+        ocp.init_solver()
+    with pytest.raises(NotImplementedError):
+        make_ocp(dynamics="centroidal_acc", default_args={"include_base": False}, robot=prod["b2"], nodes=10, solver="osqp", device="layout")
+
+
+def test_retract_integrates_on_the_manifold(robots):
+    from oracle.dynamics import DynamicsWholeBodyTorque
+    prod, ora = robots
+    ocp = make_ocp(dynamics="whole_body_rnea", default_args=OCP_ARGS["whole_body_rnea"], robot=prod["b2g"], nodes=6, solver="osqp",
+                   batch=2, device="layout")
+    rng = np.random.default_rng(1)
+    x = np.stack([ocp.x_nom, ocp.x_nom])
+    x[1, 3:7] = [0.1, -0.2, 0.3, 0.9]
+    x[1, 3:7] /= np.linalg.norm(x[1, 3:7])
+    dx = rng.normal(size=(2, ocp.ndx_opt)) * 0.4
+    dx[0, 3:6] = 0
+    got = ocp.state_integrate(x, dx)
+    dyn = DynamicsWholeBodyTorque(ora["b2g"].model, ora["b2g"].mass, ora["b2g"].foot_frames)
+    for b in range(2):
+        assert np.abs(got[b] - dyn.state_integrate()(x[b], dx[b])).max() < 1e-12
