@@ -1,0 +1,363 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: batched SQP iterations (dyn+Jacobian node evaluation -> ADMM QP -> Armijo).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE.json configs[4] per-GPU share, weak scaling): B2G (B2 + Z1 arm) whole_body_rnea, trot, N=20
+nodes, `batch` independent MPC instances per GPU with the synthetic state distributions of SURVEY.md 8(d)
+(seed 1234 + 1000*rank).  One "step" = one full SQP iteration of every instance (optimization/ocp.py:383-406);
+consecutive steps continue the SQP sequence (x <- x_new, warm-started ADMM iterates), as the MPC loop does.
+
+Prints ONE JSON line on rank 0.  `value` = SQP iterations/s with inputs resident in HBM; `e2e` = the same through
+the plugin surface (OCP.solve with host buffers, H2D + D2H inside the timed region); `node_evals_per_s` and the two
+roofline objects report the dyn+Jacobian kernel and the dominant (ADMM) kernel against the measured HBM peak;
+`cpu_baseline` is the numpy oracle on one host core (a port, for context only).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ROBOT, DYNAMICS, NODES = "b2g", "whole_body_rnea", 20
+# ALGORITHMIC bytes per node-eval / residual-only eval, B2G whole_body_rnea, avg over N=20
+BYTES_NODE_EVAL = 10464.0
+BYTES_NODE_RESID = 2220.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def synthetic_inputs(robot, ocp, batch, rank):
+    """x [B,n], p [B,np] on the host, distributions of SURVEY.md 8(d)."""
+    rng = np.random.default_rng(1234 + 1000 * rank)
+    B, nj = batch, robot.nj
+    q = np.tile(robot.q0, (B, 1))
+    q[:, 0:2] = rng.uniform(-1, 1, (B, 2))
+    q[:, 2] = rng.uniform(0.45, 0.65, B)
+    yaw, roll, pitch = rng.uniform(-np.pi, np.pi, B), rng.uniform(-0.3, 0.3, B), rng.uniform(-0.3, 0.3, B)
+    cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+    q[:, 3] = sr * cp * cy - cr * sp * sy
+    q[:, 4] = cr * sp * cy + sr * cp * sy
+    q[:, 5] = cr * cp * sy - sr * sp * cy
+    q[:, 6] = cr * cp * cy + sr * sp * sy
+    qj = rng.uniform(robot.joint_pos_min, robot.joint_pos_max, (B, nj))
+    q[:, 7:] = robot.q0[7:] + 0.9 * (qj - robot.q0[7:])
+    v = np.concatenate((rng.uniform(-1, 1, (B, 6)), rng.uniform(-0.25, 0.25, (B, nj)) * robot.joint_vel_max), 1)
+    ocp.set_time_params(0.01, 0.08)
+    ocp.set_swing_params(0.07, [0.1, -0.2])
+    ocp.set_tracking_targets(np.array([0.2, 0, 0, 0, 0, 0]), rng.uniform(-20, 20, (B, 3)), rng.uniform(-0.2, 0.2, (B, 3)))
+    ocp.update_initial_state(np.concatenate((q, v), 1))
+    ocp.update_gait_sequence(rng.integers(0, 80, B) * 0.01)
+    ocp.update_previous_torques(np.zeros(nj))
+    x = ocp.initial_guess()
+    h = ocp.handle
+    contact = ocp._get("contact_schedule").reshape(B, ocp.nodes, 4)
+    mg = ocp.mass * 9.81
+    lead = robot.nv
+    for i in range(ocp.nodes + 1):
+        o = h.x_off[i]
+        if i > 0:
+            x[:, o:o + ocp.ndx_opt] = rng.normal(0, 0.05, (B, ocp.ndx_opt))
+        if i == ocp.nodes:
+            break
+        u = x[:, o + ocp.ndx_opt:o + ocp.ndx_opt + ocp.nu_opt[i]]
+        u[:, :lead] = rng.normal(0, 5, (B, lead))
+        for k in range(4):
+            fz = rng.uniform(0, mg, B)
+            u[:, lead + 3 * k] = 0.7 * fz * rng.uniform(-0.5, 0.5, B) * contact[:, i, k]
+            u[:, lead + 3 * k + 1] = 0.7 * fz * rng.uniform(-0.5, 0.5, B) * contact[:, i, k]
+            u[:, lead + 3 * k + 2] = fz * contact[:, i, k]
+        u[:, lead + 12:lead + 15] = rng.uniform(-20, 20, (B, 3))
+        if ocp.nu_opt[i] > lead + robot.nf:
+            u[:, lead + robot.nf:] = rng.uniform(-0.5, 0.5, (B, nj)) * robot.joint_torque_max
+    return x, ocp._p.copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the numpy oracle (a port of the reference algorithm; see oracle/__init__.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_sqp_worker(args):
+    x, p, iters = args
+    from oracle.model import OracleRobot
+    from oracle.ocp import OracleOCP
+    from oracle.sqp import OracleSQP
+    o = OracleOCP(OracleRobot(ROBOT), DYNAMICS, NODES)
+    for name, (off, sz) in o.p_layout.items():
+        o.params[name][:] = p[off:off + sz]
+    s = OracleSQP(o)
+    s.init_solver()
+    t_eval = t_all = 0.0
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        o.sqp_data(x, p)
+        t_eval += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        x, _ = s.solve(x, p)
+        t_all += time.perf_counter() - t0
+    return t_eval, t_all
+
+
+def cpu_oracle_timing(x, p, n_inst, iters, procs):
+    jobs = [(x[i], p[i], iters) for i in range(n_inst)]
+    t0 = time.perf_counter()
+    if procs > 1:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_oracle_sqp_worker, jobs)
+    else:
+        res = [_oracle_sqp_worker(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    t_eval = sum(r[0] for r in res)
+    t_all = sum(r[1] for r in res)
+    return wall, t_eval, t_all
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port: casadi/pinocchio/OSQP are not installable here)."""
+    if rank != 0:
+        return
+    from pino_locoman_b200 import OCP_ARGS
+    from pino_locoman_b200.optimization import make_ocp
+    from pino_locoman_b200.utils.robot import B2G
+    robot = B2G()
+    robot.set_gait_sequence("trot", 0.8)
+    procs = os.cpu_count() or 1
+    n_inst = max(procs, 2)
+    ocp = make_ocp(dynamics=DYNAMICS, default_args=OCP_ARGS[DYNAMICS], robot=robot, nodes=NODES, solver="osqp", batch=n_inst, device="layout")
+    x, p = synthetic_inputs(robot, ocp, n_inst, 0)
+    walls = []
+    for step in range(args.warmup + args.steps):
+        _, _, t_all = cpu_oracle_timing(x, p, n_inst, 1, procs)
+        if step >= args.warmup:
+            walls.append(t_all / n_inst)      # seconds per SQP iteration on one core; `procs` cores run concurrently
+    ms = 1e3 * float(np.mean(walls)) * n_inst / procs
+    value = n_inst / (ms / 1e3)
+    line = {"impl": "reference", "metric": "sqp_iters_per_s", "value": value, "unit": "SQP iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{ROBOT} {DYNAMICS} trot N={NODES}, SQP iteration (sqp_data + OSQP + Armijo)", "robot": ROBOT,
+                       "dynamics": DYNAMICS, "nodes": NODES, "instances_per_step": n_inst},
+            "cpu_baseline": {"value": value, "unit": "SQP iters/s", "cores": procs, "kind": "port",
+                             "sample": f"{n_inst} instances x 1 SQP iteration per step, one process per core, numpy oracle "
+                                       "(restated reference algorithm; casadi/pinocchio/osqp not installable)"},
+            "e2e": {"value": value, "unit": "SQP iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8192, help="MPC instances per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pino_locoman_b200 import OCP_ARGS
+    from pino_locoman_b200.handle import _ptr
+    from pino_locoman_b200.optimization import make_ocp
+    from pino_locoman_b200.utils.robot import B2G
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pino_locoman_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, W, K = args.batch, max(args.warmup, 0), args.steps
+
+    robot = B2G()
+    robot.set_gait_sequence("trot", 0.8)
+    ocp = make_ocp(dynamics=DYNAMICS, default_args=OCP_ARGS[DYNAMICS], robot=robot, nodes=NODES, solver="osqp", batch=B, device=dev)
+    h = ocp.handle
+    x_host, p_host = synthetic_inputs(robot, ocp, B, rank)
+    ocp.init_solver()
+    x = torch.from_numpy(x_host).to(dev)
+    p = torch.from_numpy(p_host).to(dev)
+    x_new = torch.empty_like(x)
+    stats = torch.empty(B, 8, dtype=torch.float64, device=dev)
+    cost_gather = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        nonlocal x, x_new
+        h.sqp_step(x, p, x_new, stats)
+        if world > 1:   # the only exchange of the path: per-instance costs to every rank
+            dist.all_gather(cost_gather, stats[:, 5].contiguous())
+        x, x_new = x_new, x
+
+    # ---- device-resident timing
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = h.launch_count()
+    phase = np.zeros(4)
+    qp_iters, trials, accepted = [], [], []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        step()
+        phase += np.array(h.last_phase_ms())     # synchronises on the step's last event
+        s = stats.cpu().numpy()
+        qp_iters.append(float(s[:, 0].mean()))
+        trials.append(float(s[:, 4].mean()))
+        accepted.append(float(s[:, 2].mean()))
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = h.launch_count() - launches0
+    # ---- dyn+Jacobian node-eval kernel alone (sqp_data without objective / bounds)
+    g = torch.empty(B, h.m, dtype=torch.float64, device=dev)
+    J = torch.empty(B, h.nnz, dtype=torch.float64, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for _ in range(3):
+        h.lib.plm_sqp_data(h._h, _ptr(x), _ptr(p), B, None, _ptr(J), _ptr(g), None, None, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        h.lib.plm_sqp_data(h._h, _ptr(x), _ptr(p), B, None, _ptr(J), _ptr(g), None, None, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_eval = e0.elapsed_time(e1) / reps
+    launches += reps
+    del g, J
+    # ---- end to end through the plugin surface: host buffers in, host buffers out
+    ocp._x0 = x.cpu().numpy()
+    for _ in range(min(W, 1)):
+        ocp.solve(retract_all=False)
+    barrier()
+    t0 = time.perf_counter()
+    ke = max(1, min(K, 3))
+    for _ in range(ke):
+        ocp.solve(retract_all=False)
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / ke
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- reduce over ranks (max time)
+    tt = torch.tensor([ms_total, ms_eval, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, ms_eval, ms_e2e = [float(v) for v in tt.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / K
+    total_inst = B * world
+    value = total_inst / (ms_per_step / 1e3)
+    peak, peak_src = load_peaks()
+    Kavg, Tavg = float(np.mean(qp_iters)), float(np.mean(trials))
+    nnzF = h.dims.kkt_factor_doubles
+    n, m = h.n, h.m
+    ms_admm = phase[2] / K
+    bytes_admm = B * Kavg * (8.0 * nnzF + 8.0 * (3 * n + 4 * m))       # K (8 nnz(F) + 8 (3n + 4m)) per instance
+    ach_admm = bytes_admm / (ms_admm / 1e3) / 1e9
+    ach_eval = B * NODES * BYTES_NODE_EVAL / (ms_eval / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
+    line = {
+        "metric": "sqp_iters_per_s", "value": value, "unit": "SQP iters/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{ROBOT} {DYNAMICS} trot N={NODES}, {B} MPC instances per GPU, one SQP iteration per step "
+                               "(BASELINE configs[4] per-GPU share; configs[1] single-instance B2 is a parity-test case)",
+                   "robot": ROBOT, "dynamics": DYNAMICS, "nodes": NODES, "instances_per_gpu": B, "n": n, "m": m, "nnz_J": h.nnz,
+                   "l2": "per-step inputs (J, scaled A, QP factor: > 10 GB per GPU) exceed the 126 MB L2",
+                   "collective": "all_gather of per-instance cost" if world > 1 else "none"},
+        "node_evals_per_s": total_inst * NODES / (ms_eval / 1e3),
+        "phase_ms": {"eval": phase[0] / K, "qp_update": phase[1] / K, "qp_solve": phase[2] / K, "line_search": phase[3] / K},
+        "qp": {"admm_iters_avg": Kavg, "line_search_trials_avg": Tavg, "accepted_frac": float(np.mean(accepted)), "nnz_F": nnzF},
+        "roofline": {"kernel": "qp_admm_kernel", "bound": "hbm", "achieved": ach_admm, "peak": peak, "unit": "GB/s",
+                     "frac": ach_admm / peak, "traffic": (traffic or {}).get("qp_admm_kernel"), "peak_source": peak_src},
+        "roofline_node_eval": {"kernel": "node_eval_kernel", "bound": "hbm", "achieved": ach_eval, "peak": peak, "unit": "GB/s",
+                               "frac": ach_eval / peak, "traffic": (traffic or {}).get("node_eval_kernel"),
+                               "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval},
+        "e2e": {"value": total_inst / (ms_e2e / 1e3), "unit": "SQP iters/s", "h2d_bytes_per_step": int(B * (n + h.np) * 8),
+                "d2h_bytes_per_step": int(B * (n + 8) * 8)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline:
+        n_cpu = 2
+        wall, t_eval, t_all = cpu_oracle_timing(x_host, p_host, n_cpu, 1, 1)
+        line["cpu_baseline"] = {"value": n_cpu / t_all, "unit": "SQP iters/s", "cores": 1, "kind": "port",
+                                "node_evals_per_s": n_cpu * NODES / t_eval,
+                                "sample": f"{n_cpu} instances x 1 SQP iteration of the same workload, numpy oracle on one core "
+                                          "(restated reference algorithm, not casadi/pinocchio/OSQP)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

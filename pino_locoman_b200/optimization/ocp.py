@@ -225,7 +225,12 @@ class OCP:
     # ------------------------------------------------------------------ solver
     def _p_device(self):
         if self._p_dirty or getattr(self, "_p_dev", None) is None:
-            self._p_dev = torch.from_numpy(self._p).to(self.handle.device)
+            if getattr(self, "_pin_p", None) is None:
+                self._pin_p = torch.empty(self.batch, self.handle.np, dtype=torch.float64)
+                if self.handle.device.type == "cuda":
+                    self._pin_p = self._pin_p.pin_memory()
+            self._pin_p.numpy()[:] = self._p
+            self._p_dev = self._pin_p.to(self.handle.device, non_blocking=True)
             self._p_dirty = False
         return self._p_dev
 
@@ -252,11 +257,21 @@ class OCP:
         h = self.handle
         current_x = self.initial_guess() if self._x0 is None else self._x0
         start_time = time.time()
-        xd = torch.from_numpy(np.ascontiguousarray(current_x)).to(h.device)
+        if getattr(self, "_pin_x", None) is None:     # pinned staging buffers for the host <-> device copies
+            self._pin_x = torch.empty(self.batch, self.n, dtype=torch.float64).pin_memory()
+            self._pin_out = torch.empty(self.batch, self.n + 8, dtype=torch.float64).pin_memory()
+            self._dev_out = torch.empty(self.batch, self.n + 8, dtype=torch.float64, device=h.device)
+        self._pin_x.numpy()[:] = current_x
+        xd = self._pin_x.to(h.device, non_blocking=True)
         pd = self._p_device()
         x_new, stats = h.sqp_step(xd, pd)
-        sol_x = x_new.cpu().numpy()
-        self.stats = stats.cpu().numpy()
+        self._dev_out[:, :self.n] = x_new
+        self._dev_out[:, self.n:] = stats
+        self._pin_out.copy_(self._dev_out, non_blocking=True)
+        torch.cuda.current_stream(h.device).synchronize()
+        out = self._pin_out.numpy()
+        sol_x = out[:, :self.n].copy()
+        self.stats = out[:, self.n:].copy()
         self.solve_time = time.time() - start_time
         self._x0 = sol_x
         self.retract_stacked_sol(sol_x, retract_all)
