@@ -380,12 +380,31 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       if (integ ? (nnext != 1 || rows[r].back() != s + (int)r) : nnext != 0) { out.error = "unexpected stage coupling pattern"; return false; }
     }
   }
+  {
+    // flat CSR / CSC of the whole pattern (value order = CSR order)
+    const int nnz = (int)out.pat_rows.size();
+    std::vector<int> rptr(L.m + 1, 0), tptr(L.n + 1, 0), tsrc(nnz), rcol(nnz), trow(nnz);
+    for (int e = 0; e < nnz; ++e) { rptr[out.pat_rows[e] + 1]++; tptr[out.pat_cols[e] + 1]++; rcol[e] = out.pat_cols[e]; }
+    for (int r = 0; r < L.m; ++r) rptr[r + 1] += rptr[r];
+    for (int j = 0; j < L.n; ++j) tptr[j + 1] += tptr[j];
+    std::vector<int> fill(tptr.begin(), tptr.end() - 1);
+    for (int e = 0; e < nnz; ++e) { const int j = out.pat_cols[e]; tsrc[fill[j]] = e; trow[fill[j]] = out.pat_rows[e]; fill[j]++; }
+    auto push32 = [&](const std::vector<int>& v) { int o = (int)out.qp_idx32.size(); for (int x : v) out.qp_idx32.push_back(x); return o; };
+    Q.f_rptr = push32(rptr); Q.f_tptr = push32(tptr); Q.f_tsrc = push32(tsrc);
+    Q.f_rcol = push(rcol); Q.f_trow = push(trow);
+    std::vector<int> rperm(L.m), cperm(L.n);
+    for (int r = 0; r < L.m; ++r) rperm[r] = r;
+    for (int j = 0; j < L.n; ++j) cperm[j] = j;
+    std::stable_sort(rperm.begin(), rperm.end(), [&](int a, int b) { return rptr[a + 1] - rptr[a] > rptr[b + 1] - rptr[b]; });
+    std::stable_sort(cperm.begin(), cperm.end(), [&](int a, int b) { return tptr[a + 1] - tptr[a] > tptr[b + 1] - tptr[b]; });
+    Q.f_rperm = push(rperm); Q.f_cperm = push(cperm);
+  }
   Q.smax = 0;
   int fo = 0;
   for (int i = 0; i <= N; ++i) {
     const int s = (i < N) ? ndx + nu[i] : ndx;
     Q.fac_off[i] = fo;
-    fo += s * (s + 1) / 2;
+    fo += (s * (s + 1) / 2 + 1) & ~1;   // blocks start 16-byte aligned (bulk copies)
     Q.smax = std::max(Q.smax, s);
   }
   Q.fac_off[N + 1] = fo;

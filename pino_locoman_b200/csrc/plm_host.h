@@ -20,7 +20,8 @@ struct HostTables {
   std::vector<int32_t> pat_rows, pat_cols;   // COO pattern of J_g in value order
   std::vector<std::vector<std::vector<int>>> type_rowcols;   // [type][row] -> local columns (ascending)
   QpLayout qp;                          // QP solver layout
-  std::vector<int16_t> qp_idx;          // pool of the per-type CSR/CSC index tables
+  std::vector<int16_t> qp_idx;          // pool of the per-type CSR/CSC index tables (+ flat column / row indices)
+  std::vector<int32_t> qp_idx32;        // pool of the flat pointer tables
   std::string error;
 };
 

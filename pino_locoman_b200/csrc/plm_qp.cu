@@ -62,7 +62,7 @@ __device__ __forceinline__ StageView stage_view(const PlmLayout& L, const QpLayo
 // optimization/ocp.py:305-310 (A = ones on the pattern, q = 1, l = -1, u = 1); only E is kept (as Eprev).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QP_THREADS)
-qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, int mode,
+qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, int mode,
                 const double* __restrict__ hess, const double* __restrict__ qin, const double* __restrict__ Jv,
                 const double* __restrict__ lin, const double* __restrict__ uin, QpWork W) {
   extern __shared__ double sm[];
@@ -151,6 +151,12 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
     const int ro = L.row_off[node], xo = L.x_off[node], no = L.nnz_off[node];
     for (int lr = tid; lr < sv.nrows; lr += nth)
       for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) Ah[no + e] = E[ro + lr] * A[no + e] * D[xo + sv.ccol[e]];
+  }
+  __syncthreads();   // Ahat complete (block-local writes are visible after the barrier)
+  {
+    const int32_t* tsrc = idx32 + Q.f_tsrc;
+    double* AT = W.AhatT + (size_t)b * L.nnz;
+    for (int e = tid; e < L.nnz; e += nth) AT[e] = Ah[tsrc[e]];
   }
   for (int j = tid; j < n; j += nth) {
     W.D[(size_t)b * n + j] = D[j];
@@ -298,90 +304,152 @@ struct AdmmVec {
   double *x, *z, *y, *xt, *w, *t, *yv;   // shared-memory vectors
 };
 
-// out[r] = sum_k A_rk v[col]  for all rows (CSR), v indexed by global column
-__device__ void spmv_rows(const PlmLayout& L, const QpLayout& Q, const int16_t* idx, const double* Ah, const double* v, double* out) {
-  const int tid = threadIdx.x, nth = blockDim.x;
-  for (int r = tid; r < L.ndx; r += nth) out[r] = Ah[r] * v[r];
-  for (int node = 0; node < L.nodes; ++node) {
-    const StageView sv = stage_view(L, Q, idx, node);
-    const double* An = Ah + L.nnz_off[node];
-    const double* vn = v + L.x_off[node];
-    double* on = out + L.row_off[node];
-    for (int lr = tid; lr < sv.nrows; lr += nth) {
-      double acc = 0.0;
-      for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) acc += An[e] * vn[sv.ccol[e]];
-      on[lr] = acc;
-    }
+// Flat index tables of the whole pattern (shared by all instances).
+struct FlatIdx {
+  const int32_t *rptr, *tptr;
+  const int16_t *rcol, *trow, *rperm, *cperm;
+};
+
+// out[r] = sum_k A_rk v[col]  for all rows (CSR order values), v indexed by global column
+__device__ __forceinline__ void spmv_rows(const FlatIdx& F, int m, const double* __restrict__ Ah, const double* v, double* out) {
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int r = F.rperm[i];       // rows of similar length share a warp
+    const int e0 = F.rptr[r], e1 = F.rptr[r + 1];
+    double a0 = 0.0, a1 = 0.0;
+    int e = e0;
+#pragma unroll 2
+    for (; e + 1 < e1; e += 2) { a0 += Ah[e] * v[F.rcol[e]]; a1 += Ah[e + 1] * v[F.rcol[e + 1]]; }
+    if (e < e1) a0 += Ah[e] * v[F.rcol[e]];
+    out[r] = a0 + a1;
   }
 }
 
-// out[j] = sum_r A_rj w[r]  for all columns (CSC gather)
-__device__ void spmv_cols(const PlmLayout& L, const QpLayout& Q, const int16_t* idx, const double* Ah, const double* w, double* out) {
-  const int tid = threadIdx.x, nth = blockDim.x;
-  const int N = L.nodes, ndx = L.ndx;
-  for (int node = 0; node <= N; ++node) {
-    const int s = (node < N) ? Q.type[L.node_type[node]].s : ndx;
-    const int xo = L.x_off[node];
-    for (int lc = tid; lc < s; lc += nth) {
-      double acc = 0.0;
-      if (node < N) {
-        const StageView sv = stage_view(L, Q, idx, node);
-        const double* An = Ah + L.nnz_off[node];
-        const double* wn = w + L.row_off[node];
-        for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) acc += An[sv.cpos[e]] * wn[sv.crow[e]];
-      }
-      if (lc < ndx) {
-        if (node == 0) acc += Ah[lc] * w[lc];
-        else {
-          const StageView sp = stage_view(L, Q, idx, node - 1);
-          const double* Ap = Ah + L.nnz_off[node - 1];
-          const double* wp = w + L.row_off[node - 1];
-          const int pc = sp.s + lc;
-          for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) acc += Ap[sp.cpos[e]] * wp[sp.crow[e]];
-        }
-      }
-      out[xo + lc] = acc;
-    }
+// out[j] = sum_r A_rj w[r]  for all columns (CSC order values)
+__device__ __forceinline__ void spmv_cols(const FlatIdx& F, int n, const double* __restrict__ AT, const double* w, double* out) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int j = F.cperm[i];
+    const int e0 = F.tptr[j], e1 = F.tptr[j + 1];
+    double a0 = 0.0, a1 = 0.0;
+    int e = e0;
+#pragma unroll 2
+    for (; e + 1 < e1; e += 2) { a0 += AT[e] * w[F.trow[e]]; a1 += AT[e + 1] * w[F.trow[e + 1]]; }
+    if (e < e1) a0 += AT[e] * w[F.trow[e]];
+    out[j] = a0 + a1;
   }
 }
 
-// y = Linv r (lower-triangular mat-vec): warp per row, lanes over columns
-__device__ __forceinline__ void tri_matvec(const double* __restrict__ Lp, int s, const double* r, double* y) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int t = warp; t < s; t += nw) {
-    const double* row = Lp + tri(t, 0);
-    double acc = 0.0;
-    for (int k = lane; k <= t; k += 32) acc += row[k] * r[k];
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[t] = acc;
+// ---- 1-D bulk asynchronous copies global -> shared (TMA, UBLKCP) tracked by an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Triangular mat-vecs on a packed lower-triangular block in shared memory.  The triangle is cut into three
+// column (row) chunks of ch = ceil(s/3); one work item = (row, column chunk) resp. (row chunk, column), at most ch
+// multiply-adds, one item per thread; partial sums are combined in a second short pass.
+// y = Linv r
+__device__ __forceinline__ void tri_matvec(const double* __restrict__ Lp, int s, const double* r, double* y, double* part, int pld) {
+  const int ch = (s + 2) / 3;
+  for (int id = threadIdx.x; id < 6 * ch; id += blockDim.x) {
+    int t, c;
+    if (id < ch) { t = id; c = 0; }
+    else if (id < 3 * ch) { const int rem = id - ch; t = ch + (rem >> 1); c = rem & 1; }
+    else { const int rem = id - 3 * ch; const int q3 = rem / 3; t = 2 * ch + q3; c = rem - 3 * q3; }
+    if (t < s) {
+      const int k0 = c * ch, k1 = min(k0 + ch, t + 1);
+      const double* row = Lp + tri(t, 0);
+      double a0 = 0.0, a1 = 0.0;
+      int k = k0;
+#pragma unroll 4
+      for (; k + 1 < k1; k += 2) { a0 += row[k] * r[k]; a1 += row[k + 1] * r[k + 1]; }
+      if (k < k1) a0 += row[k] * r[k];
+      part[c * pld + t] = a0 + a1;
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < s; t += blockDim.x) {
+    double acc = part[t];
+    if (t >= ch) acc += part[pld + t];
+    if (t >= 2 * ch) acc += part[2 * pld + t];
+    y[t] = acc;
   }
 }
-// x = Linv^T y: thread per column, rows t >= j
-__device__ __forceinline__ void tri_matvec_t(const double* __restrict__ Lp, int s, const double* y, double* x) {
-  for (int j = threadIdx.x; j < s; j += blockDim.x) {
-    double acc = 0.0;
-    for (int t = j; t < s; ++t) acc += Lp[tri(t, j)] * y[t];
-    x[j] = acc;
+// x = Linv^T y
+__device__ __forceinline__ void tri_matvec_t(const double* __restrict__ Lp, int s, const double* y, double* x, double* part, int pld) {
+  const int ch = (s + 2) / 3;
+  for (int id = threadIdx.x; id < 3 * ch + s; id += blockDim.x) {
+    int R, k;
+    if (id < ch) { R = 0; k = id; }
+    else if (id < 3 * ch) { R = 1; k = id - ch; }
+    else { R = 2; k = id - 3 * ch; }
+    const int t0 = max(R * ch, k), t1 = min((R + 1) * ch, s);
+    double a0 = 0.0, a1 = 0.0;
+    int off = tri(t0, k);
+    int t = t0;
+#pragma unroll 4
+    for (; t + 1 < t1; t += 2) {
+      a0 += Lp[off] * y[t];
+      a1 += Lp[off + t + 1] * y[t + 1];
+      off += 2 * t + 3;
+    }
+    if (t < t1) a0 += Lp[off] * y[t];
+    part[R * pld + k] = a0 + a1;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < s; k += blockDim.x) {
+    double acc = part[2 * pld + k];
+    if (k < 2 * ch) acc += part[pld + k];
+    if (k < ch) acc += part[k];
+    x[k] = acc;
   }
 }
 
 __global__ void __launch_bounds__(QP_THREADS)
-qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, QpWork W,
+qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
                double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
   const QpLayout& Q = *Qp;
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
-  double* x = sm;              // [n]
+  // double-buffered stage factors first (16-byte aligned for the bulk copies), then the mbarriers and the vectors
+  const int fpad = (smax * (smax + 1) / 2 + 1) & ~1;
+  double* fbuf[2] = {sm, sm + fpad};
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + 2 * fpad);
+  double* x = sm + 2 * fpad + 2;   // [n]
   double* xt = x + n;          // [n]  rhs -> forward solution y -> x~
   double* z = xt + n;          // [m]
   double* y = z + m;           // [m]
   double* w = y + m;           // [m]  rho z - y, then z~ = A x~
   double* tv = w + m;          // [smax] Linv^T y of the previous stage / G^T x of the next stage
   double* rv = tv + smax;      // [smax] stage right-hand side
-  double* red = rv + smax;     // [32]
+  double* part = rv + smax;    // [3][smax] partial sums of the triangular mat-vecs
+  double* red = part + 3 * smax; // [32]
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
+  const double* AT = W.AhatT + (size_t)b * L.nnz;
+  FlatIdx F;
+  F.rptr = idx32 + Q.f_rptr; F.tptr = idx32 + Q.f_tptr; F.rcol = idx + Q.f_rcol; F.trow = idx + Q.f_trow; F.rperm = idx + Q.f_rperm; F.cperm = idx + Q.f_cperm;
   const double* Ph = W.Ph + (size_t)b * n;
   const double* qh = W.qh + (size_t)b * n;
   const double* lh = W.lh + (size_t)b * m;
@@ -397,14 +465,47 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const double alpha = Q.alpha, sigma = Q.sigma;
   for (int j = tid; j < n; j += nth) x[j] = xg[j];
   for (int r = tid; r < m; r += nth) { z[r] = zg[r]; y[r] = yg[r]; }
+  // the sweeps visit the stage blocks as a triangle wave 0,1,..,N,N-1,..,1,0,1,..: `seq` counts distinct blocks
+  int cur = 0, seq = 0;
+  unsigned par[2] = {0u, 0u};
+  auto blk_of = [&](int d) { const int r = d % (2 * N); return N - abs(N - r); };
+  auto blk_bytes = [&](int blk) { return (unsigned)(((Q.fac_off[blk + 1] - Q.fac_off[blk]) * 8 + 15) & ~15); };
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], blk_bytes(0));
+    bulk_g2s(fbuf[0], Lf + Q.fac_off[0], blk_bytes(0), &bars[0]);
+    mbar_expect_tx(&bars[1], blk_bytes(1));
+    bulk_g2s(fbuf[1], Lf + Q.fac_off[1], blk_bytes(1), &bars[1]);
+  }
+  mbar_wait(&bars[0], par[0]);
+  par[0] ^= 1u;
+  // switch to the next distinct block (already in flight), then prefetch the one after it into the freed buffer.
+  // Callers guarantee a __syncthreads() since the last read of the current buffer.
+#define FAC_ADVANCE()                                                                   \
+  do {                                                                                  \
+    const int nxt = cur ^ 1;                                                            \
+    mbar_wait(&bars[nxt], par[nxt]);                                                    \
+    par[nxt] ^= 1u;                                                                     \
+    ++seq;                                                                              \
+    if (tid == 0) {                                                                     \
+      const int pb = blk_of(seq + 1);                                                   \
+      mbar_expect_tx(&bars[cur], blk_bytes(pb));                                        \
+      bulk_g2s(fbuf[cur], Lf + Q.fac_off[pb], blk_bytes(pb), &bars[cur]);               \
+    }                                                                                   \
+    cur = nxt;                                                                          \
+  } while (0)
   int status = 0, it = 0;
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
   for (it = 1; it <= Q.max_iter; ++it) {
     // ---- rhs = sigma x - q + A^T (rho z - y)
     for (int r = tid; r < m; r += nth) w[r] = rho[r] * z[r] - y[r];
     __syncthreads();
-    spmv_cols(L, Q, idx, Ah, w, xt);
+    spmv_cols(F, n, AT, w, xt);
     __syncthreads();
     for (int j = tid; j < n; j += nth) xt[j] += sigma * x[j] - qh[j];
     __syncthreads();
@@ -423,14 +524,15 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           bi[c2] -= rp[c2] * Ap[e1] * acc;
         }
         __syncthreads();
+        FAC_ADVANCE();      // block i replaces block i-1
       }
       for (int k = tid; k < s; k += nth) rv[k] = bi[k];
       __syncthreads();
-      const double* Lp = Lf + Q.fac_off[i];
-      tri_matvec(Lp, s, rv, bi);
+      const double* Lp = fbuf[cur];
+      tri_matvec(Lp, s, rv, bi, part, smax);
       __syncthreads();
       if (i < N) {
-        tri_matvec_t(Lp, s, bi, tv);
+        tri_matvec_t(Lp, s, bi, tv, part, smax);
         __syncthreads();
       }
     }
@@ -438,8 +540,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     for (int i = N; i >= 0; --i) {
       const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
       double* yi = xt + L.x_off[i];
-      const double* Lp = Lf + Q.fac_off[i];
       if (i < N) {
+        FAC_ADVANCE();      // block i replaces block i+1
         const StageView sv = stage_view(L, Q, idx, i);
         const double* An = Ah + L.nnz_off[i];
         const double* rh = rho + L.row_off[i];
@@ -456,18 +558,18 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           tv[k] = acc;
         }
         __syncthreads();
-        tri_matvec(Lp, s, tv, rv);
+        tri_matvec(fbuf[cur], s, tv, rv, part, smax);
         __syncthreads();
         for (int k = tid; k < s; k += nth) rv[k] = yi[k] - rv[k];
       } else {
         for (int k = tid; k < s; k += nth) rv[k] = yi[k];
       }
       __syncthreads();
-      tri_matvec_t(Lp, s, rv, yi);
+      tri_matvec_t(fbuf[cur], s, rv, yi, part, smax);
       __syncthreads();
     }
     // ---- z~ = A x~ ; relaxation, projection, dual update
-    spmv_rows(L, Q, idx, Ah, xt, w);
+    spmv_rows(F, m, Ah, xt, w);
     __syncthreads();
     double mdx = 0.0;
     for (int j = tid; j < n; j += nth) {
@@ -501,18 +603,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       {
         // A x row by row (no storage)
         for (int r = tid; r < m; r += nth) {
-          double ax;
-          if (r < ndx) ax = Ah[r] * x[r];
-          else {
-            int node = 0;
-            while (node + 1 < N && r >= L.row_off[node + 1]) ++node;
-            const StageView sv = stage_view(L, Q, idx, node);
-            const int lr = r - L.row_off[node];
-            const double* An = Ah + L.nnz_off[node];
-            const double* vn = x + L.x_off[node];
-            ax = 0.0;
-            for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) ax += An[e] * vn[sv.ccol[e]];
-          }
+          double ax = 0.0;
+          for (int e = F.rptr[r]; e < F.rptr[r + 1]; ++e) ax += Ah[e] * x[F.rcol[e]];
           const double ei = 1.0 / Ev[r];
           pr = fmax(pr, fabs((ax - z[r]) * ei));
           nz = fmax(nz, fabs(z[r] * ei));
@@ -525,36 +617,15 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       // dual residual: ||D^-1 (P x + q + A^T y)|| / c
       double dr = 0.0, nq = 0.0, naty = 0.0, npx = 0.0;
       {
-        const int NN = L.nodes;
-        for (int node = 0; node <= NN; ++node) {
-          const int s = (node < NN) ? Q.type[L.node_type[node]].s : ndx;
-          const int xo = L.x_off[node];
-          for (int lc = tid; lc < s; lc += nth) {
-            double acc = 0.0;
-            if (node < NN) {
-              const StageView sv = stage_view(L, Q, idx, node);
-              const double* An = Ah + L.nnz_off[node];
-              const double* wn = y + L.row_off[node];
-              for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) acc += An[sv.cpos[e]] * wn[sv.crow[e]];
-            }
-            if (lc < ndx) {
-              if (node == 0) acc += Ah[lc] * y[lc];
-              else {
-                const StageView sp = stage_view(L, Q, idx, node - 1);
-                const double* Ap = Ah + L.nnz_off[node - 1];
-                const double* wp = y + L.row_off[node - 1];
-                const int pc = sp.s + lc;
-                for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) acc += Ap[sp.cpos[e]] * wp[sp.crow[e]];
-              }
-            }
-            const int j = xo + lc;
-            const double di = 1.0 / Dv[j];
-            const double px = Ph[j] * x[j];
-            dr = fmax(dr, fabs((px + qh[j] + acc) * di));
-            nq = fmax(nq, fabs(qh[j] * di));
-            naty = fmax(naty, fabs(acc * di));
-            npx = fmax(npx, fabs(px * di));
-          }
+        for (int j = tid; j < n; j += nth) {
+          double acc = 0.0;
+          for (int e = F.tptr[j]; e < F.tptr[j + 1]; ++e) acc += AT[e] * y[F.trow[e]];
+          const double di = 1.0 / Dv[j];
+          const double px = Ph[j] * x[j];
+          dr = fmax(dr, fabs((px + qh[j] + acc) * di));
+          nq = fmax(nq, fabs(qh[j] * di));
+          naty = fmax(naty, fabs(acc * di));
+          npx = fmax(npx, fabs(px * di));
         }
       }
       dr = block_reduce(dr, red, true) / cs;
@@ -591,29 +662,10 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           }
           __syncthreads();
           double na = 0.0;
-          const int NN = L.nodes;
-          for (int node = 0; node <= NN; ++node) {
-            const int s = (node < NN) ? Q.type[L.node_type[node]].s : ndx;
-            for (int lc = tid; lc < s; lc += nth) {
-              double acc = 0.0;
-              if (node < NN) {
-                const StageView sv = stage_view(L, Q, idx, node);
-                const double* An = Ah + L.nnz_off[node];
-                const double* wn = zg + L.row_off[node];
-                for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) acc += An[sv.cpos[e]] * wn[sv.crow[e]];
-              }
-              if (lc < ndx) {
-                if (node == 0) acc += Ah[lc] * zg[lc];
-                else {
-                  const StageView sp = stage_view(L, Q, idx, node - 1);
-                  const double* Ap = Ah + L.nnz_off[node - 1];
-                  const double* wp = zg + L.row_off[node - 1];
-                  const int pc = sp.s + lc;
-                  for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) acc += Ap[sp.cpos[e]] * wp[sp.crow[e]];
-                }
-              }
-              na = fmax(na, fabs(acc / Dv[L.x_off[node] + lc]));
-            }
+          for (int j = tid; j < n; j += nth) {
+            double acc = 0.0;
+            for (int e = F.tptr[j]; e < F.tptr[j + 1]; ++e) acc += AT[e] * zg[F.trow[e]];
+            na = fmax(na, fabs(acc / Dv[j]));
           }
           na = block_reduce(na, red, true);
           prim_inf = na < eps_pinf * ndy;
@@ -632,18 +684,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           if (qd < -cs * eps_dinf * ndx_max && npd < cs * eps_dinf * ndx_max) {
             double bad = 0.0;
             for (int r = tid; r < m; r += nth) {
-              double ax;
-              if (r < ndx) ax = Ah[r] * xt[r];
-              else {
-                int node = 0;
-                while (node + 1 < N && r >= L.row_off[node + 1]) ++node;
-                const StageView sv = stage_view(L, Q, idx, node);
-                const int lr = r - L.row_off[node];
-                const double* An = Ah + L.nnz_off[node];
-                const double* vn = xt + L.x_off[node];
-                ax = 0.0;
-                for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) ax += An[e] * vn[sv.ccol[e]];
-              }
+              double ax = 0.0;
+              for (int e = F.rptr[r]; e < F.rptr[r + 1]; ++e) ax += Ah[e] * xt[F.rcol[e]];
               ax /= Ev[r];
               if ((uh[r] < OSQP_INFTY * MIN_SCALING && ax > eps_dinf * ndx_max) ||
                   (lh[r] > -OSQP_INFTY * MIN_SCALING && ax < -eps_dinf * ndx_max)) bad = 1.0;
@@ -659,6 +701,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     }
     if (status != 0) break;
   }
+  mbar_wait(&bars[cur ^ 1], par[cur ^ 1]);   // drain the prefetch that is still in flight
   if (it > Q.max_iter) it = Q.max_iter;
   if (status == 0) status = -2;   // maximum iterations reached
   const bool no_solution = (status == 3 || status == -3 || status == 4 || status == -4);
@@ -698,8 +741,10 @@ int plm_qp_alloc(plm_handle* h) {
   QP_CUDA(h, cudaMemcpy(W.d_ql, &Q, sizeof(QpLayout), cudaMemcpyHostToDevice));
   QP_CUDA(h, cudaMalloc(&W.d_idx, h->host.qp_idx.size() * sizeof(int16_t)));
   QP_CUDA(h, cudaMemcpy(W.d_idx, h->host.qp_idx.data(), h->host.qp_idx.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+  QP_CUDA(h, cudaMalloc(&W.d_idx32, h->host.qp_idx32.size() * sizeof(int32_t)));
+  QP_CUDA(h, cudaMemcpy(W.d_idx32, h->host.qp_idx32.data(), h->host.qp_idx32.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   auto al = [&](double** p, size_t per) { return cudaMalloc(p, B * per * sizeof(double)); };
-  QP_CUDA(h, al(&W.Ahat, L.nnz)); QP_CUDA(h, al(&W.D, L.n)); QP_CUDA(h, al(&W.E, L.m)); QP_CUDA(h, al(&W.Eprev, L.m));
+  QP_CUDA(h, al(&W.Ahat, L.nnz)); QP_CUDA(h, al(&W.AhatT, L.nnz)); QP_CUDA(h, al(&W.D, L.n)); QP_CUDA(h, al(&W.E, L.m)); QP_CUDA(h, al(&W.Eprev, L.m));
   QP_CUDA(h, al(&W.cscale, 1)); QP_CUDA(h, al(&W.Ph, L.n)); QP_CUDA(h, al(&W.qh, L.n)); QP_CUDA(h, al(&W.lh, L.m));
   QP_CUDA(h, al(&W.uh, L.m)); QP_CUDA(h, al(&W.rho, L.m)); QP_CUDA(h, al(&W.Linv, Q.fac_total));
   QP_CUDA(h, al(&W.x, L.n)); QP_CUDA(h, al(&W.z, L.m)); QP_CUDA(h, al(&W.y, L.m));
@@ -718,7 +763,7 @@ int plm_qp_alloc(plm_handle* h) {
   const int smax = Q.smax, ndx = L.ndx;
   h->smem_scale = (size_t)(2 * L.n + 2 * L.m + 32) * 8;
   h->smem_factor = (size_t)(smax * (smax + 1) + smax * ndx + ndx * ndx + ndx) * 8;
-  h->smem_admm = (size_t)(2 * L.n + 3 * L.m + 2 * smax + 32) * 8;
+  h->smem_admm = (size_t)(2 * L.n + 3 * L.m + 5 * smax + 32 + 2 * ((smax * (smax + 1) / 2 + 1) & ~1) + 4) * 8;
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
     return 7;
@@ -731,7 +776,7 @@ int plm_qp_alloc(plm_handle* h) {
 
 void plm_qp_free(plm_handle* h) {
   QpWork& W = h->qp;
-  cudaFree(W.d_ql); cudaFree(W.d_idx); cudaFree(W.Ahat); cudaFree(W.D); cudaFree(W.E); cudaFree(W.Eprev);
+  cudaFree(W.d_ql); cudaFree(W.d_idx); cudaFree(W.d_idx32); cudaFree(W.AhatT); cudaFree(W.Ahat); cudaFree(W.D); cudaFree(W.E); cudaFree(W.Eprev);
   cudaFree(W.cscale); cudaFree(W.Ph); cudaFree(W.qh); cudaFree(W.lh); cudaFree(W.uh); cudaFree(W.rho); cudaFree(W.Linv);
   cudaFree(W.x); cudaFree(W.z); cudaFree(W.y); cudaFree(h->d_qp_fail);
 }
@@ -742,7 +787,7 @@ int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream
   QP_CUDA(h, cudaMemsetAsync(W.x, 0, (size_t)batch * L.n * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.z, 0, (size_t)batch * L.m * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.y, 0, (size_t)batch * L.m * sizeof(double), s));
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W);
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }
@@ -750,7 +795,7 @@ int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J,
                        const double* d_l, const double* d_u, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, 0, d_hess, d_q, d_J, d_l, d_u, W);
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, d_hess, d_q, d_J, d_l, d_u, W);
   PLM_LAUNCH_CHECK(h);
   qp_factor_kernel<<<batch, QP_THREADS, h->smem_factor, s>>>(h->tab, W.d_ql, W.d_idx, W, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);
@@ -759,7 +804,7 @@ int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const dou
 
 int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int* d_status, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_admm_kernel<<<batch, QP_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W, d_dx, d_iters, d_status);
+  qp_admm_kernel<<<batch, QP_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }

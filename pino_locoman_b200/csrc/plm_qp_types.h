@@ -20,6 +20,10 @@ struct QpTypeIdx {
 
 struct QpLayout {
   QpTypeIdx type[4];
+  // flat (whole-problem) index tables, offsets into the int32 pool: CSR row pointers, CSC column pointers,
+  // CSC source positions (into the CSR value order); and into the int16 pool: CSR global columns, CSC global rows
+  int32_t f_rptr, f_tptr, f_tsrc, f_rcol, f_trow;
+  int32_t f_rperm, f_cperm;            // int16 pool: rows / columns sorted by descending length (balanced warps)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
   int32_t fac_total;
   int32_t smax;                        // largest stage size
@@ -32,8 +36,10 @@ struct QpWork {
   int allocated = 0;
   QpLayout* d_ql = nullptr;
   int16_t* d_idx = nullptr;
+  int32_t* d_idx32 = nullptr;
   // per instance, [max_batch][...]
-  double* Ahat = nullptr;    // [nnz]   E A D
+  double* Ahat = nullptr;    // [nnz]   E A D, CSR order (value order of J)
+  double* AhatT = nullptr;   // [nnz]   the same values in CSC order
   double* D = nullptr;       // [n]
   double* E = nullptr;       // [m]
   double* Eprev = nullptr;   // [m]     row scaling in force when the bounds are classified (osqp update order)
