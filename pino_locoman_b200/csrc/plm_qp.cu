@@ -64,69 +64,51 @@ __device__ __forceinline__ StageView stage_view(const PlmLayout& L, const QpLayo
 __global__ void __launch_bounds__(QP_THREADS)
 qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, int mode,
                 const double* __restrict__ hess, const double* __restrict__ qin, const double* __restrict__ Jv,
-                const double* __restrict__ lin, const double* __restrict__ uin, QpWork W) {
+                const double* __restrict__ lin, const double* __restrict__ uin, QpWork W, int stage_A) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
   const QpLayout& Q = *Qp;
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-  const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes;
+  const int n = L.n, m = L.m, nnz = L.nnz;
   double* D = sm;            // [n]
   double* E = D + n;         // [m]
-  double* Dt = E + m;        // [n]
-  double* Et = Dt + n;       // [m]
-  double* red = Et + m;      // [32]
+  double* red = E + m;       // [32]
+  double* As = red + 32;     // [nnz] when the values fit in shared memory
+  const int32_t* rptr = idx32 + Q.f_rptr;
+  const int32_t* tptr = idx32 + Q.f_tptr;
+  const int32_t* tsrc = idx32 + Q.f_tsrc;
+  const int16_t* rcol = idx + Q.f_rcol;
+  const int16_t* trow = idx + Q.f_trow;
   const double* P = hess + (size_t)b * n;
-  const double* A = Jv ? Jv + (size_t)b * L.nnz : nullptr;
+  const double* Ag = Jv ? Jv + (size_t)b * nnz : nullptr;     // mode 1: A = ones on the pattern
   const double* q = qin ? qin + (size_t)b * n : nullptr;
+  double* Dg = W.D + (size_t)b * n;      // also the exchange buffers of the Jacobi-style update
+  double* Eg = W.E + (size_t)b * m;
+  const double* A = Ag;
+  if (stage_A && Ag) {
+    for (int e = tid; e < nnz; e += nth) As[e] = Ag[e];
+    A = As;
+  }
   for (int j = tid; j < n; j += nth) D[j] = 1.0;
   for (int r = tid; r < m; r += nth) E[r] = 1.0;
   double c = 1.0;
   __syncthreads();
   for (int pass = 0; pass < Q.scaling; ++pass) {
-    // row norms of the current scaled A: E_r * max_k |A_rk| D_col
+    // row norms of the current scaled A: E_r * max_k |A_rk| D_col ; column norms: max(|P^_jj|, D_j * max_r E_r |A_rj|)
     for (int r = tid; r < m; r += nth) {
       double v = 0.0;
-      if (r < ndx) v = ((A ? fabs(A[r]) : 1.0)) * D[r];
-      else {
-        // locate node by linear scan over row offsets (N <= 64)
-        int node = 0;
-        while (node + 1 < N && r >= L.row_off[node + 1]) ++node;
-        const StageView sv = stage_view(L, Q, idx, node);
-        const int lr = r - L.row_off[node];
-        const double* An = A ? A + L.nnz_off[node] : nullptr;
-        const int xo = L.x_off[node];
-        for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) v = fmax(v, (An ? fabs(An[e]) : 1.0) * D[xo + sv.ccol[e]]);
-      }
-      Et[r] = 1.0 / sqrt(limit_scaling(E[r] * v));
+      for (int e = rptr[r]; e < rptr[r + 1]; ++e) v = fmax(v, (A ? fabs(A[e]) : 1.0) * D[rcol[e]]);
+      Eg[r] = E[r] / sqrt(limit_scaling(E[r] * v));
     }
-    // column norms: max(|P^_jj|, D_j * max_r E_r |A_rj|)
     for (int j = tid; j < n; j += nth) {
-      int node = 0;
-      while (node < N && j >= L.x_off[node + 1]) ++node;     // node == N: terminal DX block
       double v = 0.0;
-      const int lc = j - L.x_off[node];
-      if (node < N) {
-        const StageView sv = stage_view(L, Q, idx, node);
-        const double* An = A ? A + L.nnz_off[node] : nullptr;
-        const int ro = L.row_off[node];
-        for (int e = sv.cptr[lc]; e < sv.cptr[lc + 1]; ++e) v = fmax(v, (An ? fabs(An[sv.cpos[e]]) : 1.0) * E[ro + sv.crow[e]]);
-      }
-      if (lc < ndx) {
-        if (node == 0) v = fmax(v, (A ? fabs(A[lc]) : 1.0) * E[lc]);      // DX_0 == 0 rows
-        else {
-          const StageView sp = stage_view(L, Q, idx, node - 1);
-          const double* Ap = A ? A + L.nnz_off[node - 1] : nullptr;
-          const int ro = L.row_off[node - 1];
-          const int pc = sp.s + lc;
-          for (int e = sp.cptr[pc]; e < sp.cptr[pc + 1]; ++e) v = fmax(v, (Ap ? fabs(Ap[sp.cpos[e]]) : 1.0) * E[ro + sp.crow[e]]);
-        }
-      }
+      for (int e = tptr[j]; e < tptr[j + 1]; ++e) v = fmax(v, (A ? fabs(A[tsrc[e]]) : 1.0) * E[trow[e]]);
       v = fmax(D[j] * v, c * D[j] * D[j] * fabs(P[j]));
-      Dt[j] = 1.0 / sqrt(limit_scaling(v));
+      Dg[j] = D[j] / sqrt(limit_scaling(v));
     }
     __syncthreads();
-    for (int j = tid; j < n; j += nth) D[j] *= Dt[j];
-    for (int r = tid; r < m; r += nth) E[r] *= Et[r];
+    for (int j = tid; j < n; j += nth) D[j] = Dg[j];
+    for (int r = tid; r < m; r += nth) E[r] = Eg[r];
     __syncthreads();
     // cost scaling: c_temp = 1 / limit(max(mean_j |P^_jj|, limit(||q^||_inf)))
     double sp_ = 0.0, mq = 0.0;
@@ -143,23 +125,14 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
     for (int r = tid; r < m; r += nth) W.Eprev[(size_t)b * m + r] = E[r];
     return;
   }
-  // scaled data
-  double* Ah = W.Ahat + (size_t)b * L.nnz;
-  for (int e = tid; e < ndx; e += nth) Ah[e] = E[e] * A[e] * D[e];
-  for (int node = 0; node < N; ++node) {
-    const StageView sv = stage_view(L, Q, idx, node);
-    const int ro = L.row_off[node], xo = L.x_off[node], no = L.nnz_off[node];
-    for (int lr = tid; lr < sv.nrows; lr += nth)
-      for (int e = sv.rptr[lr]; e < sv.rptr[lr + 1]; ++e) Ah[no + e] = E[ro + lr] * A[no + e] * D[xo + sv.ccol[e]];
-  }
-  __syncthreads();   // Ahat complete (block-local writes are visible after the barrier)
-  {
-    const int32_t* tsrc = idx32 + Q.f_tsrc;
-    double* AT = W.AhatT + (size_t)b * L.nnz;
-    for (int e = tid; e < L.nnz; e += nth) AT[e] = Ah[tsrc[e]];
-  }
+  // scaled data: CSR-ordered and CSC-ordered copies of E A D
+  double* Ah = W.Ahat + (size_t)b * nnz;
+  double* AT = W.AhatT + (size_t)b * nnz;
+  for (int r = tid; r < m; r += nth)
+    for (int e = rptr[r]; e < rptr[r + 1]; ++e) Ah[e] = E[r] * A[e] * D[rcol[e]];
+  for (int j = tid; j < n; j += nth)
+    for (int e = tptr[j]; e < tptr[j + 1]; ++e) AT[e] = E[trow[e]] * A[tsrc[e]] * D[j];
   for (int j = tid; j < n; j += nth) {
-    W.D[(size_t)b * n + j] = D[j];
     W.Ph[(size_t)b * n + j] = c * D[j] * D[j] * P[j];
     W.qh[(size_t)b * n + j] = c * D[j] * q[j];
   }
@@ -178,7 +151,6 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
     W.rho[(size_t)b * m + r] = rho;
     W.lh[(size_t)b * m + r] = E[r] * lc;
     W.uh[(size_t)b * m + r] = E[r] * uc;
-    W.E[(size_t)b * m + r] = E[r];
     W.Eprev[(size_t)b * m + r] = E[r];
   }
 }
@@ -197,10 +169,14 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
   const int tsz = smax * (smax + 1) / 2;
   double* H = sm;                      // [tsz]  stage block -> Cholesky factor (packed lower)
-  double* Li = H + tsz;                // [tsz]  inverse of the factor (packed lower)
+  double* Li = H + tsz;                // [tsz]  inverse of the factor (packed lower), built alongside the factorisation
   double* Wm = Li + tsz;               // [smax][ndx]  W = Linv G^T
   double* K = Wm + smax * ndx;         // [ndx][ndx]   Schur term for the next stage
-  double* gsc = K + ndx * ndx;         // [ndx]  rho_r * (next entry) of the integrator rows
+  double* gsc = K + ndx * ndx;         // [ndx]  rho_r * (next entry)^2 of the integrator rows
+  double* colk = gsc + ndx;            // [smax] current Cholesky column
+  double* rowk = colk + smax;          // [smax] current row of the inverse
+  double* As = rowk + smax;            // [max_nnz] scaled A values of the node block
+  double* rs = As + L.max_nnz;         // [max_rows] rho of the node rows
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* Ph = W.Ph + (size_t)b * n;
   const double* rho = W.rho + (size_t)b * m;
@@ -212,12 +188,20 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     if (!last) sv = stage_view(L, Q, idx, i);
     const int s = last ? ndx : sv.s;
     const int xo = L.x_off[i];
-    const double* An = last ? nullptr : Ah + L.nnz_off[i];
-    const double* rh = last ? nullptr : rho + L.row_off[i];
-    // ---- H_ii (lower triangle): thread j owns row j
+    if (!last) {   // stage the node's values in shared memory: every entry is used many times below
+      const double* An = Ah + L.nnz_off[i];
+      const double* rh = rho + L.row_off[i];
+      const int nnz_i = L.types[L.node_type[i]].nnz;
+      for (int e = tid; e < nnz_i; e += nth) As[e] = An[e];
+      for (int r = tid; r < sv.nrows; r += nth) rs[r] = rh[r];
+    }
+    __syncthreads();
+    // ---- H_ii (lower triangle): thread j owns row j;  Linv starts as the identity
     for (int j = tid; j < s; j += nth) {
       double* Hj = H + tri(j, 0);
-      for (int k = 0; k <= j; ++k) Hj[k] = 0.0;
+      double* Xj = Li + tri(j, 0);
+      for (int k = 0; k <= j; ++k) { Hj[k] = 0.0; Xj[k] = 0.0; }
+      Xj[j] = 1.0;
       Hj[j] = Ph[xo + j] + Q.sigma;
       if (j < ndx) {
         if (i == 0) Hj[j] += rho[j] * Ah[j] * Ah[j];           // DX_0 == 0 rows
@@ -229,59 +213,59 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       if (!last) {
         for (int e = sv.cptr[j]; e < sv.cptr[j + 1]; ++e) {
           const int r = sv.crow[e];
-          const double w = rh[r] * An[sv.cpos[e]];
+          const double w = rs[r] * As[sv.cpos[e]];
           for (int e2 = sv.rptr[r]; e2 < sv.rptr[r + 1]; ++e2) {
             const int k = sv.ccol[e2];
-            if (k <= j) Hj[k] += w * An[e2];
+            if (k > j) break;
+            Hj[k] += w * As[e2];
           }
         }
       }
     }
     __syncthreads();
-    // ---- in-place Cholesky (right-looking)
+    // ---- right-looking Cholesky; the same column sweeps apply L^-1 to the identity (X <- L^-1), two barriers per column
     for (int k = 0; k < s; ++k) {
       const double piv = H[tri(k, k)];
       if (!(piv > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
-      const double d = sqrt(piv > 0.0 ? piv : 1.0);
+      const double dinv = 1.0 / sqrt(piv > 0.0 ? piv : 1.0);
+      for (int r = k + 1 + tid; r < s; r += nth) colk[r] = H[tri(r, k)] * dinv;
+      for (int c2 = tid; c2 <= k; c2 += nth) {
+        const double v = Li[tri(k, c2)] * dinv;     // row k of X is final after scaling by 1/L_kk
+        rowk[c2] = v;
+      }
       __syncthreads();
-      for (int r = k + tid; r < s; r += nth) H[tri(r, k)] = (r == k) ? d : H[tri(r, k)] / d;
-      __syncthreads();
-      // trailing update: rows k+1.., 8 column lanes per row
+      // trailing update of H (rows r > k, columns k < c2 <= r) and of X (rows r > k, columns c2 <= k)
       const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
       for (int r = k + 1 + slot; r < s; r += nslot) {
-        const double lrk = H[tri(r, k)];
+        const double lrk = colk[r];
         double* Hr = H + tri(r, 0);
-        for (int c2 = k + 1 + lane8; c2 <= r; c2 += 8) Hr[c2] -= lrk * H[tri(c2, k)];
+        double* Xr = Li + tri(r, 0);
+        for (int c2 = k + 1 + lane8; c2 <= r; c2 += 8) Hr[c2] -= lrk * colk[c2];
+        for (int c2 = lane8; c2 <= k; c2 += 8) Xr[c2] -= lrk * rowk[c2];
+        if (lane8 == 0) Hr[k] = lrk;
       }
+      if (tid <= k) Li[tri(k, tid)] = rowk[tid];
+      if (tid == 0) H[tri(k, k)] = 1.0 / dinv;
+      for (int c2 = nth + tid; c2 <= k; c2 += nth) Li[tri(k, c2)] = rowk[c2];
       __syncthreads();
     }
-    // ---- Linv: column j by forward substitution (thread per column)
-    for (int j = tid; j < s; j += nth) {
-      for (int r = j; r < s; ++r) {
-        double acc = (r == j) ? 1.0 : 0.0;
-        const double* Hr = H + tri(r, 0);
-        for (int k = j; k < r; ++k) acc -= Hr[k] * Li[tri(k, j)];
-        Li[tri(r, j)] = acc / Hr[r];
-      }
-    }
-    __syncthreads();
     for (int e = tid; e < s * (s + 1) / 2; e += nth) Lout[Q.fac_off[i] + e] = Li[e];
     if (last) break;
     // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = Linv G^T ; K = W^T W
     for (int c2 = tid; c2 < ndx; c2 += nth) {
       const int elast = sv.rptr[c2 + 1] - 1;              // next entry of integrator row c2
-      const double nn = An[elast];
-      gsc[c2] = rh[c2] * nn * nn;
+      const double nn = As[elast];
+      gsc[c2] = rs[c2] * nn * nn;
     }
     for (int o = tid; o < s * ndx; o += nth) {
       const int t = o / ndx, c2 = o % ndx;
       const int e0 = sv.rptr[c2], e1 = sv.rptr[c2 + 1] - 1;
-      const double g = rh[c2] * An[e1];
+      const double g = rs[c2] * As[e1];
       double acc = 0.0;
       const double* Lt = Li + tri(t, 0);
       for (int e = e0; e < e1; ++e) {
         const int k = sv.ccol[e];
-        if (k <= t) acc += An[e] * Lt[k];
+        if (k <= t) acc += As[e] * Lt[k];
       }
       Wm[o] = g * acc;
     }
@@ -289,9 +273,11 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     for (int o = tid; o < ndx * ndx; o += nth) {
       const int r = o / ndx, c2 = o % ndx;
       if (c2 > r) continue;
-      double acc = 0.0;
-      for (int t = 0; t < s; ++t) acc += Wm[t * ndx + r] * Wm[t * ndx + c2];
-      K[o] = acc;
+      double a0 = 0.0, a1 = 0.0;
+      int t = 0;
+      for (; t + 1 < s; t += 2) { a0 += Wm[t * ndx + r] * Wm[t * ndx + c2]; a1 += Wm[(t + 1) * ndx + r] * Wm[(t + 1) * ndx + c2]; }
+      if (t < s) a0 += Wm[t * ndx + r] * Wm[t * ndx + c2];
+      K[o] = a0 + a1;
     }
     __syncthreads();
   }
@@ -300,6 +286,16 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
 // ------------------------------------------------------------------------------------------------------------
 // ADMM iterations.
 // ------------------------------------------------------------------------------------------------------------
+// Optional in-kernel phase timers (build with -DPLM_ADMM_PROFILE): cycles of thread 0 of CTA 0 per phase class.
+#ifdef PLM_ADMM_PROFILE
+__device__ long long g_admm_prof[16];
+#define PROF_T0() long long _pt = clock64()
+#define PROF_ADD(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long _n = clock64(); g_admm_prof[k] += _n - _pt; _pt = _n; } } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(k)
+#endif
+
 struct AdmmVec {
   double *x, *z, *y, *xt, *w, *t, *yv;   // shared-memory vectors
 };
@@ -365,17 +361,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// Triangular mat-vecs on a packed lower-triangular block in shared memory.  The triangle is cut into three
-// column (row) chunks of ch = ceil(s/3); one work item = (row, column chunk) resp. (row chunk, column), at most ch
-// multiply-adds, one item per thread; partial sums are combined in a second short pass.
-// y = Linv r
-__device__ __forceinline__ void tri_matvec(const double* __restrict__ Lp, int s, const double* r, double* y, double* part, int pld) {
-  const int ch = (s + 2) / 3;
-  for (int id = threadIdx.x; id < 6 * ch; id += blockDim.x) {
-    int t, c;
-    if (id < ch) { t = id; c = 0; }
-    else if (id < 3 * ch) { const int rem = id - ch; t = ch + (rem >> 1); c = rem & 1; }
-    else { const int rem = id - 3 * ch; const int q3 = rem / 3; t = 2 * ch + q3; c = rem - 3 * q3; }
+// Triangular mat-vecs on a packed lower-triangular block in shared memory.  The triangle is cut into NCH
+// column (row) chunks of ch = ceil(s/NCH); one work item = (row, column chunk) resp. (row chunk, column), at most ch
+// multiply-adds, one item per thread; partial sums are combined in a second short pass.  In-place use is allowed.
+#define ADMM_THREADS 512
+#define NCH 6
+// y = (sub ? sub - Linv r : Linv r)
+__device__ __forceinline__ void tri_matvec(const double* __restrict__ Lp, int s, const double* r, double* y, const double* sub,
+                                           double* part, int pld) {
+  const int ch = (s + NCH - 1) / NCH;
+  for (int id = threadIdx.x; id < ch * (NCH * (NCH + 1) / 2); id += blockDim.x) {
+    int g = 0, base = 0;
+    while (id >= base + ch * (g + 1)) { base += ch * (g + 1); ++g; }     // band g: rows [g ch, (g+1) ch), g+1 chunks each
+    const int rem = id - base, q = rem / (g + 1);
+    const int t = g * ch + q, c = rem - q * (g + 1);
     if (t < s) {
       const int k0 = c * ch, k1 = min(k0 + ch, t + 1);
       const double* row = Lp + tri(t, 0);
@@ -390,19 +389,21 @@ __device__ __forceinline__ void tri_matvec(const double* __restrict__ Lp, int s,
   __syncthreads();
   for (int t = threadIdx.x; t < s; t += blockDim.x) {
     double acc = part[t];
-    if (t >= ch) acc += part[pld + t];
-    if (t >= 2 * ch) acc += part[2 * pld + t];
-    y[t] = acc;
+    const int nc = t / ch;
+    for (int c = 1; c <= nc; ++c) acc += part[c * pld + t];
+    y[t] = sub ? sub[t] - acc : acc;
   }
 }
 // x = Linv^T y
 __device__ __forceinline__ void tri_matvec_t(const double* __restrict__ Lp, int s, const double* y, double* x, double* part, int pld) {
-  const int ch = (s + 2) / 3;
-  for (int id = threadIdx.x; id < 3 * ch + s; id += blockDim.x) {
-    int R, k;
-    if (id < ch) { R = 0; k = id; }
-    else if (id < 3 * ch) { R = 1; k = id - ch; }
-    else { R = 2; k = id - 3 * ch; }
+  const int ch = (s + NCH - 1) / NCH;
+  // row chunk R covers rows [R ch, (R+1) ch) and columns k < min((R+1) ch, s)
+  int total = 0;
+  for (int R = 0; R < NCH; ++R) total += min((R + 1) * ch, s);
+  for (int id = threadIdx.x; id < total; id += blockDim.x) {
+    int R = 0, base = 0;
+    while (id >= base + min((R + 1) * ch, s)) { base += min((R + 1) * ch, s); ++R; }
+    const int k = id - base;
     const int t0 = max(R * ch, k), t1 = min((R + 1) * ch, s);
     double a0 = 0.0, a1 = 0.0;
     int off = tri(t0, k);
@@ -418,14 +419,14 @@ __device__ __forceinline__ void tri_matvec_t(const double* __restrict__ Lp, int 
   }
   __syncthreads();
   for (int k = threadIdx.x; k < s; k += blockDim.x) {
-    double acc = part[2 * pld + k];
-    if (k < 2 * ch) acc += part[pld + k];
-    if (k < ch) acc += part[k];
+    double acc = 0.0;
+    for (int R = k / ch; R < NCH; ++R)
+      if (R * ch < s) acc += part[R * pld + k];
     x[k] = acc;
   }
 }
 
-__global__ void __launch_bounds__(QP_THREADS)
+__global__ void __launch_bounds__(ADMM_THREADS)
 qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
                double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out) {
   extern __shared__ double sm[];
@@ -444,8 +445,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* w = y + m;           // [m]  rho z - y, then z~ = A x~
   double* tv = w + m;          // [smax] Linv^T y of the previous stage / G^T x of the next stage
   double* rv = tv + smax;      // [smax] stage right-hand side
-  double* part = rv + smax;    // [3][smax] partial sums of the triangular mat-vecs
-  double* red = part + 3 * smax; // [32]
+  double* part = rv + smax;    // [NCH][smax] partial sums of the triangular mat-vecs
+  double* red = part + NCH * smax; // [32]
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
   FlatIdx F;
@@ -501,7 +502,9 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   } while (0)
   int status = 0, it = 0;
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
+  PROF_T0();
   for (it = 1; it <= Q.max_iter; ++it) {
+    PROF_ADD(15);
     // ---- rhs = sigma x - q + A^T (rho z - y)
     for (int r = tid; r < m; r += nth) w[r] = rho[r] * z[r] - y[r];
     __syncthreads();
@@ -509,6 +512,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     __syncthreads();
     for (int j = tid; j < n; j += nth) xt[j] += sigma * x[j] - qh[j];
     __syncthreads();
+    PROF_ADD(0);
     // ---- forward sweep: y_i = Linv_i (b_i - G_{i-1} Linv_{i-1}^T y_{i-1})
     for (int i = 0; i <= N; ++i) {
       const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
@@ -524,16 +528,18 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           bi[c2] -= rp[c2] * Ap[e1] * acc;
         }
         __syncthreads();
+        PROF_ADD(1);
         FAC_ADVANCE();      // block i replaces block i-1
+        PROF_ADD(2);
       }
-      for (int k = tid; k < s; k += nth) rv[k] = bi[k];
-      __syncthreads();
       const double* Lp = fbuf[cur];
-      tri_matvec(Lp, s, rv, bi, part, smax);
+      tri_matvec(Lp, s, bi, bi, nullptr, part, smax);
       __syncthreads();
+      PROF_ADD(3);
       if (i < N) {
         tri_matvec_t(Lp, s, bi, tv, part, smax);
         __syncthreads();
+        PROF_ADD(4);
       }
     }
     // ---- backward sweep: x_i = Linv_i^T (y_i - Linv_i G_i^T x_{i+1})
@@ -542,6 +548,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       double* yi = xt + L.x_off[i];
       if (i < N) {
         FAC_ADVANCE();      // block i replaces block i+1
+        PROF_ADD(2);
         const StageView sv = stage_view(L, Q, idx, i);
         const double* An = Ah + L.nnz_off[i];
         const double* rh = rho + L.row_off[i];
@@ -558,19 +565,21 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           tv[k] = acc;
         }
         __syncthreads();
-        tri_matvec(fbuf[cur], s, tv, rv, part, smax);
+        PROF_ADD(5);
+        tri_matvec(fbuf[cur], s, tv, rv, yi, part, smax);     // rv = y_i - Linv_i G_i^T x_{i+1}
         __syncthreads();
-        for (int k = tid; k < s; k += nth) rv[k] = yi[k] - rv[k];
+        PROF_ADD(3);
+        tri_matvec_t(fbuf[cur], s, rv, yi, part, smax);
       } else {
-        for (int k = tid; k < s; k += nth) rv[k] = yi[k];
+        tri_matvec_t(fbuf[cur], s, yi, yi, part, smax);
       }
       __syncthreads();
-      tri_matvec_t(fbuf[cur], s, rv, yi, part, smax);
-      __syncthreads();
+      PROF_ADD(4);
     }
     // ---- z~ = A x~ ; relaxation, projection, dual update
     spmv_rows(F, m, Ah, xt, w);
     __syncthreads();
+    PROF_ADD(6);
     double mdx = 0.0;
     for (int j = tid; j < n; j += nth) {
       const double xn = alpha * xt[j] + (1.0 - alpha) * x[j];
@@ -588,6 +597,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       w[r] = dy;                  // delta_y (kept for the primal infeasibility test)
     }
     __syncthreads();
+    PROF_ADD(7);
     const bool check = (Q.check_termination > 0 && it % Q.check_termination == 0) || it == Q.max_iter;
     if (!check) continue;
     const bool approx = !(Q.check_termination > 0 && it % Q.check_termination == 0);
@@ -699,6 +709,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       else if (prim_inf) status = apx ? 3 : -3;
       else if (dual_inf) status = apx ? 4 : -4;
     }
+    PROF_ADD(8);
     if (status != 0) break;
   }
   mbar_wait(&bars[cur ^ 1], par[cur ^ 1]);   // drain the prefetch that is still in flight
@@ -761,9 +772,11 @@ int plm_qp_alloc(plm_handle* h) {
   W.allocated = 1;
   h->qp_factor_doubles = Q.fac_total;
   const int smax = Q.smax, ndx = L.ndx;
-  h->smem_scale = (size_t)(2 * L.n + 2 * L.m + 32) * 8;
-  h->smem_factor = (size_t)(smax * (smax + 1) + smax * ndx + ndx * ndx + ndx) * 8;
-  h->smem_admm = (size_t)(2 * L.n + 3 * L.m + 5 * smax + 32 + 2 * ((smax * (smax + 1) / 2 + 1) & ~1) + 4) * 8;
+  h->smem_scale = (size_t)(L.n + L.m + 32) * 8;
+  h->scale_stage_A = (h->smem_scale + (size_t)L.nnz * 8 <= 200 * 1024) ? 1 : 0;
+  if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
+  h->smem_factor = (size_t)(smax * (smax + 1) + smax * ndx + ndx * ndx + ndx + 2 * smax + L.max_nnz + L.max_rows) * 8;
+  h->smem_admm = (size_t)(2 * L.n + 3 * L.m + (2 + NCH) * smax + 32 + 2 * ((smax * (smax + 1) / 2 + 1) & ~1) + 4) * 8;
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
     return 7;
@@ -787,7 +800,7 @@ int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream
   QP_CUDA(h, cudaMemsetAsync(W.x, 0, (size_t)batch * L.n * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.z, 0, (size_t)batch * L.m * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.y, 0, (size_t)batch * L.m * sizeof(double), s));
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W);
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W, 0);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }
@@ -795,7 +808,7 @@ int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J,
                        const double* d_l, const double* d_u, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, d_hess, d_q, d_J, d_l, d_u, W);
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, d_hess, d_q, d_J, d_l, d_u, W, h->scale_stage_A);
   PLM_LAUNCH_CHECK(h);
   qp_factor_kernel<<<batch, QP_THREADS, h->smem_factor, s>>>(h->tab, W.d_ql, W.d_idx, W, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);
@@ -804,7 +817,7 @@ int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const dou
 
 int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int* d_status, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_admm_kernel<<<batch, QP_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status);
+  qp_admm_kernel<<<batch, ADMM_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }
@@ -845,6 +858,13 @@ int plm_qp_set_iterates(plm_handle* h, int32_t batch, const double* d_x, const d
   QP_CUDA(h, cudaMemcpyAsync(h->qp.y, d_y, (size_t)batch * L.m * 8, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
+
+#ifdef PLM_ADMM_PROFILE
+int plm_debug_admm_profile(long long* out16, int reset) {
+  if (reset) { long long z[16] = {0}; return (int)cudaMemcpyToSymbol(g_admm_prof, z, sizeof(z)); }
+  return (int)cudaMemcpyFromSymbol(out16, g_admm_prof, 16 * sizeof(long long));
+}
+#endif
 
 /* Debug / test access to the scaling of the last plm_qp_update: D [batch][n], E [batch][m], c [batch]. */
 int plm_qp_get_scaling(plm_handle* h, int32_t batch, double* d_D, double* d_E, double* d_c, void* stream) {
