@@ -125,8 +125,10 @@ int plm_dyn_gaps(plm_handle* h, int32_t dynamics, const double* d_q, const doubl
 int plm_centroidal_vel_gaps(plm_handle* h, const double* d_h, const double* d_q, const double* d_v, int32_t batch,
                             double* d_gaps, void* stream);
 int plm_com_dyn(plm_handle* h, const double* d_q, const double* d_forces, int32_t batch, double* d_dh, void* stream);
-/* frame_vel(q, v) -> vel [6] for contact frame `contact` (0..nfeet-1 feet, nfeet = ext-force frame, -1 = arm frame);
- * relative_to_base as in dynamics/dynamics.py:77-118 */
+/* frame_vel(q, v) -> linear part vel[:3] (the components the OCP rows use, optimization/ocp.py:143-180) of
+ * dynamics/dynamics.py:77-118: foot frame `contact` in 0..nfeet-1 with relative_to_base = 0 (LOCAL_WORLD_ALIGNED),
+ * or the arm end-effector frame (contact = -1) with relative_to_base = 1 (x, y in base axes, z in the world).
+ * d_vel is [batch][3]. */
 int plm_frame_vel(plm_handle* h, int32_t contact, int32_t relative_to_base, const double* d_q, const double* d_v,
                   int32_t batch, double* d_vel, void* stream);
 

@@ -103,6 +103,7 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
 void plm_destroy(plm_handle* h) {
   if (!h) return;
   if (h->max_batch == 0) { delete h; return; }
+  plm_dyn_free(h);
   plm_qp_free(h);
   plm_sqp_free(h);
   cudaFree(h->d_model);

@@ -1,0 +1,324 @@
+// Dynamics* Function entry points (dynamics/*.py of the reference), batched.
+// Each call packs its arguments into a two-node probe problem of the matching formulation (x_init = the given
+// state, DX = 0, dt = 1), runs the node kernel of that formulation once and unpacks the requested rows /
+// Jacobian entries -- the same device code that evaluates the OCP rows, so values and derivatives are identical.
+#include <string.h>
+
+#include <vector>
+
+#include "plm_handle.cuh"
+#include "plm_vec.cuh"
+
+using namespace plm;
+
+#define DYN_CUDA(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      (h)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+      return 10;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+struct plm_probe {
+  plm_handle* h = nullptr;       // probe handle (nodes = 2)
+  double *x = nullptr, *p = nullptr, *g = nullptr, *J = nullptr;
+  int32_t* map = nullptr;        // [rows_out][cols_out] -> position in the probe's J values (or -1)
+  int rows_out = 0, cols_out = 0;
+};
+
+__global__ void probe_pack_kernel(int batch, int n, int np, double* __restrict__ x, double* __restrict__ p,
+                                  int p_x_init, int nx_a, const double* __restrict__ a_src, int nx_b, const double* __restrict__ b_src,
+                                  int u_off, int nu_a, const double* __restrict__ ua, int nu_b, const double* __restrict__ ub,
+                                  int p_dt_min, int p_dt_max, int p_n_contacts, int p_swing_period, int p_contact, int ncontact_flags) {
+  const int b = blockIdx.x;
+  double* xb = x + (size_t)b * n;
+  double* pb = p + (size_t)b * np;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xb[i] = 0.0;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) pb[i] = 0.0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nx_a; i += blockDim.x) pb[p_x_init + i] = a_src ? a_src[(size_t)b * nx_a + i] : 0.0;
+  for (int i = threadIdx.x; i < nx_b; i += blockDim.x) pb[p_x_init + nx_a + i] = b_src ? b_src[(size_t)b * nx_b + i] : 0.0;
+  for (int i = threadIdx.x; i < nu_a; i += blockDim.x) xb[u_off + i] = ua ? ua[(size_t)b * nu_a + i] : 0.0;
+  for (int i = threadIdx.x; i < nu_b; i += blockDim.x) xb[u_off + nu_a + i] = ub ? ub[(size_t)b * nu_b + i] : 0.0;
+  for (int i = threadIdx.x; i < ncontact_flags; i += blockDim.x) pb[p_contact + i] = 1.0;   // every foot in contact
+  if (threadIdx.x == 0) {
+    pb[p_dt_min] = 1.0; pb[p_dt_max] = 1.0; pb[p_n_contacts] = 1.0; pb[p_swing_period] = 1.0;
+  }
+}
+
+// out[b][r] = sign * g[b][row0 + r]
+__global__ void probe_rows_kernel(int batch, int m, int row0, int nrows, double sign, const double* __restrict__ g, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * nrows) return;
+  const int b = i / nrows, r = i % nrows;
+  out[i] = sign * g[(size_t)b * m + row0 + r];
+}
+
+// jac[b][r][c] = sign * J[b][map[r][c]] (+ diag_add on r == c + diag_col0), 0 where the entry is structurally absent
+__global__ void probe_jac_kernel(int batch, int nnz, int rows, int cols, const int32_t* __restrict__ map, double sign,
+                                 int diag_col0, double diag_add, const double* __restrict__ J, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)batch * rows * cols) return;
+  const int b = (int)(i / (rows * cols)), rc = (int)(i % (rows * cols));
+  const int r = rc / cols, c = rc % cols;
+  const int pos = map[rc];
+  double v = pos >= 0 ? sign * J[(size_t)b * nnz + pos] : 0.0;
+  if (diag_col0 >= 0 && c == diag_col0 + r) v += diag_add;
+  out[i] = v;
+}
+
+static void probe_free(plm_probe* pr) {
+  if (!pr) return;
+  cudaFree(pr->x); cudaFree(pr->p); cudaFree(pr->g); cudaFree(pr->J); cudaFree(pr->map);
+  if (pr->h) plm_destroy(pr->h);
+  delete pr;
+}
+
+void plm_dyn_free(plm_handle* h) {
+  for (int k = 0; k < 5; ++k) { probe_free(h->probes[k]); h->probes[k] = nullptr; }
+}
+
+// Lazily create the probe of one formulation; row0/nrows select the rows whose Jacobian is exported, `cols` lists the
+// local columns (node-0 block of x) of the exported Jacobian.
+static int get_probe(plm_handle* h, int dynamics, plm_probe** out) {
+  if (h->is_probe) { h->error = "probe handles do not nest"; return 10; }
+  if (h->probes[dynamics]) { *out = h->probes[dynamics]; return 0; }
+  const PlmModel& M = h->host.model;
+  std::vector<double> placement(12 * M.nbody), axis(3 * M.nbody), inertia(10 * M.nbody), coff(3 * M.ncontact);
+  std::vector<int32_t> parent(M.nbody), cbody(M.ncontact);
+  for (int b = 0; b < M.nbody; ++b) {
+    parent[b] = M.parent[b];
+    for (int i = 0; i < 9; ++i) placement[12 * b + i] = M.place_R[b][i];
+    for (int i = 0; i < 3; ++i) { placement[12 * b + 9 + i] = M.place_p[b][i]; axis[3 * b + i] = M.axis[b][i]; inertia[10 * b + 1 + i] = M.com[b][i]; }
+    inertia[10 * b] = M.mass[b];
+    for (int i = 0; i < 6; ++i) inertia[10 * b + 4 + i] = M.Ic[b][i];
+  }
+  for (int k = 0; k < M.ncontact; ++k) { cbody[k] = M.contact_body[k]; for (int i = 0; i < 3; ++i) coff[3 * k + i] = M.contact_off[k][i]; }
+  plm_robot_desc rd;
+  memset(&rd, 0, sizeof(rd));
+  rd.nbody = M.nbody; rd.parent = parent.data(); rd.placement = placement.data(); rd.axis = axis.data(); rd.inertia = inertia.data();
+  rd.nfeet = M.nfeet; rd.has_ext_force = M.has_ext; rd.contact_body = cbody.data(); rd.contact_offset = coff.data();
+  rd.arm_body = M.arm_body;
+  for (int i = 0; i < 3; ++i) rd.arm_offset[i] = M.arm_off[i];
+  rd.joint_pos_min = M.joint_pos_min; rd.joint_pos_max = M.joint_pos_max; rd.joint_vel_max = M.joint_vel_max;
+  rd.joint_torque_max = M.joint_torque_max; rd.q0 = M.q0;
+  plm_ocp_desc od = h->ocp;
+  od.dynamics = dynamics; od.nodes = 2; od.tau_nodes = 2;
+  plm_probe* pr = new plm_probe();
+  int rc = plm_create(&rd, &od, h->max_batch, &pr->h);
+  if (rc) { h->error = std::string("probe: ") + (pr->h ? pr->h->error : "alloc"); probe_free(pr); return rc; }
+  pr->h->is_probe = 1;
+  const PlmLayout& L = pr->h->host.layout;
+  const size_t B = (size_t)h->max_batch;
+  DYN_CUDA(h, cudaMalloc(&pr->x, B * L.n * 8));
+  DYN_CUDA(h, cudaMalloc(&pr->p, B * L.np * 8));
+  DYN_CUDA(h, cudaMalloc(&pr->g, B * L.m * 8));
+  DYN_CUDA(h, cudaMalloc(&pr->J, B * L.nnz * 8));
+  h->probes[dynamics] = pr;
+  *out = pr;
+  return 0;
+}
+
+// Build / upload the (row, col) -> J position map for rows [row0, row0 + nrows) of node `node` and the given local columns.
+static int set_map(plm_handle* h, plm_probe* pr, int node, int row0, int nrows, const std::vector<int>& cols) {
+  const HostTables& T = pr->h->host;
+  const PlmLayout& L = T.layout;
+  std::vector<int32_t> map((size_t)nrows * cols.size(), -1);
+  std::vector<int> colpos(L.n + 1, -1);
+  for (size_t c = 0; c < cols.size(); ++c) colpos[L.x_off[node] + cols[c]] = (int)c;
+  const int gr0 = L.row_off[node] + row0;
+  for (size_t e = 0; e < T.pat_rows.size(); ++e) {
+    const int r = T.pat_rows[e] - gr0;
+    if (r < 0 || r >= nrows) continue;
+    const int c = colpos[T.pat_cols[e]];
+    if (c >= 0) map[(size_t)r * cols.size() + c] = (int32_t)e;
+  }
+  if (pr->map) cudaFree(pr->map);
+  DYN_CUDA(h, cudaMalloc(&pr->map, map.size() * sizeof(int32_t)));
+  DYN_CUDA(h, cudaMemcpy(pr->map, map.data(), map.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  pr->rows_out = nrows;
+  pr->cols_out = (int)cols.size();
+  return 0;
+}
+
+static int run_probe(plm_handle* h, plm_probe* pr, int batch, const double* xa, int nxa, const double* xb, int nxb,
+                     const double* ua, int nua, const double* ub, int nub, int want_jac, cudaStream_t s) {
+  const PlmLayout& L = pr->h->host.layout;
+  probe_pack_kernel<<<batch, 128, 0, s>>>(batch, L.n, L.np, pr->x, pr->p, L.p_x_init, nxa, xa, nxb, xb, L.ndx, nua, ua, nub, ub,
+                                          L.p_dt_min, L.p_dt_max, L.p_n_contacts, L.p_swing_period, L.p_contact, 4 * L.nodes);
+  PLM_LAUNCH_CHECK(h);
+  int rc = plm_launch_node_eval(pr->h, pr->x, pr->p, batch, pr->g, pr->J, want_jac, s);
+  if (rc) { h->error = pr->h->error; return rc; }
+  h->launches++;
+  return 0;
+}
+
+static int emit_rows(plm_handle* h, plm_probe* pr, int batch, int node, int row0, int nrows, double sign, double* out, cudaStream_t s) {
+  const PlmLayout& L = pr->h->host.layout;
+  probe_rows_kernel<<<(batch * nrows + 127) / 128, 128, 0, s>>>(batch, L.m, L.row_off[node] + row0, nrows, sign, pr->g, out);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+static int emit_jac(plm_handle* h, plm_probe* pr, int batch, double sign, int diag_col0, double diag_add, double* out, cudaStream_t s) {
+  const PlmLayout& L = pr->h->host.layout;
+  const long long tot = (long long)batch * pr->rows_out * pr->cols_out;
+  probe_jac_kernel<<<(int)((tot + 127) / 128), 128, 0, s>>>(batch, L.nnz, pr->rows_out, pr->cols_out, pr->map, sign, diag_col0, diag_add, pr->J, out);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+static std::vector<int> cols_qvaf(const PlmLayout& L, int nv, int lead) {
+  std::vector<int> c;
+  for (int i = 0; i < nv; ++i) c.push_back(i);                  // dq (tangent)
+  for (int i = 0; i < nv; ++i) c.push_back(nv + i);             // dv
+  for (int i = 0; i < lead; ++i) c.push_back(L.ndx + i);        // a (or tau_j)
+  for (int i = 0; i < L.nf; ++i) c.push_back(L.ndx + L.f_idx + i);
+  return c;
+}
+
+extern "C" {
+
+int plm_rnea_dyn(plm_handle* h, const double* d_q, const double* d_v, const double* d_a, const double* d_forces, int32_t batch,
+                 double* d_tau, double* d_jac, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  plm_probe* pr;
+  if (int rc = get_probe(h, PLM_WHOLE_BODY_RNEA, &pr)) return rc;
+  const PlmLayout& L = pr->h->host.layout;
+  const PlmModel& M = pr->h->host.model;
+  const PlmNodeType& T = L.types[L.node_type[0]];
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = run_probe(h, pr, batch, d_q, M.nq, d_v, M.nv, d_a, M.nv, d_forces, L.nf, d_jac != nullptr, s)) return rc;
+  // rows: tau[:6] (row_dyn) and tau[6:] - tau_j (row_tauj, tau_j = 0); they are consecutive
+  if (int rc = emit_rows(h, pr, batch, 0, T.row_dyn, M.nv, 1.0, d_tau, s)) return rc;
+  if (d_jac) {
+    if (pr->rows_out != M.nv) if (int rc = set_map(h, pr, 0, T.row_dyn, M.nv, cols_qvaf(L, M.nv, M.nv))) return rc;
+    if (int rc = emit_jac(h, pr, batch, 1.0, -1, 0.0, d_jac, s)) return rc;
+  }
+  return 0;
+}
+
+int plm_dyn_gaps(plm_handle* h, int32_t dynamics, const double* d_q, const double* d_v, const double* d_a, const double* d_forces,
+                 int32_t batch, double* d_gaps, double* d_jac, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  if (dynamics != PLM_CENTROIDAL_ACC && dynamics != PLM_WHOLE_BODY_ACC) { h->error = "plm_dyn_gaps: centroidal_acc or whole_body_acc"; return 11; }
+  plm_probe* pr;
+  if (int rc = get_probe(h, dynamics, &pr)) return rc;
+  const PlmLayout& L = pr->h->host.layout;
+  const PlmModel& M = pr->h->host.model;
+  const PlmNodeType& T = L.types[L.node_type[0]];
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = run_probe(h, pr, batch, d_q, M.nq, d_v, M.nv, d_a, M.nv, d_forces, L.nf, d_jac != nullptr, s)) return rc;
+  if (int rc = emit_rows(h, pr, batch, 0, T.row_dyn, 6, 1.0, d_gaps, s)) return rc;
+  if (d_jac) {
+    if (pr->rows_out != 6) if (int rc = set_map(h, pr, 0, T.row_dyn, 6, cols_qvaf(L, M.nv, M.nv))) return rc;
+    if (int rc = emit_jac(h, pr, batch, 1.0, -1, 0.0, d_jac, s)) return rc;
+  }
+  return 0;
+}
+
+int plm_aba_dyn(plm_handle* h, const double* d_q, const double* d_v, const double* d_tau_j, const double* d_forces, int32_t batch,
+                double* d_a, double* d_jac, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  plm_probe* pr;
+  if (int rc = get_probe(h, PLM_WHOLE_BODY_ABA, &pr)) return rc;
+  const PlmLayout& L = pr->h->host.layout;
+  const PlmModel& M = pr->h->host.model;
+  const PlmNodeType& T = L.types[L.node_type[0]];
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = run_probe(h, pr, batch, d_q, M.nq, d_v, M.nv, d_tau_j, M.nj, d_forces, L.nf, d_jac != nullptr, s)) return rc;
+  // rows dv_next - (dv + a dt) with dv = dv_next = 0, dt = 1  =>  a = -row ; d a / d v = -(entry) - I
+  if (int rc = emit_rows(h, pr, batch, 0, T.row_int + M.nv, M.nv, -1.0, d_a, s)) return rc;
+  if (d_jac) {
+    if (pr->rows_out != M.nv) if (int rc = set_map(h, pr, 0, T.row_int + M.nv, M.nv, cols_qvaf(L, M.nv, M.nj))) return rc;
+    if (int rc = emit_jac(h, pr, batch, -1.0, M.nv, -1.0, d_jac, s)) return rc;
+  }
+  return 0;
+}
+
+int plm_centroidal_vel_gaps(plm_handle* h, const double* d_h, const double* d_q, const double* d_v, int32_t batch, double* d_gaps, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  plm_probe* pr;
+  if (int rc = get_probe(h, PLM_CENTROIDAL_VEL, &pr)) return rc;
+  const PlmLayout& L = pr->h->host.layout;
+  const PlmModel& M = pr->h->host.model;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = run_probe(h, pr, batch, d_h, 6, d_q, M.nq, d_v, M.nv, nullptr, L.nf, 0, s)) return rc;
+  return emit_rows(h, pr, batch, 0, L.types[L.node_type[0]].row_dyn, 6, 1.0, d_gaps, s);
+}
+
+int plm_com_dyn(plm_handle* h, const double* d_q, const double* d_forces, int32_t batch, double* d_dh, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  plm_probe* pr;
+  if (int rc = get_probe(h, PLM_CENTROIDAL_VEL, &pr)) return rc;
+  const PlmLayout& L = pr->h->host.layout;
+  const PlmModel& M = pr->h->host.model;
+  cudaStream_t s = (cudaStream_t)stream;
+  // x_init = [h = 0 | q], U_0 = [v = 0 | forces]; rows dh_next - (dh + h_dot dt) with dh = dh_next = 0, dt = 1  =>  h_dot = -row
+  if (int rc = run_probe(h, pr, batch, nullptr, 6, d_q, M.nq, nullptr, M.nv, d_forces, L.nf, 0, s)) return rc;
+  return emit_rows(h, pr, batch, 0, L.types[L.node_type[0]].row_int, 6, -1.0, d_dh, s);
+}
+
+int plm_frame_vel(plm_handle* h, int32_t contact, int32_t relative_to_base, const double* d_q, const double* d_v, int32_t batch,
+                  double* d_vel, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  plm_probe* pr;
+  if (int rc = get_probe(h, PLM_WHOLE_BODY_RNEA, &pr)) return rc;
+  const PlmLayout& L = pr->h->host.layout;
+  const PlmModel& M = pr->h->host.model;
+  const PlmNodeType& T = L.types[L.node_type[1]];      // node 1 carries the state rows
+  int row0;
+  if (!relative_to_base && contact >= 0 && contact < M.nfeet) row0 = T.row_foot[contact] + 5;
+  else if (relative_to_base && contact == -1 && T.row_arm >= 0) row0 = T.row_arm;
+  else { h->error = "plm_frame_vel: foot frames (world-aligned) or the arm frame (base-relative) only"; return 11; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = run_probe(h, pr, batch, d_q, M.nq, d_v, M.nv, nullptr, M.nv, nullptr, L.nf, 0, s)) return rc;
+  return emit_rows(h, pr, batch, 1, row0, 3, 1.0, d_vel, s);
+}
+
+__global__ void state_integrate_kernel(int batch, int nq, int nv, int cvel, const double* __restrict__ x, const double* __restrict__ dx,
+                                       double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int nx = cvel ? 6 + nq : nq + nv, ndx = cvel ? 6 + nv : 2 * nv, qo = cvel ? 6 : 0;
+  const double* xb = x + (size_t)b * nx;
+  const double* db = dx + (size_t)b * ndx;
+  double* ob = out + (size_t)b * nx;
+  se3_integrate(xb + qo, xb + qo + 3, db + qo, ob + qo, ob + qo + 3);
+  for (int j = 0; j < nq - 7; ++j) ob[qo + 7 + j] = xb[qo + 7 + j] + db[qo + 6 + j];
+  if (cvel) { for (int i = 0; i < 6; ++i) ob[i] = xb[i] + db[i]; }
+  else { for (int i = 0; i < nv; ++i) ob[nq + i] = xb[nq + i] + db[nv + i]; }
+}
+
+__global__ void state_difference_kernel(int batch, int nq, int nv, int cvel, const double* __restrict__ x0, const double* __restrict__ x1,
+                                        double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int nx = cvel ? 6 + nq : nq + nv, ndx = cvel ? 6 + nv : 2 * nv, qo = cvel ? 6 : 0;
+  const double* a = x0 + (size_t)b * nx;
+  const double* c = x1 + (size_t)b * nx;
+  double* ob = out + (size_t)b * ndx;
+  se3_difference(a + qo, a + qo + 3, c + qo, c + qo + 3, ob + qo);
+  for (int j = 0; j < nq - 7; ++j) ob[qo + 6 + j] = c[qo + 7 + j] - a[qo + 7 + j];
+  if (cvel) { for (int i = 0; i < 6; ++i) ob[i] = c[i] - a[i]; }
+  else { for (int i = 0; i < nv; ++i) ob[nv + i] = c[nq + i] - a[nq + i]; }
+}
+
+int plm_state_integrate(plm_handle* h, const double* d_x, const double* d_dx, int32_t batch, double* d_x_next, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  const PlmModel& M = h->host.model;
+  state_integrate_kernel<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(batch, M.nq, M.nv, h->host.layout.dynamics == PLM_CENTROIDAL_VEL, d_x, d_dx, d_x_next);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int plm_state_difference(plm_handle* h, const double* d_x0, const double* d_x1, int32_t batch, double* d_dx, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  const PlmModel& M = h->host.model;
+  state_difference_kernel<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(batch, M.nq, M.nv, h->host.layout.dynamics == PLM_CENTROIDAL_VEL, d_x0, d_x1, d_dx);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+}  // extern "C"

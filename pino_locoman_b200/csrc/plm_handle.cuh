@@ -29,6 +29,8 @@ struct LsWork {
 };
 }  // namespace plm
 
+struct plm_probe;
+
 struct plm_handle {
   plm::HostTables host;
   plm_ocp_desc ocp;
@@ -53,6 +55,9 @@ struct plm_handle {
   int scale_stage_A = 0;      // J values of one instance fit in shared memory during the Ruiz passes
   // line search / SQP step workspaces, timing
   plm::LsWork ls;
+  // lazily created two-node probe problems backing the Dynamics* entry points (one per formulation)
+  plm_probe* probes[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int is_probe = 0;
   int qp_setup_done = 0;
   int sqp_alloc_done = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -71,6 +76,7 @@ int plm_line_search_impl(plm_handle* h, const double* x, const double* p, const 
                          const double* lbg, const double* ubg, double* x_new, cudaStream_t s);
 int plm_launch_bounds_shift(plm_handle* h, int batch, const double* g, const double* lbg, const double* ubg, double* l, double* u, cudaStream_t s);
 int plm_launch_stats(plm_handle* h, int batch, const int* iters, const int* status, double* stats, cudaStream_t s);
+void plm_dyn_free(plm_handle* h);
 int plm_qp_alloc(plm_handle* h);
 int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream_t s);
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J, const double* d_l, const double* d_u, cudaStream_t s);

@@ -158,40 +158,6 @@ __global__ void bounds_kernel(DeviceTables tab, const double* __restrict__ p, in
   }
 }
 
-// SE(3) logarithm of M0^-1 M1 from positions and unit quaternions [x,y,z,w]  (pin.difference, base part)
-__device__ inline void se3_difference(const double* p0, const double* q0, const double* p1, const double* q1, double* nu) {
-  // relative quaternion qr = conj(q0) * q1
-  double ax = -q0[0], ay = -q0[1], az = -q0[2], aw = q0[3];
-  double bx = q1[0], by = q1[1], bz = q1[2], bw = q1[3];
-  double qr[4] = {aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
-                  aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz};
-  if (qr[3] < 0) { qr[0] = -qr[0]; qr[1] = -qr[1]; qr[2] = -qr[2]; qr[3] = -qr[3]; }
-  double n = sqrt(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2]);
-  double w[3];
-  if (n < 1e-12) {
-    double s = 2.0 / qr[3];
-    w[0] = s * qr[0]; w[1] = s * qr[1]; w[2] = s * qr[2];
-  } else {
-    double s = 2.0 * atan2(n, qr[3]) / n;
-    w[0] = s * qr[0]; w[1] = s * qr[1]; w[2] = s * qr[2];
-  }
-  double R0[9], d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, pl[3];
-  quat_to_R(q0, R0);
-  matTvec3(R0, d, pl);
-  double t2 = dot3(w, w), beta;
-  if (t2 < 1e-2) beta = 1.0 / 12 + t2 / 720 + t2 * t2 / 30240 + t2 * t2 * t2 / 1209600;
-  else {
-    double t = sqrt(t2);
-    beta = 1.0 / t2 - (1.0 + cos(t)) / (2.0 * t * sin(t));
-  }
-  // Vinv p = p - 0.5 w x p + beta w x (w x p)
-  double wp[3], wwp[3];
-  cross3(w, pl, wp);
-  cross3(w, wp, wwp);
-  for (int i = 0; i < 3; ++i) nu[i] = pl[i] - 0.5 * wp[i] + beta * wwp[i];
-  nu[3] = w[0]; nu[4] = w[1]; nu[5] = w[2];
-}
-
 // Per-instance tracking targets (setup_targets of each ocp_*.py): tgt[b][0:ndx] = dx_des, tgt[b][ndx:ndx+nu0] = u_des
 __global__ void targets_kernel(DeviceTables tab, const double* __restrict__ p, int batch, double* __restrict__ tgt, int tgt_ld) {
   const PlmModel& M = *tab.model;

@@ -132,4 +132,66 @@ PLM_HD void quat_to_R(const double* q, double* R) {
   R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
 }
 
+// SE(3) logarithm of M0^-1 M1 from positions and unit quaternions [x,y,z,w]  (pin.difference, base part)
+PLM_HD void se3_difference(const double* p0, const double* q0, const double* p1, const double* q1, double* nu) {
+  // relative quaternion qr = conj(q0) * q1
+  double ax = -q0[0], ay = -q0[1], az = -q0[2], aw = q0[3];
+  double bx = q1[0], by = q1[1], bz = q1[2], bw = q1[3];
+  double qr[4] = {aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                  aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz};
+  if (qr[3] < 0) { qr[0] = -qr[0]; qr[1] = -qr[1]; qr[2] = -qr[2]; qr[3] = -qr[3]; }
+  double n = sqrt(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2]);
+  double w[3];
+  if (n < 1e-12) {
+    double s = 2.0 / qr[3];
+    w[0] = s * qr[0]; w[1] = s * qr[1]; w[2] = s * qr[2];
+  } else {
+    double s = 2.0 * atan2(n, qr[3]) / n;
+    w[0] = s * qr[0]; w[1] = s * qr[1]; w[2] = s * qr[2];
+  }
+  double R0[9], d[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, pl[3];
+  quat_to_R(q0, R0);
+  matTvec3(R0, d, pl);
+  double t2 = dot3(w, w), beta;
+  if (t2 < 1e-2) beta = 1.0 / 12 + t2 / 720 + t2 * t2 / 30240 + t2 * t2 * t2 / 1209600;
+  else {
+    double t = sqrt(t2);
+    beta = 1.0 / t2 - (1.0 + cos(t)) / (2.0 * t * sin(t));
+  }
+  // Vinv p = p - 0.5 w x p + beta w x (w x p)
+  double wp[3], wwp[3];
+  cross3(w, pl, wp);
+  cross3(w, wp, wwp);
+  for (int i = 0; i < 3; ++i) nu[i] = pl[i] - 0.5 * wp[i] + beta * wwp[i];
+  nu[3] = w[0]; nu[4] = w[1]; nu[5] = w[2];
+}
+
+
+// pin.integrate on SE(3): (p, quat) * exp6([rho; w]); quaternion [x,y,z,w], renormalised
+PLM_HD void se3_integrate(const double* p0, const double* q0, const double* nu, double* p1, double* q1) {
+  const double* rho = nu;
+  const double* w = nu + 3;
+  double A, B, C;
+  const double t2 = dot3(w, w);
+  exp_coeffs(t2, &A, &B, &C);
+  double wr[3], wwr[3], pl[3], R0[9], pw[3];
+  cross3(w, rho, wr);
+  cross3(w, wr, wwr);
+  for (int i = 0; i < 3; ++i) pl[i] = rho[i] + B * wr[i] + C * wwr[i];     // V(w) rho
+  quat_to_R(q0, R0);
+  matvec3(R0, pl, pw);
+  for (int i = 0; i < 3; ++i) p1[i] = p0[i] + pw[i];
+  // quaternion of Exp(w): [sin(t/2)/t w, cos(t/2)] with sin(t/2)/t = 0.5 * sinc(t/2)
+  double Ah, Bh, Ch;
+  exp_coeffs(0.25 * t2, &Ah, &Bh, &Ch);
+  const double s = 0.5 * Ah, c = 1.0 - 0.25 * t2 * Bh;
+  const double e[4] = {s * w[0], s * w[1], s * w[2], c};
+  double r[4] = {q0[3] * e[0] + q0[0] * e[3] + q0[1] * e[2] - q0[2] * e[1],
+                 q0[3] * e[1] - q0[0] * e[2] + q0[1] * e[3] + q0[2] * e[0],
+                 q0[3] * e[2] + q0[0] * e[1] - q0[1] * e[0] + q0[2] * e[3],
+                 q0[3] * e[3] - q0[0] * e[0] - q0[1] * e[1] - q0[2] * e[2]};
+  const double nrm = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+  for (int i = 0; i < 4; ++i) q1[i] = r[i] / nrm;
+}
+
 }  // namespace plm

@@ -164,6 +164,7 @@ class Robot:
     def __init__(self, urdf_path, srdf_path, reference_pose, lock_joints=None):
         self.tree = KinematicTree(urdf_path, tuple(lock_joints or ()))
         self.model = self.tree          # the tables play the role of pin.Model
+        self.tree.robot = self          # Dynamics*(robot.model, mass, foot_frames) finds the limits / frames here
         if srdf_path and reference_pose:
             self.q0 = self.tree.reference_configuration(srdf_path, reference_pose)
         else:
