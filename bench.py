@@ -211,6 +211,7 @@ def main():
     from pino_locoman_b200 import OCP_ARGS
     from pino_locoman_b200.handle import _ptr
     from pino_locoman_b200.optimization import make_ocp
+    from pino_locoman_b200.sharding import gather_instance_results
     from pino_locoman_b200.utils.robot import B2G
 
     if not torch.cuda.is_available():
@@ -231,7 +232,6 @@ def main():
     p = torch.from_numpy(p_host).to(dev)
     x_new = torch.empty_like(x)
     stats = torch.empty(B, 8, dtype=torch.float64, device=dev)
-    cost_gather = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -242,7 +242,7 @@ def main():
         nonlocal x, x_new
         h.sqp_step(x, p, x_new, stats)
         if world > 1:   # the only exchange of the path: per-instance costs to every rank
-            dist.all_gather(cost_gather, stats[:, 5].contiguous())
+            gather_instance_results(stats[:, 5].contiguous(), B * world)
         x, x_new = x_new, x
 
     # ---- device-resident timing
