@@ -398,6 +398,9 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     std::stable_sort(rperm.begin(), rperm.end(), [&](int a, int b) { return rptr[a + 1] - rptr[a] > rptr[b + 1] - rptr[b]; });
     std::stable_sort(cperm.begin(), cperm.end(), [&](int a, int b) { return tptr[a + 1] - tptr[a] > tptr[b + 1] - tptr[b]; });
     Q.f_rperm = push(rperm); Q.f_cperm = push(cperm);
+    Q.n_long_rows = Q.n_long_cols = 0;
+    for (int r : rperm) if (rptr[r + 1] - rptr[r] >= PLM_LONG) Q.n_long_rows++;
+    for (int j : cperm) if (tptr[j + 1] - tptr[j] >= PLM_LONG) Q.n_long_cols++;
   }
   Q.smax = 0;
   int fo = 0;
@@ -409,6 +412,35 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   }
   Q.fac_off[N + 1] = fo;
   Q.fac_total = fo;
+  {
+    // panel schedule: forward sweep stages 0..N, backward sweep stages N..0, each stage cut into row panels
+    std::vector<int> sched;
+    auto add_stage = [&](int i, int dir) {
+      const int s = (i < N) ? ndx + nu[i] : ndx;
+      std::vector<int> cuts(1, 0);
+      int r = 0;
+      while (r < s) {
+        int r1 = r + 1;
+        while (r1 < s && (r1 + 1) * (r1 + 2) / 2 - r * (r + 1) / 2 <= PLM_PANEL_DOUBLES) ++r1;
+        cuts.push_back(r1);
+        r = r1;
+      }
+      for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        const int r0 = cuts[k], r1 = cuts[k + 1];
+        int o0 = r0 * (r0 + 1) / 2, o1 = r1 * (r1 + 1) / 2;
+        const int start = o0 & ~1;                       // 16-byte aligned start (stage blocks start even)
+        const int len = ((o1 - start) + 1) & ~1;
+        sched.push_back(Q.fac_off[i] + start); sched.push_back(len); sched.push_back(r0); sched.push_back(r1);
+        sched.push_back(i); sched.push_back(dir); sched.push_back(k == 0); sched.push_back(k + 2 == cuts.size());
+      }
+    };
+    for (int i = 0; i <= N; ++i) add_stage(i, 0);
+    for (int i = N; i >= 0; --i) add_stage(i, 1);
+    Q.n_sched = (int)sched.size() / PLM_SCHED_INTS;
+    Q.f_sched = (int)out.qp_idx32.size();
+    for (int v : sched) out.qp_idx32.push_back(v);
+    Q.panel_doubles = PLM_PANEL_DOUBLES + 2;
+  }
   Q.max_iter = ocp.osqp_max_iter; Q.check_termination = ocp.osqp_check_termination; Q.scaling = ocp.osqp_scaling;
   Q.rho = ocp.osqp_rho; Q.sigma = ocp.osqp_sigma; Q.alpha = ocp.osqp_alpha;
   Q.eps_abs = ocp.osqp_eps_abs; Q.eps_rel = ocp.osqp_eps_rel;

@@ -306,31 +306,77 @@ struct FlatIdx {
   const int16_t *rcol, *trow, *rperm, *cperm;
 };
 
-// out[r] = sum_k A_rk v[col]  for all rows (CSR order values), v indexed by global column
-__device__ __forceinline__ void spmv_rows(const FlatIdx& F, int m, const double* __restrict__ Ah, const double* v, double* out) {
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    const int r = F.rperm[i];       // rows of similar length share a warp
-    const int e0 = F.rptr[r], e1 = F.rptr[r + 1];
-    double a0 = 0.0, a1 = 0.0;
-    int e = e0;
-#pragma unroll 2
-    for (; e + 1 < e1; e += 2) { a0 += Ah[e] * v[F.rcol[e]]; a1 += Ah[e + 1] * v[F.rcol[e + 1]]; }
-    if (e < e1) a0 += Ah[e] * v[F.rcol[e]];
-    out[r] = a0 + a1;
+__device__ __forceinline__ double group8_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// Sparse products.  All global loads of a work item are issued before the first use (the SM issues in order: a
+// load that is consumed immediately serialises the DRAM latencies of the loop).
+#define SPMV_B 6   // entries fetched per lane and batch
+__device__ __forceinline__ double dot_batch(const double* __restrict__ vals, const int16_t* __restrict__ ind, int e0, int e1, int stride,
+                                            const double* v) {
+  double acc = 0.0;
+  for (int e = e0; e < e1; e += SPMV_B * stride) {
+    double a[SPMV_B];
+    int c[SPMV_B];
+#pragma unroll
+    for (int j = 0; j < SPMV_B; ++j) {
+      const int ee = e + j * stride;
+      const bool ok = ee < e1;
+      a[j] = ok ? __ldg(vals + ee) : 0.0;
+      c[j] = ok ? (int)__ldg(ind + ee) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < SPMV_B; ++j) acc += a[j] * v[c[j]];
+  }
+  return acc;
+}
+
+// out[r] = sum_k A_rk v[col]  for all rows (CSR order values), v indexed by global column.
+// Rows are visited in order of decreasing length: the long ones by 8-lane groups (coalesced value / index loads),
+// the short ones one per thread.
+__device__ __forceinline__ void spmv_rows(const FlatIdx& F, int m, int nlong, const double* __restrict__ Ah, const double* v, double* out) {
+  const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7, ngrp = blockDim.x >> 3;
+  for (int i0 = 0; i0 < nlong; i0 += ngrp) {
+    const int i = i0 + grp;
+    double acc = 0.0;
+    int r = 0;
+    if (i < nlong) {
+      r = F.rperm[i];
+      acc = dot_batch(Ah, F.rcol, F.rptr[r] + l8, F.rptr[r + 1], 8, v);
+    }
+    acc = group8_sum(acc);
+    if (i < nlong && l8 == 0) out[r] = acc;
+  }
+  for (int i = nlong + threadIdx.x; i < m; i += blockDim.x) {
+    const int r = F.rperm[i];
+    out[r] = dot_batch(Ah, F.rcol, F.rptr[r], F.rptr[r + 1], 1, v);
   }
 }
 
-// out[j] = sum_r A_rj w[r]  for all columns (CSC order values)
-__device__ __forceinline__ void spmv_cols(const FlatIdx& F, int n, const double* __restrict__ AT, const double* w, double* out) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+// out[j] = sum_r A_rj w[r] + sigma x[j] - q[j]  for all columns (CSC order values)
+__device__ __forceinline__ void spmv_cols(const FlatIdx& F, int n, int nlong, const double* __restrict__ AT, const double* w, double* out,
+                                          double sigma, const double* __restrict__ x, const double* __restrict__ q) {
+  const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7, ngrp = blockDim.x >> 3;
+  for (int i0 = 0; i0 < nlong; i0 += ngrp) {
+    const int i = i0 + grp;
+    double acc = 0.0, add = 0.0;
+    int j = 0;
+    if (i < nlong) {
+      j = F.cperm[i];
+      if (l8 == 0) add = sigma * __ldg(x + j) - __ldg(q + j);
+      acc = dot_batch(AT, F.trow, F.tptr[j] + l8, F.tptr[j + 1], 8, w);
+    }
+    acc = group8_sum(acc);
+    if (i < nlong && l8 == 0) out[j] = acc + add;
+  }
+  for (int i = nlong + threadIdx.x; i < n; i += blockDim.x) {
     const int j = F.cperm[i];
-    const int e0 = F.tptr[j], e1 = F.tptr[j + 1];
-    double a0 = 0.0, a1 = 0.0;
-    int e = e0;
-#pragma unroll 2
-    for (; e + 1 < e1; e += 2) { a0 += AT[e] * w[F.trow[e]]; a1 += AT[e + 1] * w[F.trow[e + 1]]; }
-    if (e < e1) a0 += AT[e] * w[F.trow[e]];
-    out[j] = a0 + a1;
+    const double add = sigma * __ldg(x + j) - __ldg(q + j);
+    out[j] = dot_batch(AT, F.trow, F.tptr[j], F.tptr[j + 1], 1, w) + add;
   }
 }
 
@@ -361,72 +407,73 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// Triangular mat-vecs on a packed lower-triangular block in shared memory.  The triangle is cut into NCH
-// column (row) chunks of ch = ceil(s/NCH); one work item = (row, column chunk) resp. (row chunk, column), at most ch
-// multiply-adds, one item per thread; partial sums are combined in a second short pass.  In-place use is allowed.
-#define ADMM_THREADS 512
-#define NCH 6
-// y = (sub ? sub - Linv r : Linv r)
-__device__ __forceinline__ void tri_matvec(const double* __restrict__ Lp, int s, const double* r, double* y, const double* sub,
-                                           double* part, int pld) {
-  const int ch = (s + NCH - 1) / NCH;
-  for (int id = threadIdx.x; id < ch * (NCH * (NCH + 1) / 2); id += blockDim.x) {
-    int g = 0, base = 0;
-    while (id >= base + ch * (g + 1)) { base += ch * (g + 1); ++g; }     // band g: rows [g ch, (g+1) ch), g+1 chunks each
-    const int rem = id - base, q = rem / (g + 1);
-    const int t = g * ch + q, c = rem - q * (g + 1);
-    if (t < s) {
-      const int k0 = c * ch, k1 = min(k0 + ch, t + 1);
-      const double* row = Lp + tri(t, 0);
-      double a0 = 0.0, a1 = 0.0;
-      int k = k0;
-#pragma unroll 4
-      for (; k + 1 < k1; k += 2) { a0 += row[k] * r[k]; a1 += row[k + 1] * r[k + 1]; }
-      if (k < k1) a0 += row[k] * r[k];
-      part[c * pld + t] = a0 + a1;
-    }
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < s; t += blockDim.x) {
-    double acc = part[t];
-    const int nc = t / ch;
-    for (int c = 1; c <= nc; ++c) acc += part[c * pld + t];
-    y[t] = sub ? sub[t] - acc : acc;
-  }
-}
-// x = Linv^T y
-__device__ __forceinline__ void tri_matvec_t(const double* __restrict__ Lp, int s, const double* y, double* x, double* part, int pld) {
-  const int ch = (s + NCH - 1) / NCH;
-  // row chunk R covers rows [R ch, (R+1) ch) and columns k < min((R+1) ch, s)
-  int total = 0;
-  for (int R = 0; R < NCH; ++R) total += min((R + 1) * ch, s);
-  for (int id = threadIdx.x; id < total; id += blockDim.x) {
-    int R = 0, base = 0;
-    while (id >= base + min((R + 1) * ch, s)) { base += min((R + 1) * ch, s); ++R; }
-    const int k = id - base;
-    const int t0 = max(R * ch, k), t1 = min((R + 1) * ch, s);
-    double a0 = 0.0, a1 = 0.0;
-    int off = tri(t0, k);
-    int t = t0;
-#pragma unroll 4
-    for (; t + 1 < t1; t += 2) {
-      a0 += Lp[off] * y[t];
-      a1 += Lp[off + t + 1] * y[t + 1];
-      off += 2 * t + 3;
-    }
-    if (t < t1) a0 += Lp[off] * y[t];
-    part[R * pld + k] = a0 + a1;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < s; k += blockDim.x) {
+// The stage factors Linv_i (packed lower triangles, row-major) are streamed through shared memory in panels of
+// consecutive rows (<= 16 KB) by bulk asynchronous copies, NBUF panels deep, following a host-built schedule of one ADMM
+// iteration.  Both triangular products of a sweep step are row-streamable, so a panel is used once and dropped:
+//   forward  stage i: y_i = Linv_i r_i (rows of the panel), then tv += panel^T y_panel          (tv = Linv_i^T y_i)
+//   backward stage i: r = y_i - Linv_i g (rows of the panel), then xacc += panel^T r_panel      (x_i = Linv_i^T r)
+#define ADMM_THREADS 384
+#define ADMM_MIN_CTAS 2
+#define NBUF 3
+#define TRI_B 14     // a lane's share of a row: covers rows of up to 8 * 14 = 112 entries per pass
+#define COL_B 16     // rows fetched per batch in the transposed product
+
+// out[t] = (sub ? sub[t] - P r : P r)[t]  for the rows [r0, r1) held in the panel; eight lanes per row.
+__device__ __forceinline__ void panel_rows(const double* pan, int shift, int r0, int r1, const double* r, double* out, const double* sub) {
+  const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7, ngrp = blockDim.x >> 3;
+  for (int t0 = r0; t0 < r1; t0 += ngrp) {
+    const int t = t0 + grp;
     double acc = 0.0;
-    for (int R = k / ch; R < NCH; ++R)
-      if (R * ch < s) acc += part[R * pld + k];
-    x[k] = acc;
+    if (t < r1) {
+      const double* row = pan + (tri(t, 0) - shift);
+      for (int kb = 0; kb <= t; kb += 8 * TRI_B) {
+        double v[TRI_B];
+#pragma unroll
+        for (int j = 0; j < TRI_B; ++j) {
+          const int k = kb + l8 + 8 * j;
+          v[j] = (k <= t) ? row[k] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < TRI_B; ++j) {
+          const int k = kb + l8 + 8 * j;
+          if (k <= t) acc += v[j] * r[k];
+        }
+      }
+    }
+    acc = group8_sum(acc);
+    if (t < r1 && l8 == 0) out[t] = sub ? sub[t] - acc : acc;
   }
 }
 
-__global__ void __launch_bounds__(ADMM_THREADS)
+// acc[k] (+)= sum_{t in [r0, r1)} P[t][k] v[t]  for the columns k < r1; two threads per column (rows of equal parity).
+__device__ __forceinline__ void panel_cols(const double* pan, int shift, int r0, int r1, const double* v, double* acc_out, bool first) {
+  const int half = threadIdx.x & 1;
+  const int ncol2 = ((r1 + 15) & ~15);
+  for (int k = threadIdx.x >> 1; k < ncol2; k += blockDim.x >> 1) {
+    double acc = 0.0;
+    if (k < r1) {
+      const int tb0 = max(r0, k);
+      for (int tb = tb0 + half; tb < r1; tb += 2 * COL_B) {
+        double a[COL_B];
+#pragma unroll
+        for (int j = 0; j < COL_B; ++j) {
+          const int t = tb + 2 * j;
+          a[j] = (t < r1) ? pan[tri(t, k) - shift] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < COL_B; ++j) {
+          const int t = tb + 2 * j;
+          if (t < r1) acc += a[j] * v[t];
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    // rows above r0 never touch the columns >= r0: those start here; earlier columns accumulate across panels
+    if (k < r1 && half == 0) acc_out[k] = (first || k >= r0) ? acc : acc_out[k] + acc;
+  }
+}
+
+__global__ void __launch_bounds__(ADMM_THREADS, ADMM_MIN_CTAS)
 qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
                double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out) {
   extern __shared__ double sm[];
@@ -434,23 +481,22 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const QpLayout& Q = *Qp;
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
-  // double-buffered stage factors first (16-byte aligned for the bulk copies), then the mbarriers and the vectors
-  const int fpad = (smax * (smax + 1) / 2 + 1) & ~1;
-  double* fbuf[2] = {sm, sm + fpad};
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + 2 * fpad);
-  double* x = sm + 2 * fpad + 2;   // [n]
-  double* xt = x + n;          // [n]  rhs -> forward solution y -> x~
-  double* z = xt + n;          // [m]
-  double* y = z + m;           // [m]
-  double* w = y + m;           // [m]  rho z - y, then z~ = A x~
-  double* tv = w + m;          // [smax] Linv^T y of the previous stage / G^T x of the next stage
-  double* rv = tv + smax;      // [smax] stage right-hand side
-  double* part = rv + smax;    // [NCH][smax] partial sums of the triangular mat-vecs
-  double* red = part + NCH * smax; // [32]
+  const int pdb = Q.panel_doubles;
+  // panel buffers first (16-byte aligned), then the mbarriers, then the gathered vectors
+  double* pbuf = sm;                                   // [NBUF][pdb]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + NBUF * pdb);   // [NBUF] (+1 pad)
+  double* xt = sm + NBUF * pdb + NBUF + 1;   // [n]  rhs -> forward solution y -> x~ -> delta_x
+  double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
+  double* tv = w + m;          // [smax] Linv^T y of the current stage (forward) / G^T x of the next stage (backward)
+  double* rv = tv + smax;      // [smax] panel-row results
+  double* xa = rv + smax;      // [smax] accumulator of the transposed product in the backward sweep
+  double* red = xa + smax;     // [32]
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
   FlatIdx F;
   F.rptr = idx32 + Q.f_rptr; F.tptr = idx32 + Q.f_tptr; F.rcol = idx + Q.f_rcol; F.trow = idx + Q.f_trow; F.rperm = idx + Q.f_rperm; F.cperm = idx + Q.f_cperm;
+  const int32_t* sched = idx32 + Q.f_sched;
+  const int nsched = Q.n_sched;
   const double* Ph = W.Ph + (size_t)b * n;
   const double* qh = W.qh + (size_t)b * n;
   const double* lh = W.lh + (size_t)b * m;
@@ -460,141 +506,170 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const double* Ev = W.E + (size_t)b * m;
   const double* Lf = W.Linv + (size_t)b * Q.fac_total;
   const double cs = W.cscale[b];
-  double* xg = W.x + (size_t)b * n;
-  double* zg = W.z + (size_t)b * m;
-  double* yg = W.y + (size_t)b * m;
+  // persistent scaled iterates live in HBM: they are only streamed (element-wise), never gathered
+  double* x = W.x + (size_t)b * n;
+  double* z = W.z + (size_t)b * m;
+  double* y = W.y + (size_t)b * m;
   const double alpha = Q.alpha, sigma = Q.sigma;
-  for (int j = tid; j < n; j += nth) x[j] = xg[j];
-  for (int r = tid; r < m; r += nth) { z[r] = zg[r]; y[r] = yg[r]; }
-  // the sweeps visit the stage blocks as a triangle wave 0,1,..,N,N-1,..,1,0,1,..: `seq` counts distinct blocks
-  int cur = 0, seq = 0;
-  unsigned par[2] = {0u, 0u};
-  auto blk_of = [&](int d) { const int r = d % (2 * N); return N - abs(N - r); };
-  auto blk_bytes = [&](int blk) { return (unsigned)(((Q.fac_off[blk + 1] - Q.fac_off[blk]) * 8 + 15) & ~15); };
+  // ---- panel pipeline: `issued` / `used` count schedule steps modulo the per-iteration schedule
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int k = 0; k < NBUF; ++k) mbar_init(&bars[k], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bars[0], blk_bytes(0));
-    bulk_g2s(fbuf[0], Lf + Q.fac_off[0], blk_bytes(0), &bars[0]);
-    mbar_expect_tx(&bars[1], blk_bytes(1));
-    bulk_g2s(fbuf[1], Lf + Q.fac_off[1], blk_bytes(1), &bars[1]);
-  }
-  mbar_wait(&bars[0], par[0]);
-  par[0] ^= 1u;
-  // switch to the next distinct block (already in flight), then prefetch the one after it into the freed buffer.
-  // Callers guarantee a __syncthreads() since the last read of the current buffer.
-#define FAC_ADVANCE()                                                                   \
-  do {                                                                                  \
-    const int nxt = cur ^ 1;                                                            \
-    mbar_wait(&bars[nxt], par[nxt]);                                                    \
-    par[nxt] ^= 1u;                                                                     \
-    ++seq;                                                                              \
-    if (tid == 0) {                                                                     \
-      const int pb = blk_of(seq + 1);                                                   \
-      mbar_expect_tx(&bars[cur], blk_bytes(pb));                                        \
-      bulk_g2s(fbuf[cur], Lf + Q.fac_off[pb], blk_bytes(pb), &bars[cur]);               \
-    }                                                                                   \
-    cur = nxt;                                                                          \
-  } while (0)
+  long long issued = 0, used = 0;      // global step counters (uniform across the CTA)
+  auto issue_next = [&]() {            // thread 0 only
+    const int32_t* S = sched + (issued % nsched) * PLM_SCHED_INTS;
+    const int bi_ = (int)(issued % NBUF);
+    const unsigned bytes = (unsigned)S[1] * 8u;
+    mbar_expect_tx(&bars[bi_], bytes);
+    bulk_g2s(pbuf + (size_t)bi_ * pdb, Lf + S[0], bytes, &bars[bi_]);
+  };
+  if (tid == 0)
+    for (int k = 0; k < NBUF - 1; ++k) { issue_next(); ++issued; }
+  if (tid != 0) issued = NBUF - 1;
   int status = 0, it = 0;
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
   PROF_T0();
   for (it = 1; it <= Q.max_iter; ++it) {
     PROF_ADD(15);
     // ---- rhs = sigma x - q + A^T (rho z - y)
-    for (int r = tid; r < m; r += nth) w[r] = rho[r] * z[r] - y[r];
-    __syncthreads();
-    spmv_cols(F, n, AT, w, xt);
-    __syncthreads();
-    for (int j = tid; j < n; j += nth) xt[j] += sigma * x[j] - qh[j];
-    __syncthreads();
-    PROF_ADD(0);
-    // ---- forward sweep: y_i = Linv_i (b_i - G_{i-1} Linv_{i-1}^T y_{i-1})
-    for (int i = 0; i <= N; ++i) {
-      const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
-      double* bi = xt + L.x_off[i];
-      if (i > 0) {
-        const StageView sp = stage_view(L, Q, idx, i - 1);
-        const double* Ap = Ah + L.nnz_off[i - 1];
-        const double* rp = rho + L.row_off[i - 1];
-        for (int c2 = tid; c2 < ndx; c2 += nth) {
-          const int e1 = sp.rptr[c2 + 1] - 1;
-          double acc = 0.0;
-          for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tv[sp.ccol[e]];
-          bi[c2] -= rp[c2] * Ap[e1] * acc;
-        }
-        __syncthreads();
-        PROF_ADD(1);
-        FAC_ADVANCE();      // block i replaces block i-1
-        PROF_ADD(2);
+    for (int r0 = tid; r0 < m; r0 += 4 * nth) {
+      double a[4], c[4], d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j * nth;
+        const bool ok = r < m;
+        a[j] = ok ? __ldg(rho + r) : 0.0;
+        c[j] = ok ? z[r] : 0.0;
+        d[j] = ok ? y[r] : 0.0;
       }
-      const double* Lp = fbuf[cur];
-      tri_matvec(Lp, s, bi, bi, nullptr, part, smax);
-      __syncthreads();
-      PROF_ADD(3);
-      if (i < N) {
-        tri_matvec_t(Lp, s, bi, tv, part, smax);
-        __syncthreads();
-        PROF_ADD(4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j * nth;
+        if (r < m) w[r] = a[j] * c[j] - d[j];
       }
     }
-    // ---- backward sweep: x_i = Linv_i^T (y_i - Linv_i G_i^T x_{i+1})
-    for (int i = N; i >= 0; --i) {
+    __syncthreads();
+    spmv_cols(F, n, Q.n_long_cols, AT, w, xt, sigma, x, qh);
+    __syncthreads();
+    PROF_ADD(0);
+    // ---- forward and backward sweeps, one schedule step = one row panel of one stage factor
+    for (int st = 0; st < nsched; ++st) {
+      const int32_t* S = sched + st * PLM_SCHED_INTS;
+      const int r0 = S[2], r1 = S[3], i = S[4], dir = S[5], first = S[6], last = S[7];
       const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
-      double* yi = xt + L.x_off[i];
-      if (i < N) {
-        FAC_ADVANCE();      // block i replaces block i+1
-        PROF_ADD(2);
-        const StageView sv = stage_view(L, Q, idx, i);
-        const double* An = Ah + L.nnz_off[i];
-        const double* rh = rho + L.row_off[i];
-        const double* xn = xt + L.x_off[i + 1];
-        // tv = G_i^T x_{i+1}: column gather over the integrator rows (rows < ndx come first in every column)
-        for (int k = tid; k < s; k += nth) {
-          double acc = 0.0;
-          for (int e = sv.cptr[k]; e < sv.cptr[k + 1]; ++e) {
-            const int r = sv.crow[e];
-            if (r >= ndx) break;
-            const int e1 = sv.rptr[r + 1] - 1;
-            acc += An[sv.cpos[e]] * rh[r] * An[e1] * xn[r];
+      const int shift = S[0] - Q.fac_off[i];
+      double* bi = xt + L.x_off[i];
+      if (first) {
+        if (dir == 0) {
+          if (i > 0) {     // b_i -= G_{i-1} tv   (tv = Linv_{i-1}^T y_{i-1})
+            const StageView sp = stage_view(L, Q, idx, i - 1);
+            const double* Ap = Ah + L.nnz_off[i - 1];
+            const double* rp = rho + L.row_off[i - 1];
+            for (int c2 = tid; c2 < ndx; c2 += nth) {
+              const int e1 = sp.rptr[c2 + 1] - 1;
+              double acc = 0.0;
+              for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tv[sp.ccol[e]];
+              bi[c2] -= rp[c2] * Ap[e1] * acc;
+            }
+            __syncthreads();
           }
-          tv[k] = acc;
+          PROF_ADD(1);
+        } else if (i < N) {   // tv = G_i^T x_{i+1}: column gather over the integrator rows (rows < ndx come first)
+          const StageView sv = stage_view(L, Q, idx, i);
+          const double* An = Ah + L.nnz_off[i];
+          const double* rh = rho + L.row_off[i];
+          const double* xn = xt + L.x_off[i + 1];
+          for (int k = tid; k < s; k += nth) {
+            double acc = 0.0;
+            for (int e = sv.cptr[k]; e < sv.cptr[k + 1]; ++e) {
+              const int r = sv.crow[e];
+              if (r >= ndx) break;
+              const int e1 = sv.rptr[r + 1] - 1;
+              acc += An[sv.cpos[e]] * rh[r] * An[e1] * xn[r];
+            }
+            tv[k] = acc;
+          }
+          __syncthreads();
+          PROF_ADD(5);
         }
-        __syncthreads();
-        PROF_ADD(5);
-        tri_matvec(fbuf[cur], s, tv, rv, yi, part, smax);     // rv = y_i - Linv_i G_i^T x_{i+1}
-        __syncthreads();
-        PROF_ADD(3);
-        tri_matvec_t(fbuf[cur], s, rv, yi, part, smax);
-      } else {
-        tri_matvec_t(fbuf[cur], s, yi, yi, part, smax);
       }
+      // wait for the panel, multiply its rows
+      const int bsel = (int)(used % NBUF);
+      mbar_wait(&bars[bsel], (unsigned)((used / NBUF) & 1));
+      const double* pan = pbuf + (size_t)bsel * pdb;
+      PROF_ADD(2);
+      if (dir == 0) panel_rows(pan, shift, r0, r1, bi, rv, nullptr);                       // rv = y_i (rows of the panel)
+      else if (i < N) panel_rows(pan, shift, r0, r1, tv, rv, bi);                          // rv = y_i - Linv_i tv
+      else { for (int t = r0 + tid; t < r1; t += nth) rv[t] = bi[t]; }                     // terminal stage: r = y_N
       __syncthreads();
+      PROF_ADD(3);
+      // every thread is past the previous step's transposed product: its buffer may be refilled
+      if (tid == 0) issue_next();
+      ++issued;
+      // transposed product of the panel
+      if (dir == 0) { if (i < N) panel_cols(pan, shift, r0, r1, rv, tv, first != 0); }
+      else panel_cols(pan, shift, r0, r1, rv, xa, first != 0);
+      ++used;
+      if (last) {
+        __syncthreads();
+        if (dir == 0) { for (int k = tid; k < s; k += nth) bi[k] = rv[k]; }                // keep y_i for the backward sweep
+        else { for (int k = tid; k < s; k += nth) bi[k] = xa[k]; }                          // x_i
+        __syncthreads();
+      }
       PROF_ADD(4);
     }
     // ---- z~ = A x~ ; relaxation, projection, dual update
-    spmv_rows(F, m, Ah, xt, w);
+    spmv_rows(F, m, Q.n_long_rows, Ah, xt, w);
     __syncthreads();
     PROF_ADD(6);
     double mdx = 0.0;
-    for (int j = tid; j < n; j += nth) {
-      const double xn = alpha * xt[j] + (1.0 - alpha) * x[j];
-      mdx = fmax(mdx, fabs(Dv[j] * (xn - x[j])));
-      xt[j] = xn - x[j];          // delta_x (kept for the dual infeasibility test)
-      x[j] = xn;
+    for (int j0 = tid; j0 < n; j0 += 4 * nth) {
+      double xo[4], dv[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int j = j0 + q4 * nth;
+        const bool ok = j < n;
+        xo[q4] = ok ? x[j] : 0.0;
+        dv[q4] = ok ? __ldg(Dv + j) : 0.0;
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int j = j0 + q4 * nth;
+        if (j < n) {
+          const double xn = alpha * xt[j] + (1.0 - alpha) * xo[q4];
+          mdx = fmax(mdx, fabs(dv[q4] * (xn - xo[q4])));
+          xt[j] = xn - xo[q4];      // delta_x (kept for the dual infeasibility test)
+          x[j] = xn;
+        }
+      }
     }
-    for (int r = tid; r < m; r += nth) {
-      const double zr = alpha * w[r] + (1.0 - alpha) * z[r];
-      double zn = zr + y[r] / rho[r];
-      zn = fmin(fmax(zn, lh[r]), uh[r]);
-      const double dy = rho[r] * (zr - zn);
-      y[r] += dy;
-      z[r] = zn;
-      w[r] = dy;                  // delta_y (kept for the primal infeasibility test)
+    for (int r0 = tid; r0 < m; r0 += 4 * nth) {
+      double zo[4], yo[4], rr[4], lo[4], up[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int r = r0 + q4 * nth;
+        const bool ok = r < m;
+        zo[q4] = ok ? z[r] : 0.0;
+        yo[q4] = ok ? y[r] : 0.0;
+        rr[q4] = ok ? __ldg(rho + r) : 1.0;
+        lo[q4] = ok ? __ldg(lh + r) : 0.0;
+        up[q4] = ok ? __ldg(uh + r) : 0.0;
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int r = r0 + q4 * nth;
+        if (r < m) {
+          const double zr = alpha * w[r] + (1.0 - alpha) * zo[q4];
+          double zn = zr + yo[q4] / rr[q4];
+          zn = fmin(fmax(zn, lo[q4]), up[q4]);
+          const double dy = rr[q4] * (zr - zn);
+          y[r] = yo[q4] + dy;
+          z[r] = zn;
+          w[r] = dy;                // delta_y (kept for the primal infeasibility test)
+        }
+      }
     }
     __syncthreads();
     PROF_ADD(7);
@@ -608,35 +683,30 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (pass == 1 && it != Q.max_iter) break;
       const double kk = apx ? 10.0 : 1.0;
       const double eps_abs = Q.eps_abs * kk, eps_rel = Q.eps_rel * kk, eps_pinf = Q.eps_prim_inf * kk, eps_dinf = Q.eps_dual_inf * kk;
-      // primal residual: ||E^-1 (A x - z)||, norms of E^-1 z and E^-1 A x       (tv/rv/… are free: use global scratch-free passes)
+      // primal residual ||E^-1 (A x - z)||, norms of E^-1 z and E^-1 A x
       double pr = 0.0, nz = 0.0, nax = 0.0;
-      {
-        // A x row by row (no storage)
-        for (int r = tid; r < m; r += nth) {
-          double ax = 0.0;
-          for (int e = F.rptr[r]; e < F.rptr[r + 1]; ++e) ax += Ah[e] * x[F.rcol[e]];
-          const double ei = 1.0 / Ev[r];
-          pr = fmax(pr, fabs((ax - z[r]) * ei));
-          nz = fmax(nz, fabs(z[r] * ei));
-          nax = fmax(nax, fabs(ax * ei));
-        }
+      for (int r = tid; r < m; r += nth) {
+        double ax = 0.0;
+        for (int e = F.rptr[r]; e < F.rptr[r + 1]; ++e) ax += Ah[e] * x[F.rcol[e]];
+        const double ei = 1.0 / Ev[r];
+        pr = fmax(pr, fabs((ax - z[r]) * ei));
+        nz = fmax(nz, fabs(z[r] * ei));
+        nax = fmax(nax, fabs(ax * ei));
       }
       pr = block_reduce(pr, red, true);
       nz = block_reduce(nz, red, true);
       nax = block_reduce(nax, red, true);
-      // dual residual: ||D^-1 (P x + q + A^T y)|| / c
+      // dual residual ||D^-1 (P x + q + A^T y)|| / c
       double dr = 0.0, nq = 0.0, naty = 0.0, npx = 0.0;
-      {
-        for (int j = tid; j < n; j += nth) {
-          double acc = 0.0;
-          for (int e = F.tptr[j]; e < F.tptr[j + 1]; ++e) acc += AT[e] * y[F.trow[e]];
-          const double di = 1.0 / Dv[j];
-          const double px = Ph[j] * x[j];
-          dr = fmax(dr, fabs((px + qh[j] + acc) * di));
-          nq = fmax(nq, fabs(qh[j] * di));
-          naty = fmax(naty, fabs(acc * di));
-          npx = fmax(npx, fabs(px * di));
-        }
+      for (int j = tid; j < n; j += nth) {
+        double acc = 0.0;
+        for (int e = F.tptr[j]; e < F.tptr[j + 1]; ++e) acc += AT[e] * y[F.trow[e]];
+        const double di = 1.0 / Dv[j];
+        const double px = Ph[j] * x[j];
+        dr = fmax(dr, fabs((px + qh[j] + acc) * di));
+        nq = fmax(nq, fabs(qh[j] * di));
+        naty = fmax(naty, fabs(acc * di));
+        npx = fmax(npx, fabs(px * di));
       }
       dr = block_reduce(dr, red, true) / cs;
       nq = block_reduce(nq, red, true);
@@ -647,7 +717,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const bool prim_ok = pr < eps_pri, dual_ok = dr < eps_dua;
       bool prim_inf = false, dual_inf = false;
       if (!prim_ok) {
-        // primal infeasibility certificate on delta_y (w): project on the polar of the recession cone of [l,u]
+        // primal infeasibility certificate: delta_y (w) is projected in place on the polar of the recession cone of
+        // [l,u], exactly as osqp does with work->delta_y
         double ndy = 0.0, lhs = 0.0;
         for (int r = tid; r < m; r += nth) {
           double dy = w[r];
@@ -655,26 +726,17 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           if (up && lo) dy = 0.0;
           else if (up) dy = fmin(dy, 0.0);
           else if (lo) dy = fmax(dy, 0.0);
+          w[r] = dy;
           ndy = fmax(ndy, fabs(Ev[r] * dy));
           lhs += uh[r] * fmax(dy, 0.0) + lh[r] * fmin(dy, 0.0);
         }
-        ndy = block_reduce(ndy, red, true);
+        ndy = block_reduce(ndy, red, true);     // (barriers inside make w visible)
         lhs = block_reduce(lhs, red, false);
         if (ndy > eps_pinf && lhs < -eps_pinf * ndy) {
-          // ||D^-1 A^T dy_proj|| < eps ||dy||
-          for (int r = tid; r < m; r += nth) {
-            double dy = w[r];
-            const bool up = uh[r] > OSQP_INFTY * MIN_SCALING, lo = lh[r] < -OSQP_INFTY * MIN_SCALING;
-            if (up && lo) dy = 0.0;
-            else if (up) dy = fmin(dy, 0.0);
-            else if (lo) dy = fmax(dy, 0.0);
-            zg[r] = dy;     // global scratch (rewritten with z at exit)
-          }
-          __syncthreads();
           double na = 0.0;
           for (int j = tid; j < n; j += nth) {
             double acc = 0.0;
-            for (int e = F.tptr[j]; e < F.tptr[j + 1]; ++e) acc += AT[e] * zg[F.trow[e]];
+            for (int e = F.tptr[j]; e < F.tptr[j + 1]; ++e) acc += AT[e] * w[F.trow[e]];
             na = fmax(na, fabs(acc / Dv[j]));
           }
           na = block_reduce(na, red, true);
@@ -712,19 +774,17 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     PROF_ADD(8);
     if (status != 0) break;
   }
-  mbar_wait(&bars[cur ^ 1], par[cur ^ 1]);   // drain the prefetch that is still in flight
+  for (long long k = used; k < issued; ++k) mbar_wait(&bars[k % NBUF], (unsigned)((k / NBUF) & 1));   // drain prefetches in flight
   if (it > Q.max_iter) it = Q.max_iter;
   if (status == 0) status = -2;   // maximum iterations reached
   const bool no_solution = (status == 3 || status == -3 || status == 4 || status == -4);
   __syncthreads();
   for (int j = tid; j < n; j += nth) {
-    xg[j] = no_solution ? 0.0 : x[j];
     if (dx_out) dx_out[(size_t)b * n + j] = no_solution ? nan("") : Dv[j] * x[j];
+    if (no_solution) x[j] = 0.0;      // store_solution(): no solution -> cold start
   }
-  for (int r = tid; r < m; r += nth) {
-    zg[r] = no_solution ? 0.0 : z[r];
-    yg[r] = no_solution ? 0.0 : y[r];
-  }
+  if (no_solution)
+    for (int r = tid; r < m; r += nth) { z[r] = 0.0; y[r] = 0.0; }
   if (tid == 0) {
     if (iters_out) iters_out[b] = it;
     if (status_out) status_out[b] = status;
@@ -776,7 +836,7 @@ int plm_qp_alloc(plm_handle* h) {
   h->scale_stage_A = (h->smem_scale + (size_t)L.nnz * 8 <= 200 * 1024) ? 1 : 0;
   if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
   h->smem_factor = (size_t)(smax * (smax + 1) + smax * ndx + ndx * ndx + ndx + 2 * smax + L.max_nnz + L.max_rows) * 8;
-  h->smem_admm = (size_t)(2 * L.n + 3 * L.m + (2 + NCH) * smax + 32 + 2 * ((smax * (smax + 1) / 2 + 1) & ~1) + 4) * 8;
+  h->smem_admm = (size_t)(NBUF * Q.panel_doubles + NBUF + 1 + L.n + L.m + 3 * smax + 32) * 8;
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
     return 7;

@@ -6,6 +6,13 @@
 
 namespace plm {
 
+// A stage factor (packed lower triangle, row-major) is streamed through shared memory in panels of consecutive rows.
+#define PLM_PANEL_DOUBLES 2048        // 16 KB
+// schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage, direction
+// (0 forward, 1 backward), first panel of the stage, last panel of the stage}
+#define PLM_SCHED_INTS 8
+#define PLM_LONG 8   // rows / columns with at least this many entries are multiplied by an 8-lane group
+
 // Per node-type local sparsity tables (offsets into one int16 pool).  Local columns of a node block are
 // [0, s) = this stage (DX_i | U_i) and [s, s + ndx) = DX_{i+1}; local rows are the node's rows in g order.
 struct QpTypeIdx {
@@ -23,7 +30,10 @@ struct QpLayout {
   // flat (whole-problem) index tables, offsets into the int32 pool: CSR row pointers, CSC column pointers,
   // CSC source positions (into the CSR value order); and into the int16 pool: CSR global columns, CSC global rows
   int32_t f_rptr, f_tptr, f_tsrc, f_rcol, f_trow;
-  int32_t f_rperm, f_cperm;            // int16 pool: rows / columns sorted by descending length (balanced warps)
+  int32_t f_rperm, f_cperm;
+  int32_t n_long_rows, n_long_cols;    // leading entries of rperm / cperm with at least PLM_LONG entries (lane-group products)            // int16 pool: rows / columns sorted by descending length (balanced warps)
+  int32_t f_sched, n_sched;            // int32 pool: panel schedule of one ADMM iteration, 8 ints per step
+  int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
   int32_t fac_total;
   int32_t smax;                        // largest stage size
