@@ -78,7 +78,7 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
   const PlmLayout& L = h->host.layout;
   h->tgt_ld = L.ndx + L.types[L.node_type[0]].nu;
   PLM_CHECK_CUDA(h, cudaMalloc(&h->d_tgt, (size_t)max_batch * h->tgt_ld * sizeof(double)));
-  h->node_ws_doubles = (int)node_ws_doubles(L, h->host.model.nv, L.nf);
+  h->node_ws_doubles = (int)node_ws_doubles(L, h->host.model.nv, L.nf, h->host.model.nbody, false);
   {
     const size_t tables = ((sizeof(PlmModel) + 7) / 8 + (sizeof(PlmLayout) + 7) / 8) * 8;
     const size_t per_warp = (size_t)h->node_ws_doubles * 8, cap = 227 * 1024;

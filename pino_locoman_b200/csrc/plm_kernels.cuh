@@ -20,7 +20,7 @@ struct TrialArgs {
 
 // One warp per (instance, node).  Shared memory: [PlmModel | PlmLayout | per-warp NodeWs + row/J staging].
 template <int KIND>
-__global__ void __launch_bounds__(PLM_NODE_WARPS * 32)
+__global__ void __launch_bounds__(PLM_NODE_WARPS * 32, 2)
 node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* __restrict__ p, int batch,
                  double* __restrict__ g, double* __restrict__ Jv, int want_jac, int ws_doubles, TrialArgs tr) {
   extern __shared__ double smem[];
@@ -46,7 +46,10 @@ node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* _
   const int b = bt / ntr, trial = tr.t0 + bt % ntr;
   if (tr.part && tr.accepted && tr.accepted[b]) return;   // line search already finished for this instance
   NodeWs& ws = *reinterpret_cast<NodeWs*>(wsbase + (size_t)warp * ws_doubles);
-  if (lane == 0) node_ws_bind(ws, L, wsbase + (size_t)warp * ws_doubles + (sizeof(NodeWs) + 7) / 8);
+  // Jacobian entries go straight to the instance's node block in HBM (every pattern entry is written exactly once)
+  if (lane == 0)
+    node_ws_bind(ws, L, sM->nv, sM->nbody, wsbase + (size_t)warp * ws_doubles + (sizeof(NodeWs) + 7) / 8,
+                 want_jac ? Jv + (size_t)b * L.nnz + L.nnz_off[node] : wsbase /* unused */);
   __syncwarp();
   NodeArgs A;
   A.M = sM;
@@ -108,8 +111,6 @@ node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* _
     for (int r = lane; r < L.ndx; r += 32) g0[r] = A.xs[r];
   }
   if (want_jac) {
-    double* Jo = Jv + (size_t)b * L.nnz + L.nnz_off[node];
-    for (int e = lane; e < T.nnz; e += 32) Jo[e] = ws.J[e];
     if (node == 0) {
       double* J0 = Jv + (size_t)b * L.nnz;
       for (int e = lane; e < L.ndx; e += 32) J0[e] = 1.0;

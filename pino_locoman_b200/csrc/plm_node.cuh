@@ -39,15 +39,15 @@ struct NodeWs {
   double cq[PLM_MAXCOL];      // dq (tangent increment of this node) per column
   double cv[PLM_MAXCOL];      // velocity coordinate per column
   double ca[PLM_MAXCOL];      // acceleration coordinate per column
-  double rec[PLM_MAXB][PLM_REC];
-  double col[PLM_MAXCOL][PLM_COLREC];
+  double (*rec)[PLM_REC];     // [nbody] body records (carved from the tail of the workspace)
+  double (*col)[PLM_COLREC];  // [nv]    column records
   double con[PLM_MAXC][PLM_CONREC];
   double arm[PLM_CONREC];
   double Rb[9];
   double Rinit[9];
   double jr[9];
   double* g;     // [max_rows]
-  double* J;     // [max_nnz]
+  double* J;     // node block of the Jacobian values: the instance's block in HBM (kernel) or a staging array (host emulation)
   double* aba;   // ABA scratch: M/L, Minv, GQ, GV (nv x 32 each), GF (nv x nf)
   double* xbuf;  // [2 ndx + nu] staged x + alpha dx of this node (line-search trials)
 };

@@ -28,18 +28,27 @@ struct HostExec {
 };
 
 // Bytes of shared workspace one warp needs for a layout.
-PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf) {
+// Doubles of workspace one warp needs.  stage_J: keep a staging copy of the node's J block in the workspace
+// (host emulation); the kernel writes J entries straight into the instance's block in HBM instead.
+PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf, int nbody, bool stage_J) {
   size_t base = (sizeof(NodeWs) + 7) / 8;
-  size_t extra = (size_t)L.max_rows + (size_t)L.max_nnz + (size_t)(2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
+  size_t extra = (size_t)nbody * PLM_REC + (size_t)nv * PLM_COLREC + (size_t)L.max_rows + (stage_J ? (size_t)L.max_nnz : 0) +
+                 (size_t)(2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
   if (L.dynamics == PLM_WHOLE_BODY_ABA) extra += aba_ws_doubles(nv, nf);
   return base + extra + 2;
 }
 
-// ws.g / ws.J / aba scratch are carved from `tail` (doubles following the NodeWs struct).
-PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, double* tail) {
+// Records, row staging, trial staging and ABA scratch are carved from `tail` (doubles following the NodeWs struct).
+PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, int nv, int nbody, double* tail, double* J_external) {
+  ws.rec = reinterpret_cast<double (*)[PLM_REC]>(tail);
+  tail += (size_t)nbody * PLM_REC;
+  ws.col = reinterpret_cast<double (*)[PLM_COLREC]>(tail);
+  tail += (size_t)nv * PLM_COLREC;
   ws.g = tail;
-  ws.J = tail + L.max_rows;
-  ws.xbuf = tail + L.max_rows + L.max_nnz;
+  tail += L.max_rows;
+  if (J_external) ws.J = J_external;
+  else { ws.J = tail; tail += L.max_nnz; }
+  ws.xbuf = tail;
   ws.aba = ws.xbuf + (2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
 }
 
@@ -51,14 +60,8 @@ template <int KIND, class Exec>
 PLM_HD void node_eval_body(Exec& ex, NodeWs& ws, const NodeArgs& A) {
   const PlmModel& M = *A.M;
   const PlmNodeType& T = *A.T;
-  if (A.want_jac) {
-    ex.run([&](int lane, LaneState&) {
-      for (int e = lane; e < T.nnz; e += 32) ws.J[e] = 0.0;
-      node_phase_a<KIND>(ws, A, lane);
-    });
-  } else {
-    ex.run([&](int lane, LaneState&) { node_phase_a<KIND>(ws, A, lane); });
-  }
+  (void)T;
+  ex.run([&](int lane, LaneState&) { node_phase_a<KIND>(ws, A, lane); });
   ex.run([&](int lane, LaneState& st) { node_phase_b<KIND>(ws, A, st, lane); });
   for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
   if (KIND == PLM_WHOLE_BODY_ABA) {

@@ -10,7 +10,7 @@
 #define PLM_MAXC 6       // contact frames: 4 feet + external-force frame (+ spare)
 #define PLM_MAXDEPTH 8   // revolute joints between the root and a leaf
 #define PLM_MAXNODES 64
-#define PLM_NODE_WARPS 4   // warps (= node evaluations) per CTA of the node kernel
+#define PLM_NODE_WARPS 8   // upper bound of warps (= node evaluations) per CTA of the node kernel
 
 enum PlmDynamics {
   PLM_CENTROIDAL_VEL = 0,

@@ -2,6 +2,7 @@
 // pino_locoman_b200/csrc/plm_node*.cuh compiled with g++, the 32 lanes of a warp run in a loop per phase.
 // TEST INFRASTRUCTURE: validates the kernel mathematics against the oracle without a GPU; it is not a product path
 // (the product library refuses to run without a CUDA device).
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -19,9 +20,10 @@ struct Emu {
 template <int KIND>
 static void run_node(const HostTables& t, const double* x, const double* p, int b, int node, double* g, double* Jv, int want_jac) {
   const PlmLayout& L = t.layout;
-  std::vector<double> buf(node_ws_doubles(L, t.model.nv, L.nf) + 8, 0.0);
+  // poison the staging area: an entry of the pattern that no lane writes shows up as NaN in the tests
+  std::vector<double> buf(node_ws_doubles(L, t.model.nv, L.nf, t.model.nbody, true) + 8, nan(""));
   NodeWs& ws = *reinterpret_cast<NodeWs*>(buf.data());
-  node_ws_bind(ws, L, buf.data() + (sizeof(NodeWs) + 7) / 8);
+  node_ws_bind(ws, L, t.model.nv, t.model.nbody, buf.data() + (sizeof(NodeWs) + 7) / 8, nullptr);
   NodeArgs A;
   A.M = &t.model;
   A.L = &L;
