@@ -413,7 +413,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   Q.fac_off[N + 1] = fo;
   Q.fac_total = fo;
   {
-    // panel schedule: forward sweep stages 0..N, backward sweep stages N..0, each stage cut into row panels
+    // panel schedule: forward sweep stages 0..N, backward sweep stages N-1..0, each stage cut into row panels
     std::vector<int> sched;
     auto add_stage = [&](int i, int dir) {
       const int s = (i < N) ? ndx + nu[i] : ndx;
@@ -435,7 +435,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       }
     };
     for (int i = 0; i <= N; ++i) add_stage(i, 0);
-    for (int i = N; i >= 0; --i) add_stage(i, 1);
+    for (int i = N - 1; i >= 0; --i) add_stage(i, 1);     // x_N = S_N^-1 r_N needs no backward work
     Q.n_sched = (int)sched.size() / PLM_SCHED_INTS;
     Q.f_sched = (int)out.qp_idx32.size();
     for (int v : sched) out.qp_idx32.push_back(v);

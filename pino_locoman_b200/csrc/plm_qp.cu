@@ -249,7 +249,19 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       for (int c2 = nth + tid; c2 <= k; c2 += nth) Li[tri(k, c2)] = rowk[c2];
       __syncthreads();
     }
-    for (int e = tid; e < s * (s + 1) / 2; e += nth) Lout[Q.fac_off[i] + e] = Li[e];
+    // S_i^-1 = Linv^T Linv (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit)
+    for (int e = tid; e < s * (s + 1) / 2; e += nth) {
+      // e -> (r, c2), c2 <= r
+      int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while (tri(r + 1, 0) <= e) ++r;
+      while (tri(r, 0) > e) --r;
+      const int c2 = e - tri(r, 0);
+      double a0 = 0.0, a1 = 0.0;
+      int t = r;
+      for (; t + 1 < s; t += 2) { a0 += Li[tri(t, r)] * Li[tri(t, c2)]; a1 += Li[tri(t + 1, r)] * Li[tri(t + 1, c2)]; }
+      if (t < s) a0 += Li[tri(t, r)] * Li[tri(t, c2)];
+      Lout[Q.fac_off[i] + e] = a0 + a1;
+    }
     if (last) break;
     // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = Linv G^T ; K = W^T W
     for (int c2 = tid; c2 < ndx; c2 += nth) {
@@ -407,69 +419,45 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// The stage factors Linv_i (packed lower triangles, row-major) are streamed through shared memory in panels of
-// consecutive rows (<= 16 KB) by bulk asynchronous copies, NBUF panels deep, following a host-built schedule of one ADMM
-// iteration.  Both triangular products of a sweep step are row-streamable, so a panel is used once and dropped:
-//   forward  stage i: y_i = Linv_i r_i (rows of the panel), then tv += panel^T y_panel          (tv = Linv_i^T y_i)
-//   backward stage i: r = y_i - Linv_i g (rows of the panel), then xacc += panel^T r_panel      (x_i = Linv_i^T r)
+// The inverse stage blocks S_i^-1 (symmetric, packed lower triangles, row-major) are streamed through shared memory in
+// panels of consecutive rows (<= 16 KB) by bulk asynchronous copies, NBUF panels deep, following a host-built schedule
+// of one ADMM iteration.  A sweep step is one symmetric product out = S_i^-1 in; each stored element S[t][k] is read
+// once and used twice (row part out[t] += S[t][k] in[k], column part out[k] += S[t][k] in[t], k < t):
+//   forward  stage i: tv_i = S_i^-1 (b_i - G_{i-1} tv_{i-1})
+//   backward stage i: x_i  = tv_i - S_i^-1 G_i^T x_{i+1}            (x_N = tv_N)
 #define ADMM_THREADS 384
 #define ADMM_MIN_CTAS 2
 #define NBUF 3
-#define TRI_B 14     // a lane's share of a row: covers rows of up to 8 * 14 = 112 entries per pass
-#define COL_B 16     // rows fetched per batch in the transposed product
+#define SYM_J 4      // lane l owns the columns l + 32 j, j < SYM_J  (stage size <= 128)
 
-// out[t] = (sub ? sub[t] - P r : P r)[t]  for the rows [r0, r1) held in the panel; eight lanes per row.
-__device__ __forceinline__ void panel_rows(const double* pan, int shift, int r0, int r1, const double* r, double* out, const double* sub) {
-  const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7, ngrp = blockDim.x >> 3;
-  for (int t0 = r0; t0 < r1; t0 += ngrp) {
-    const int t = t0 + grp;
-    double acc = 0.0;
-    if (t < r1) {
-      const double* row = pan + (tri(t, 0) - shift);
-      for (int kb = 0; kb <= t; kb += 8 * TRI_B) {
-        double v[TRI_B];
-#pragma unroll
-        for (int j = 0; j < TRI_B; ++j) {
-          const int k = kb + l8 + 8 * j;
-          v[j] = (k <= t) ? row[k] : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < TRI_B; ++j) {
-          const int k = kb + l8 + 8 * j;
-          if (k <= t) acc += v[j] * r[k];
-        }
-      }
-    }
-    acc = group8_sum(acc);
-    if (t < r1 && l8 == 0) out[t] = sub ? sub[t] - acc : acc;
-  }
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-// acc[k] (+)= sum_{t in [r0, r1)} P[t][k] v[t]  for the columns k < r1; two threads per column (rows of equal parity).
-__device__ __forceinline__ void panel_cols(const double* pan, int shift, int r0, int r1, const double* v, double* acc_out, bool first) {
-  const int half = threadIdx.x & 1;
-  const int ncol2 = ((r1 + 15) & ~15);
-  for (int k = threadIdx.x >> 1; k < ncol2; k += blockDim.x >> 1) {
-    double acc = 0.0;
-    if (k < r1) {
-      const int tb0 = max(r0, k);
-      for (int tb = tb0 + half; tb < r1; tb += 2 * COL_B) {
-        double a[COL_B];
+// One warp per row of the panel.  inr[j] = in[lane + 32 j] (registers, loaded once per stage), colacc[j] accumulates the
+// column part of the lane's columns over every row this warp handles in the stage; rowres[t] receives the row part.
+__device__ __forceinline__ void sym_panel(const double* pan, int shift, int r0, int r1, const double* vin, const double (&inr)[SYM_J],
+                                          double (&colacc)[SYM_J], double* rowres) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = r0 + warp; t < r1; t += nw) {
+    const double* row = pan + (tri(t, 0) - shift);
+    const double in_t = vin[t];
+    double a[SYM_J];
 #pragma unroll
-        for (int j = 0; j < COL_B; ++j) {
-          const int t = tb + 2 * j;
-          a[j] = (t < r1) ? pan[tri(t, k) - shift] : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < COL_B; ++j) {
-          const int t = tb + 2 * j;
-          if (t < r1) acc += a[j] * v[t];
-        }
-      }
+    for (int j = 0; j < SYM_J; ++j) {
+      const int k = lane + 32 * j;
+      a[j] = (k <= t) ? row[k] : 0.0;
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    // rows above r0 never touch the columns >= r0: those start here; earlier columns accumulate across panels
-    if (k < r1 && half == 0) acc_out[k] = (first || k >= r0) ? acc : acc_out[k] + acc;
+    double p = 0.0;
+#pragma unroll
+    for (int j = 0; j < SYM_J; ++j) {
+      const int k = lane + 32 * j;
+      p += a[j] * inr[j];
+      colacc[j] += (k < t) ? a[j] * in_t : 0.0;
+    }
+    p = warp_sum(p);
+    if (lane == 0) rowres[t] = p;
   }
 }
 
@@ -489,8 +477,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   double* tv = w + m;          // [smax] Linv^T y of the current stage (forward) / G^T x of the next stage (backward)
   double* rv = tv + smax;      // [smax] panel-row results
-  double* xa = rv + smax;      // [smax] accumulator of the transposed product in the backward sweep
-  double* red = xa + smax;     // [32]
+  double* cpart = rv + smax;   // [warps][smax] column parts of the symmetric product, one slice per warp
+  double* red = cpart + (ADMM_THREADS / 32) * smax;     // [32]
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
   FlatIdx F;
@@ -554,29 +542,32 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     spmv_cols(F, n, Q.n_long_cols, AT, w, xt, sigma, x, qh);
     __syncthreads();
     PROF_ADD(0);
-    // ---- forward and backward sweeps, one schedule step = one row panel of one stage factor
+    // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
+    double inr[SYM_J], colacc[SYM_J];
     for (int st = 0; st < nsched; ++st) {
       const int32_t* S = sched + st * PLM_SCHED_INTS;
       const int r0 = S[2], r1 = S[3], i = S[4], dir = S[5], first = S[6], last = S[7];
       const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
       const int shift = S[0] - Q.fac_off[i];
       double* bi = xt + L.x_off[i];
+      const double* vin = (dir == 0) ? bi : tv;
       if (first) {
         if (dir == 0) {
-          if (i > 0) {     // b_i -= G_{i-1} tv   (tv = Linv_{i-1}^T y_{i-1})
+          if (i > 0) {     // b_i -= G_{i-1} tv_{i-1}
             const StageView sp = stage_view(L, Q, idx, i - 1);
             const double* Ap = Ah + L.nnz_off[i - 1];
             const double* rp = rho + L.row_off[i - 1];
+            const double* tprev = xt + L.x_off[i - 1];
             for (int c2 = tid; c2 < ndx; c2 += nth) {
               const int e1 = sp.rptr[c2 + 1] - 1;
               double acc = 0.0;
-              for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tv[sp.ccol[e]];
+              for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tprev[sp.ccol[e]];
               bi[c2] -= rp[c2] * Ap[e1] * acc;
             }
             __syncthreads();
           }
           PROF_ADD(1);
-        } else if (i < N) {   // tv = G_i^T x_{i+1}: column gather over the integrator rows (rows < ndx come first)
+        } else {   // tv = G_i^T x_{i+1}: column gather over the integrator rows (rows < ndx come first in every column)
           const StageView sv = stage_view(L, Q, idx, i);
           const double* An = Ah + L.nnz_off[i];
           const double* rh = rho + L.row_off[i];
@@ -594,31 +585,43 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           __syncthreads();
           PROF_ADD(5);
         }
+#pragma unroll
+        for (int j = 0; j < SYM_J; ++j) {
+          const int k = (tid & 31) + 32 * j;
+          inr[j] = (k < s) ? vin[k] : 0.0;
+          colacc[j] = 0.0;
+        }
       }
-      // wait for the panel, multiply its rows
+      // wait for the panel, multiply
       const int bsel = (int)(used % NBUF);
       mbar_wait(&bars[bsel], (unsigned)((used / NBUF) & 1));
-      const double* pan = pbuf + (size_t)bsel * pdb;
       PROF_ADD(2);
-      if (dir == 0) panel_rows(pan, shift, r0, r1, bi, rv, nullptr);                       // rv = y_i (rows of the panel)
-      else if (i < N) panel_rows(pan, shift, r0, r1, tv, rv, bi);                          // rv = y_i - Linv_i tv
-      else { for (int t = r0 + tid; t < r1; t += nth) rv[t] = bi[t]; }                     // terminal stage: r = y_N
-      __syncthreads();
-      PROF_ADD(3);
-      // every thread is past the previous step's transposed product: its buffer may be refilled
-      if (tid == 0) issue_next();
-      ++issued;
-      // transposed product of the panel
-      if (dir == 0) { if (i < N) panel_cols(pan, shift, r0, r1, rv, tv, first != 0); }
-      else panel_cols(pan, shift, r0, r1, rv, xa, first != 0);
+      sym_panel(pbuf + (size_t)bsel * pdb, shift, r0, r1, vin, inr, colacc, rv);
       ++used;
+      PROF_ADD(3);
       if (last) {
+        // combine: out[k] = rowres[k] + sum over warps of their column parts
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int j = 0; j < SYM_J; ++j) {
+          const int k = lane + 32 * j;
+          if (k < s) cpart[warp * smax + k] = colacc[j];
+        }
+        __syncthreads();      // also: every thread is done with all panels of this stage
+        if (tid == 0) issue_next();
+        ++issued;
+        for (int k = tid; k < s; k += nth) {
+          double acc = rv[k];
+          for (int w2 = 0; w2 < (nth >> 5); ++w2) acc += cpart[w2 * smax + k];
+          bi[k] = (dir == 0) ? acc : bi[k] - acc;
+        }
         __syncthreads();
-        if (dir == 0) { for (int k = tid; k < s; k += nth) bi[k] = rv[k]; }                // keep y_i for the backward sweep
-        else { for (int k = tid; k < s; k += nth) bi[k] = xa[k]; }                          // x_i
-        __syncthreads();
+        PROF_ADD(4);
+      } else {
+        __syncthreads();      // the panel buffer may be refilled once every warp has left it
+        if (tid == 0) issue_next();
+        ++issued;
       }
-      PROF_ADD(4);
     }
     // ---- z~ = A x~ ; relaxation, projection, dual update
     spmv_rows(F, m, Q.n_long_rows, Ah, xt, w);
@@ -836,7 +839,8 @@ int plm_qp_alloc(plm_handle* h) {
   h->scale_stage_A = (h->smem_scale + (size_t)L.nnz * 8 <= 200 * 1024) ? 1 : 0;
   if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
   h->smem_factor = (size_t)(smax * (smax + 1) + smax * ndx + ndx * ndx + ndx + 2 * smax + L.max_nnz + L.max_rows) * 8;
-  h->smem_admm = (size_t)(NBUF * Q.panel_doubles + NBUF + 1 + L.n + L.m + 3 * smax + 32) * 8;
+  h->smem_admm = (size_t)(NBUF * Q.panel_doubles + NBUF + 1 + L.n + L.m + (2 + ADMM_THREADS / 32) * smax + 32) * 8;
+  if (smax > 32 * SYM_J) { h->error = "stage size exceeds the lane-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
     return 7;
