@@ -66,7 +66,7 @@ struct NodeArgs {
 };
 
 struct LaneState {
-  double J[6], Vj[6], Vp[6], Ap[6], Aj[6];
+  double J[6], Vj[6], Vp[6], Ap[6];
   double Jq[6];
   double w[6], y[6], dFv[6], dFq[6], dFqn[6];
   double tau;
@@ -162,6 +162,21 @@ PLM_HD void apply_joint_rot(double* R, int axtype, const double* axis, double s,
   }
 }
 
+// q-direction of a column: base angular columns are mixed by the right Jacobian of Exp (dq -> local tangent), base
+// linear columns have no effect on any row, joint columns are their own direction.
+PLM_HD void lane_q_direction(const NodeWs& ws, LaneState& st, int lane, int body) {
+  if (body == 0) {
+    st.Jq[0] = st.Jq[1] = st.Jq[2] = 0.0;
+    if (lane < 3) { st.Jq[3] = st.Jq[4] = st.Jq[5] = 0.0; }
+    else {
+      double e[3] = {ws.jr[lane - 3], ws.jr[3 + lane - 3], ws.jr[6 + lane - 3]};   // column (lane-3) of Jr
+      matvec3(ws.Rb, e, st.Jq + 3);
+    }
+  } else {
+    for (int i = 0; i < 6; ++i) st.Jq[i] = st.J[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Phase B: every lane walks its own chain (forward kinematics + velocity/acceleration recursion),
 // forms the world inertia of its body, the body force and Coriolis block, and the owner lane stores
@@ -212,7 +227,8 @@ PLM_HD void node_phase_b(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
       Vj[i] += J[i] * vq;
     }
   }
-  for (int i = 0; i < 6; ++i) { st.J[i] = J[i]; st.Vj[i] = Vj[i]; st.Vp[i] = Vp[i]; st.Ap[i] = Ap[i]; st.Aj[i] = Aj[i]; }
+  for (int i = 0; i < 6; ++i) { st.J[i] = J[i]; st.Vj[i] = Vj[i]; st.Vp[i] = Vp[i]; st.Ap[i] = Ap[i]; }
+  lane_q_direction(ws, st, lane, body);
 
   const bool owner = (body > 0) || (lane == 0);
   if (!owner) return;
@@ -352,20 +368,8 @@ PLM_HD void node_phase_d(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
   const double* IbC = rec + PLM_REC_IB;
   st.tau = dot6(st.J, FC);
   if (!A.want_jac) return;
-  // q-direction: base angular columns are mixed by the right Jacobian of Exp (dq -> local tangent),
-  // base linear columns have no effect on any row.
   double Jq[6];
-  if (body == 0) {
-    Jq[0] = Jq[1] = Jq[2] = 0.0;
-    if (lane < 3) { Jq[3] = Jq[4] = Jq[5] = 0.0; }
-    else {
-      double e[3] = {ws.jr[lane - 3], ws.jr[3 + lane - 3], ws.jr[6 + lane - 3]};   // column (lane-3) of Jr
-      matvec3(ws.Rb, e, Jq + 3);
-    }
-  } else {
-    for (int i = 0; i < 6; ++i) Jq[i] = st.J[i];
-  }
-  for (int i = 0; i < 6; ++i) st.Jq[i] = Jq[i];
+  for (int i = 0; i < 6; ++i) Jq[i] = st.Jq[i];
   double phi[6], chi[6], psi[6], t6[6], VV[6];
   mxm(st.Vp, Jq, phi);
   mxm(st.Ap, Jq, chi);

@@ -66,14 +66,20 @@ PLM_HD void node_eval_body(Exec& ex, NodeWs& ws, const NodeArgs& A) {
   for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
   if (KIND == PLM_WHOLE_BODY_ABA) {
     aba_solve_and_derivatives<Exec>(ex, ws, A);
+    ex.run([&](int lane, LaneState& st) {
+      node_phase_f<KIND>(ws, A, st, lane);
+      if (A.want_jac) node_phase_consts(ws, A, lane, 32);
+    });
   } else {
-    ex.run([&](int lane, LaneState& st) { node_phase_d<KIND>(ws, A, st, lane); });
+    // contact / arm / shared rows first: they only need the chain state of phase B, which keeps the register
+    // footprint of the derivative phases (D, E) down
+    ex.run([&](int lane, LaneState& st) {
+      node_phase_f<KIND>(ws, A, st, lane);
+      if (A.want_jac) node_phase_consts(ws, A, lane, 32);
+      node_phase_d<KIND>(ws, A, st, lane);
+    });
     ex.run([&](int lane, LaneState& st) { node_phase_e<KIND>(ws, A, st, lane); });
   }
-  ex.run([&](int lane, LaneState& st) {
-    node_phase_f<KIND>(ws, A, st, lane);
-    if (A.want_jac) node_phase_consts(ws, A, lane, 32);
-  });
 }
 
 }  // namespace plm
