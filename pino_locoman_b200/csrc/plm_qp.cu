@@ -443,21 +443,22 @@ __device__ __forceinline__ void sym_panel(const double* pan, int shift, int r0, 
   for (int t = r0 + warp; t < r1; t += nw) {
     const double* row = pan + (tri(t, 0) - shift);
     const double in_t = vin[t];
+    const double diag = row[t];
+    // strictly-lower entries feed both parts unconditionally (zero beyond the row end); the diagonal only the row part
     double a[SYM_J];
 #pragma unroll
     for (int j = 0; j < SYM_J; ++j) {
       const int k = lane + 32 * j;
-      a[j] = (k <= t) ? row[k] : 0.0;
+      a[j] = (k < t) ? row[k] : 0.0;
     }
     double p = 0.0;
 #pragma unroll
     for (int j = 0; j < SYM_J; ++j) {
-      const int k = lane + 32 * j;
       p += a[j] * inr[j];
-      colacc[j] += (k < t) ? a[j] * in_t : 0.0;
+      colacc[j] += a[j] * in_t;
     }
     p = warp_sum(p);
-    if (lane == 0) rowres[t] = p;
+    if (lane == 0) rowres[t] = p + diag * in_t;
   }
 }
 
@@ -544,6 +545,10 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     PROF_ADD(0);
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
     double inr[SYM_J], colacc[SYM_J];
+    if (it == 1) {       // later iterations: the last step of the previous iteration already waited for this panel
+      if (tid == 0) mbar_wait(&bars[used % NBUF], (unsigned)((used / NBUF) & 1));
+      __syncthreads();
+    }
     for (int st = 0; st < nsched; ++st) {
       const int32_t* S = sched + st * PLM_SCHED_INTS;
       const int r0 = S[2], r1 = S[3], i = S[4], dir = S[5], first = S[6], last = S[7];
@@ -592,9 +597,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           colacc[j] = 0.0;
         }
       }
-      // wait for the panel, multiply
+      // the panel has landed: thread 0 waited for it before the last barrier (see below)
       const int bsel = (int)(used % NBUF);
-      mbar_wait(&bars[bsel], (unsigned)((used / NBUF) & 1));
       PROF_ADD(2);
       sym_panel(pbuf + (size_t)bsel * pdb, shift, r0, r1, vin, inr, colacc, rv);
       ++used;
@@ -615,9 +619,11 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           for (int w2 = 0; w2 < (nth >> 5); ++w2) acc += cpart[w2 * smax + k];
           bi[k] = (dir == 0) ? acc : bi[k] - acc;
         }
+        if (tid == 0) mbar_wait(&bars[used % NBUF], (unsigned)((used / NBUF) & 1));    // next panel, single waiter
         __syncthreads();
         PROF_ADD(4);
       } else {
+        if (tid == 0) mbar_wait(&bars[used % NBUF], (unsigned)((used / NBUF) & 1));    // next panel, single waiter
         __syncthreads();      // the panel buffer may be refilled once every warp has left it
         if (tid == 0) issue_next();
         ++issued;
