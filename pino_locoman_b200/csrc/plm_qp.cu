@@ -160,7 +160,7 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-__global__ void __launch_bounds__(QP_THREADS)
+__global__ void __launch_bounds__(QP_THREADS, 2)
 qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, QpWork W, int* __restrict__ fail) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
@@ -168,11 +168,10 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
   const int tsz = smax * (smax + 1) / 2;
-  double* H = sm;                      // [tsz]  stage block -> Cholesky factor (packed lower)
-  double* Li = H + tsz;                // [tsz]  inverse of the factor (packed lower), built alongside the factorisation
-  double* Wm = Li + tsz;               // [smax][ndx]  W = Linv G^T
-  double* K = Wm + smax * ndx;         // [ndx][ndx]   Schur term for the next stage
-  double* gsc = K + ndx * ndx;         // [ndx]  rho_r * (next entry)^2 of the integrator rows
+  double* H = sm;                      // [tsz]  stage block -> (in place) inverse X = L^-1 of its Cholesky factor, packed lower
+  double* Wm = H + tsz;                // [smax][ndx]  W = X G^T
+  double* K = Wm + smax * ndx;         // [ndx (ndx+1)/2] Schur term for the next stage, packed lower
+  double* gsc = K + ndx * (ndx + 1) / 2;   // [ndx]  rho_r * (next entry)^2 of the integrator rows
   double* colk = gsc + ndx;            // [smax] current Cholesky column
   double* rowk = colk + smax;          // [smax] current row of the inverse
   double* As = rowk + smax;            // [max_nnz] scaled A values of the node block
@@ -196,17 +195,15 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       for (int r = tid; r < sv.nrows; r += nth) rs[r] = rh[r];
     }
     __syncthreads();
-    // ---- H_ii (lower triangle): thread j owns row j;  Linv starts as the identity
+    // ---- H_ii (lower triangle): thread j owns row j
     for (int j = tid; j < s; j += nth) {
       double* Hj = H + tri(j, 0);
-      double* Xj = Li + tri(j, 0);
-      for (int k = 0; k <= j; ++k) { Hj[k] = 0.0; Xj[k] = 0.0; }
-      Xj[j] = 1.0;
+      for (int k = 0; k <= j; ++k) Hj[k] = 0.0;
       Hj[j] = Ph[xo + j] + Q.sigma;
       if (j < ndx) {
         if (i == 0) Hj[j] += rho[j] * Ah[j] * Ah[j];           // DX_0 == 0 rows
         else {
-          for (int k = 0; k <= j; ++k) Hj[k] -= K[j * ndx + k];  // Schur complement of stage i-1
+          for (int k = 0; k <= j; ++k) Hj[k] -= K[tri(j, k)];    // Schur complement of stage i-1
           Hj[j] += gsc[j];                                       // rho_r n_r^2 of the integrator row feeding DX_i[j]
         }
       }
@@ -223,47 +220,40 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       }
     }
     __syncthreads();
-    // ---- right-looking Cholesky; the same column sweeps apply L^-1 to the identity (X <- L^-1), two barriers per column
+    // ---- right-looking Cholesky fused with the inversion of the factor, in place: after step k the columns <= k of the
+    // buffer hold X = L^-1 (rows > k partially applied), the columns > k the trailing matrix.  Two barriers per column.
     for (int k = 0; k < s; ++k) {
       const double piv = H[tri(k, k)];
       if (!(piv > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
       const double dinv = 1.0 / sqrt(piv > 0.0 ? piv : 1.0);
       for (int r = k + 1 + tid; r < s; r += nth) colk[r] = H[tri(r, k)] * dinv;
-      for (int c2 = tid; c2 <= k; c2 += nth) {
-        const double v = Li[tri(k, c2)] * dinv;     // row k of X is final after scaling by 1/L_kk
-        rowk[c2] = v;
-      }
+      for (int c2 = tid; c2 <= k; c2 += nth) rowk[c2] = (c2 == k) ? dinv : H[tri(k, c2)] * dinv;   // row k of X is final
       __syncthreads();
-      // trailing update of H (rows r > k, columns k < c2 <= r) and of X (rows r > k, columns c2 <= k)
       const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
       for (int r = k + 1 + slot; r < s; r += nslot) {
         const double lrk = colk[r];
         double* Hr = H + tri(r, 0);
-        double* Xr = Li + tri(r, 0);
-        for (int c2 = k + 1 + lane8; c2 <= r; c2 += 8) Hr[c2] -= lrk * colk[c2];
-        for (int c2 = lane8; c2 <= k; c2 += 8) Xr[c2] -= lrk * rowk[c2];
-        if (lane8 == 0) Hr[k] = lrk;
+        for (int c2 = k + 1 + lane8; c2 <= r; c2 += 8) Hr[c2] -= lrk * colk[c2];     // trailing matrix
+        for (int c2 = lane8; c2 < k; c2 += 8) Hr[c2] -= lrk * rowk[c2];              // X, columns < k
+        if (lane8 == 0) Hr[k] = -lrk * rowk[k];                                      // X, column k (L[r][k] is consumed)
       }
-      if (tid <= k) Li[tri(k, tid)] = rowk[tid];
-      if (tid == 0) H[tri(k, k)] = 1.0 / dinv;
-      for (int c2 = nth + tid; c2 <= k; c2 += nth) Li[tri(k, c2)] = rowk[c2];
+      for (int c2 = tid; c2 <= k; c2 += nth) H[tri(k, c2)] = rowk[c2];
       __syncthreads();
     }
-    // S_i^-1 = Linv^T Linv (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit)
+    // ---- S_i^-1 = X^T X (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit)
     for (int e = tid; e < s * (s + 1) / 2; e += nth) {
-      // e -> (r, c2), c2 <= r
       int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
       while (tri(r + 1, 0) <= e) ++r;
       while (tri(r, 0) > e) --r;
       const int c2 = e - tri(r, 0);
       double a0 = 0.0, a1 = 0.0;
       int t = r;
-      for (; t + 1 < s; t += 2) { a0 += Li[tri(t, r)] * Li[tri(t, c2)]; a1 += Li[tri(t + 1, r)] * Li[tri(t + 1, c2)]; }
-      if (t < s) a0 += Li[tri(t, r)] * Li[tri(t, c2)];
+      for (; t + 1 < s; t += 2) { a0 += H[tri(t, r)] * H[tri(t, c2)]; a1 += H[tri(t + 1, r)] * H[tri(t + 1, c2)]; }
+      if (t < s) a0 += H[tri(t, r)] * H[tri(t, c2)];
       Lout[Q.fac_off[i] + e] = a0 + a1;
     }
     if (last) break;
-    // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = Linv G^T ; K = W^T W
+    // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = X G^T ; K = W^T W
     for (int c2 = tid; c2 < ndx; c2 += nth) {
       const int elast = sv.rptr[c2 + 1] - 1;              // next entry of integrator row c2
       const double nn = As[elast];
@@ -274,17 +264,19 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       const int e0 = sv.rptr[c2], e1 = sv.rptr[c2 + 1] - 1;
       const double g = rs[c2] * As[e1];
       double acc = 0.0;
-      const double* Lt = Li + tri(t, 0);
+      const double* Xt = H + tri(t, 0);
       for (int e = e0; e < e1; ++e) {
         const int k = sv.ccol[e];
-        if (k <= t) acc += As[e] * Lt[k];
+        if (k <= t) acc += As[e] * Xt[k];
       }
       Wm[o] = g * acc;
     }
     __syncthreads();
-    for (int o = tid; o < ndx * ndx; o += nth) {
-      const int r = o / ndx, c2 = o % ndx;
-      if (c2 > r) continue;
+    for (int o = tid; o < ndx * (ndx + 1) / 2; o += nth) {
+      int r = (int)((sqrt(8.0 * o + 1.0) - 1.0) * 0.5);
+      while (tri(r + 1, 0) <= o) ++r;
+      while (tri(r, 0) > o) --r;
+      const int c2 = o - tri(r, 0);
       double a0 = 0.0, a1 = 0.0;
       int t = 0;
       for (; t + 1 < s; t += 2) { a0 += Wm[t * ndx + r] * Wm[t * ndx + c2]; a1 += Wm[(t + 1) * ndx + r] * Wm[(t + 1) * ndx + c2]; }
@@ -842,9 +834,10 @@ int plm_qp_alloc(plm_handle* h) {
   h->qp_factor_doubles = Q.fac_total;
   const int smax = Q.smax, ndx = L.ndx;
   h->smem_scale = (size_t)(L.n + L.m + 32) * 8;
-  h->scale_stage_A = (h->smem_scale + (size_t)L.nnz * 8 <= 200 * 1024) ? 1 : 0;
+  // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
+  h->scale_stage_A = 0;
   if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
-  h->smem_factor = (size_t)(smax * (smax + 1) + smax * ndx + ndx * ndx + ndx + 2 * smax + L.max_nnz + L.max_rows) * 8;
+  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 2 * smax + L.max_nnz + L.max_rows + 2) * 8;
   h->smem_admm = (size_t)(NBUF * Q.panel_doubles + NBUF + 1 + L.n + L.m + (2 + ADMM_THREADS / 32) * smax + 32) * 8;
   if (smax > 32 * SYM_J) { h->error = "stage size exceeds the lane-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
