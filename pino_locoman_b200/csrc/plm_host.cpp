@@ -402,6 +402,10 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     for (int r : rperm) if (rptr[r + 1] - rptr[r] >= PLM_LONG) Q.n_long_rows++;
     for (int j : cperm) if (tptr[j + 1] - tptr[j] >= PLM_LONG) Q.n_long_cols++;
   }
+  Q.sparse_coupling = 1;
+  for (int t = 0; t < L.ntypes; ++t)
+    for (int r = 0; r < ndx; ++r)
+      if ((int)out.type_rowcols[t][r].size() - 1 > 4) Q.sparse_coupling = 0;
   Q.smax = 0;
   int fo = 0;
   for (int i = 0; i <= N; ++i) {

@@ -160,7 +160,7 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-__global__ void __launch_bounds__(QP_THREADS, 2)
+__global__ void __launch_bounds__(QP_THREADS, 3)
 qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, QpWork W, int* __restrict__ fail) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
@@ -169,8 +169,8 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
   const int tsz = smax * (smax + 1) / 2;
   double* H = sm;                      // [tsz]  stage block -> (in place) inverse X = L^-1 of its Cholesky factor, packed lower
-  double* Wm = H + tsz;                // [smax][ndx]  W = X G^T
-  double* K = Wm + smax * ndx;         // [ndx (ndx+1)/2] Schur term for the next stage, packed lower
+  double* Wm = H + tsz;                // [smax][ndx]  W = X G^T (dense coupling only)
+  double* K = Wm + (Q.sparse_coupling ? 0 : smax * ndx);   // [ndx (ndx+1)/2] Schur term for the next stage, packed lower
   double* gsc = K + ndx * (ndx + 1) / 2;   // [ndx]  rho_r * (next entry)^2 of the integrator rows
   double* colk = gsc + ndx;            // [smax] current Cholesky column
   double* rowk = colk + smax;          // [smax] current row of the inverse
@@ -258,6 +258,29 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       const int elast = sv.rptr[c2 + 1] - 1;              // next entry of integrator row c2
       const double nn = As[elast];
       gsc[c2] = rs[c2] * nn * nn;
+    }
+    if (Q.sparse_coupling) {
+      // K = G S^-1 G^T straight from the block just written (L2-hot): a handful of terms per entry
+      __syncthreads();     // the S^-1 block written above is visible to the whole CTA
+      const double* Sg = Lout + Q.fac_off[i];
+      for (int o = tid; o < ndx * (ndx + 1) / 2; o += nth) {
+        int r = (int)((sqrt(8.0 * o + 1.0) - 1.0) * 0.5);
+        while (tri(r + 1, 0) <= o) ++r;
+        while (tri(r, 0) > o) --r;
+        const int c2 = o - tri(r, 0);
+        const int ea0 = sv.rptr[r], ea1 = sv.rptr[r + 1] - 1, eb0 = sv.rptr[c2], eb1 = sv.rptr[c2 + 1] - 1;
+        double acc = 0.0;
+        for (int ea = ea0; ea < ea1; ++ea) {
+          const int ja = sv.ccol[ea];
+          for (int eb = eb0; eb < eb1; ++eb) {
+            const int jb = sv.ccol[eb];
+            acc += As[ea] * As[eb] * Sg[ja >= jb ? tri(ja, jb) : tri(jb, ja)];
+          }
+        }
+        K[o] = rs[r] * As[ea1] * rs[c2] * As[eb1] * acc;
+      }
+      __syncthreads();
+      continue;
     }
     for (int o = tid; o < s * ndx; o += nth) {
       const int t = o / ndx, c2 = o % ndx;
@@ -838,6 +861,7 @@ int plm_qp_alloc(plm_handle* h) {
   h->scale_stage_A = 0;
   if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 2 * smax + L.max_nnz + L.max_rows + 2) * 8;
+  if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
   h->smem_admm = (size_t)(NBUF * Q.panel_doubles + NBUF + 1 + L.n + L.m + (2 + ADMM_THREADS / 32) * smax + 32) * 8;
   if (smax > 32 * SYM_J) { h->error = "stage size exceeds the lane-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {

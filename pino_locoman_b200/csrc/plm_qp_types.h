@@ -31,6 +31,7 @@ struct QpLayout {
   // CSC source positions (into the CSR value order); and into the int16 pool: CSR global columns, CSC global rows
   int32_t f_rptr, f_tptr, f_tsrc, f_rcol, f_trow;
   int32_t f_rperm, f_cperm;
+  int32_t sparse_coupling;             // every integrator row has at most 4 entries in its own stage (all but whole_body_aba / centroidal_vel)
   int32_t n_long_rows, n_long_cols;    // leading entries of rperm / cperm with at least PLM_LONG entries (lane-group products)            // int16 pool: rows / columns sorted by descending length (balanced warps)
   int32_t f_sched, n_sched;            // int32 pool: panel schedule of one ADMM iteration, 8 ints per step
   int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
