@@ -320,11 +320,11 @@ def main():
     bytes_admm = B * Kavg * (8.0 * nnzF + 8.0 * (3 * n + 4 * m))       # K (8 nnz(F) + 8 (3n + 4m)) per instance
     ach_admm = bytes_admm / (ms_admm / 1e3) / 1e9
     ach_eval = B * NODES * BYTES_NODE_EVAL / (ms_eval / 1e3) / 1e9
-    traffic = None
+    traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath):     # per-instance DRAM bytes from the committed ncu captures, scaled to this batch
         with open(tpath) as f:
-            traffic = json.load(f)
+            traffic = {k: v * B for k, v in json.load(f).get("per_instance_bytes", {}).items()}
     line = {
         "metric": "sqp_iters_per_s", "value": value, "unit": "SQP iters/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -338,9 +338,10 @@ def main():
         "phase_ms": {"eval": phase[0] / K, "qp_update": phase[1] / K, "qp_solve": phase[2] / K, "line_search": phase[3] / K},
         "qp": {"admm_iters_avg": Kavg, "line_search_trials_avg": Tavg, "accepted_frac": float(np.mean(accepted)), "nnz_F": nnzF},
         "roofline": {"kernel": "qp_admm_kernel", "bound": "hbm", "achieved": ach_admm, "peak": peak, "unit": "GB/s",
-                     "frac": ach_admm / peak, "traffic": (traffic or {}).get("qp_admm_kernel"), "peak_source": peak_src},
+                     "frac": ach_admm / peak, "traffic": traffic.get("qp_admm_kernel"), "peak_source": peak_src,
+                     "algorithmic_bytes": bytes_admm},
         "roofline_node_eval": {"kernel": "node_eval_kernel", "bound": "hbm", "achieved": ach_eval, "peak": peak, "unit": "GB/s",
-                               "frac": ach_eval / peak, "traffic": (traffic or {}).get("node_eval_kernel"),
+                               "frac": ach_eval / peak, "traffic": traffic.get("node_eval_kernel"),
                                "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval},
         "e2e": {"value": total_inst / (ms_e2e / 1e3), "unit": "SQP iters/s", "h2d_bytes_per_step": int(B * (n + h.np) * 8),
                 "d2h_bytes_per_step": int(B * (n + 8) * 8)},

@@ -141,7 +141,9 @@ int plm_qp_setup(plm_handle* h, int32_t batch, const double* d_hess, void* strea
  * d_hess is the diagonal P. */
 int plm_qp_update(plm_handle* h, int32_t batch, const double* d_hess, const double* d_q, const double* d_J,
                   const double* d_l, const double* d_u, void* stream);
-/* solve().x : ADMM from the persistent iterates; d_iters / d_status are int32 [batch] (may be NULL). */
+/* solve().x : ADMM from the persistent iterates; d_iters / d_status are int32 [batch] (may be NULL).
+ * status: osqp codes (1 solved, 2 solved inaccurate, -2 max iterations, -3/3 primal infeasible (in)accurate,
+ * -4/4 dual infeasible) plus -10 non-positive pivot in the stage factorisation, -11 NaN iterates. */
 int plm_qp_solve(plm_handle* h, int32_t batch, double* d_dx, int32_t* d_iters, int32_t* d_status, void* stream);
 /* Read / write the persistent scaled iterates: x [batch][n], z [batch][m], y [batch][m]. */
 int plm_qp_get_iterates(plm_handle* h, int32_t batch, double* d_x, double* d_z, double* d_y, void* stream);

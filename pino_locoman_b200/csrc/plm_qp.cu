@@ -180,6 +180,7 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   const double* Ph = W.Ph + (size_t)b * n;
   const double* rho = W.rho + (size_t)b * m;
   double* Lout = W.Linv + (size_t)b * Q.fac_total;
+  if (tid == 0) fail[b] = 0;
 
   for (int i = 0; i <= N; ++i) {
     const bool last = (i == N);
@@ -479,7 +480,7 @@ __device__ __forceinline__ void sym_panel(const double* pan, int shift, int r0, 
 
 __global__ void __launch_bounds__(ADMM_THREADS, ADMM_MIN_CTAS)
 qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
-               double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out) {
+               double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out, const int* __restrict__ fail) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
   const QpLayout& Q = *Qp;
@@ -801,6 +802,14 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   for (long long k = used; k < issued; ++k) mbar_wait(&bars[k % NBUF], (unsigned)((k / NBUF) & 1));   // drain prefetches in flight
   if (it > Q.max_iter) it = Q.max_iter;
   if (status == 0) status = -2;   // maximum iterations reached
+  // failure detection beyond osqp's own codes: -10 the stage factorisation met a non-positive pivot, -11 NaN iterates
+  {
+    double bad = 0.0;      // max-reductions ignore NaN, so look for it explicitly once at the end
+    for (int j = tid; j < n; j += nth) if (x[j] != x[j]) bad = 1.0;
+    bad = block_reduce(bad, red, true);
+    if (fail[b] != 0) status = -10;
+    else if (bad != 0.0) status = -11;
+  }
   const bool no_solution = (status == 3 || status == -3 || status == 4 || status == -4);
   __syncthreads();
   for (int j = tid; j < n; j += nth) {
@@ -904,7 +913,7 @@ int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const dou
 
 int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int* d_status, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_admm_kernel<<<batch, ADMM_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status);
+  qp_admm_kernel<<<batch, ADMM_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }

@@ -63,3 +63,27 @@ def test_qp_matches_oracle_osqp(robots, rn, kind, N):
             assert np.abs(yq[b].cpu().numpy() - Q.y).max() <= 1e-6 * max(1.0, np.abs(Q.y).max())
             new_x.append(xb + dx_r)
         x = torch.tensor(np.stack(new_x), device="cuda")
+
+
+def test_failure_codes(robots):
+    """Numeric failures surface as per-instance status codes, never as exceptions."""
+    from pino_locoman_b200.handle import Handle
+    prod, ora = robots
+    rng = np.random.default_rng(1)
+    o = OracleOCP(ora["b2"], "centroidal_acc", 4)
+    x0, p0 = _nominal_problem(o, rng, 3)
+    h = Handle(prod["b2"], "centroidal_acc", 4, max_batch=3)
+    x = torch.tensor(np.tile(x0, (3, 1)), device="cuda")
+    p = torch.tensor(np.tile(p0, (3, 1)), device="cuda")
+    hess = h.hess_diag(p)
+    h.qp_setup(hess)
+    grad, J, g, lbg, ubg = h.sqp_data(x, p)
+    grad[1, 5] = float("nan")                 # NaN in the linear cost of instance 1
+    bad_hess = hess.clone()
+    bad_hess[2] = -1e9                        # indefinite P for instance 2: the stage Cholesky must report it
+    h.qp_update(bad_hess, grad, J, lbg - g, ubg - g)
+    dx, iters, status = h.qp_solve(3)
+    status = status.cpu().numpy()
+    assert status[0] in (1, 2, -2) and torch.isfinite(dx[0]).all()
+    assert status[1] == -11
+    assert status[2] == -10
