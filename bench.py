@@ -285,6 +285,33 @@ def main():
     ms_eval = e0.elapsed_time(e1) / reps
     launches += reps
     del g, J
+    # ---- BASELINE configs[1]: single B2 whole_body_rnea instance, latency of one SQP iteration (parity-test case, extra key)
+    single_ms = None
+    if rank == 0:
+        from pino_locoman_b200.utils.robot import B2
+        r1 = B2()
+        r1.set_gait_sequence("trot", 0.8)
+        o1 = make_ocp(dynamics=DYNAMICS, default_args=OCP_ARGS[DYNAMICS], robot=r1, nodes=NODES, solver="osqp", batch=1, device=dev)
+        o1.set_time_params(0.01, 0.08)
+        o1.set_swing_params(0.07, [0.1, -0.2])
+        o1.set_tracking_targets(np.array([0.2, 0, 0, 0, 0, 0]))
+        o1.update_previous_torques(np.zeros(r1.nj))
+        o1.update_initial_state(o1.x_nom)
+        o1.update_gait_sequence(0.0)
+        o1.init_solver()
+        x1 = torch.from_numpy(o1.initial_guess()).to(dev)
+        p1 = o1._p_device()
+        ts = []
+        for k in range(6):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            x1, _ = o1.handle.sqp_step(x1, p1)
+            a1.record()
+            torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        single_ms = float(np.median(ts[1:]))
+        launches += o1.handle.launch_count()
+        del o1
     # ---- end to end through the plugin surface: host buffers in, host buffers out
     ocp._x0 = x.cpu().numpy()
     for _ in range(min(W, 1)):
@@ -345,6 +372,7 @@ def main():
                                "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval},
         "e2e": {"value": total_inst / (ms_e2e / 1e3), "unit": "SQP iters/s", "h2d_bytes_per_step": int(B * (n + h.np) * 8),
                 "d2h_bytes_per_step": int(B * (n + 8) * 8)},
+        "single_instance": {"workload": "b2 whole_body_rnea trot N=20, 1 instance (BASELINE configs[1])", "ms_per_sqp_iter": single_ms},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }

@@ -7,7 +7,7 @@ using namespace plm;
 
 template <int KIND>
 static int setup_one(plm_handle* h) {
-  cudaError_t e = cudaFuncSetAttribute(node_eval_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->node_smem);
+  cudaError_t e = cudaFuncSetAttribute(node_eval_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per function, shared by all handles
   if (e != cudaSuccess) { h->error = std::string("node kernel shared memory: ") + cudaGetErrorString(e); return 6; }
   return 0;
 }

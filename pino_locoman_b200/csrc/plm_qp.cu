@@ -877,9 +877,9 @@ int plm_qp_alloc(plm_handle* h) {
     h->error = "QP workspace exceeds shared memory";
     return 7;
   }
-  QP_CUDA(h, cudaFuncSetAttribute(qp_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_scale));
-  QP_CUDA(h, cudaFuncSetAttribute(qp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_factor));
-  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_admm));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 

@@ -77,3 +77,22 @@ def test_input_validation(robots):
         h.g_data(torch.zeros(3, h.n, dtype=torch.float64, device="cuda"), torch.zeros(3, h.np, dtype=torch.float64, device="cuda"))
     with pytest.raises(ValueError):
         Handle(prod["b2"], "whole_body_foo", 4, max_batch=2)
+
+
+def test_handles_of_different_sizes_coexist(robots):
+    """Kernel attributes (dynamic shared memory) are per function, not per handle: a small handle created after a large one
+    must not break the large one."""
+    from pino_locoman_b200.handle import Handle
+    prod, ora = robots
+    rng = np.random.default_rng(2)
+    big = Handle(prod["b2g"], "whole_body_rnea", 6, max_batch=2)
+    o = OracleOCP(ora["b2g"], "whole_body_rnea", 6)
+    x0, p0 = random_problem(o, rng)
+    x = torch.tensor(np.tile(x0, (2, 1)), device="cuda")
+    p = torch.tensor(np.tile(p0, (2, 1)), device="cuda")
+    x1, _ = big.sqp_step(x, p)
+    small = Handle(prod["go2"], "centroidal_vel", 4, max_batch=1)
+    assert small.n < big.n
+    x2, _ = big.sqp_step(x, p)      # same inputs, but the QP iterates are warm now: only check that it runs and is finite
+    torch.cuda.synchronize()
+    assert torch.isfinite(x1).all() and torch.isfinite(x2).all()
