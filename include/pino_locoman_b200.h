@@ -125,6 +125,11 @@ int plm_dyn_gaps(plm_handle* h, int32_t dynamics, const double* d_q, const doubl
 int plm_centroidal_vel_gaps(plm_handle* h, const double* d_h, const double* d_q, const double* d_v, int32_t batch,
                             double* d_gaps, void* stream);
 int plm_com_dyn(plm_handle* h, const double* d_q, const double* d_forces, int32_t batch, double* d_dh, void* stream);
+/* base_acc(q, v, a_j, forces) -> a_b [6] for dynamics = centroidal_acc (dynamics_centroidal_acc.py:43-82, also
+ * dynamics_centroidal_vel.py:91-134) or whole_body_acc (dynamics_whole_body_acc.py:43-83) with d_h = NULL;
+ * base_vel(h, q, v_j) -> v_b [6] for dynamics = centroidal_vel (dynamics_centroidal_vel.py:73-89) with d_v = d_forces = NULL. */
+int plm_base_solve(plm_handle* h, int32_t dynamics, const double* d_h, const double* d_q, const double* d_v,
+                   const double* d_lead_j, const double* d_forces, int32_t batch, double* d_base, void* stream);
 /* frame_vel(q, v) -> linear part vel[:3] (the components the OCP rows use, optimization/ocp.py:143-180) of
  * dynamics/dynamics.py:77-118: foot frame `contact` in 0..nfeet-1 with relative_to_base = 0 (LOCAL_WORLD_ALIGNED),
  * or the arm end-effector frame (contact = -1) with relative_to_base = 1 (x, y in base axes, z in the world).

@@ -114,6 +114,26 @@ class DynamicsWholeBodyAcc(Dynamics):
             return full(q, v, a, forces)[..., :6]
         return dyn_gaps
 
+    # dynamics_whole_body_acc.py:43-83: a_b = M_bb^-1 (-nle_b - M_bj a_j + sum J_c^T f); M columns from RNEA differences
+    def base_acc_dynamics(self, ext_force_frame=None):
+        ee = self._ee(ext_force_frame)
+
+        def base_acc(q, v, a_j, forces):
+            kin = rbd.Kin(self.model, q)
+            zero_f = rbd.local_ext_forces(self.model, kin, ee, np.zeros_like(forces))
+            fext = rbd.local_ext_forces(self.model, kin, ee, forces)
+            zv = np.zeros_like(v)
+            grav = rbd.rnea(self.model, kin, zv, zv, zero_f)
+            M_b = []
+            for c in range(self.nv):
+                e = np.zeros_like(v)
+                e[..., c] = 1.0
+                M_b.append((rbd.rnea(self.model, kin, zv, e, zero_f) - grav)[..., :6])
+            M_b = np.stack(M_b, -1)                                   # [.., 6, nv] = M[:6, :]
+            rhs = -rbd.rnea(self.model, kin, v, zv, fext)[..., :6] - np.einsum("...ij,...j->...i", M_b[..., 6:], a_j)
+            return np.linalg.solve(M_b[..., :6], rhs[..., None])[..., 0]
+        return base_acc
+
 
 class DynamicsCentroidalAcc(Dynamics):
     def state_integrate(self):
@@ -132,6 +152,10 @@ class DynamicsCentroidalAcc(Dynamics):
             dh = self._com_wrench(kin, com, ee, forces)
             return rbd.centroidal_momentum_rate(self.model, kin, v, a) - dh
         return dyn_gaps
+
+    # dynamics_centroidal_acc.py:43-82: a_b = A_b^-1 (dh - Adot v - A_j a_j)
+    def base_acc_dynamics(self, ext_force_frame=None):
+        return _centroidal_base_acc(self, ext_force_frame)
 
 
 class DynamicsCentroidalVel(Dynamics):
@@ -164,3 +188,29 @@ class DynamicsCentroidalVel(Dynamics):
             kin = rbd.Kin(self.model, q)
             return rbd.centroidal_momentum(self.model, kin, v) - h * self.mass
         return dyn_gaps
+
+    # dynamics_centroidal_vel.py:73-89: v_b = A_b^-1 (m h - A_j v_j)
+    def base_vel_dynamics(self):
+        def base_vel(h, q, v_j):
+            kin = rbd.Kin(self.model, q)
+            A = rbd.centroidal_map(self.model, kin)
+            rhs = h * self.mass - np.einsum("...ij,...j->...i", A[..., 6:], v_j)
+            return np.linalg.solve(A[..., :6], rhs[..., None])[..., 0]
+        return base_vel
+
+    # dynamics_centroidal_vel.py:91-134
+    def base_acc_dynamics(self, ext_force_frame=None):
+        return _centroidal_base_acc(self, ext_force_frame)
+
+
+def _centroidal_base_acc(dyn, ext_force_frame):
+    ee = dyn._ee(ext_force_frame)
+
+    def base_acc(q, v, a_j, forces):
+        kin = rbd.Kin(dyn.model, q)
+        com = rbd.center_of_mass(dyn.model, kin)
+        dh = dyn._com_wrench(kin, com, ee, forces)
+        A = rbd.centroidal_map(dyn.model, kin)
+        rhs = dh - rbd.dccrba_times_v(dyn.model, kin, v) - np.einsum("...ij,...j->...i", A[..., 6:], a_j)
+        return np.linalg.solve(A[..., :6], rhs[..., None])[..., 0]
+    return base_acc

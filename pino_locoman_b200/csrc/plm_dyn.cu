@@ -23,8 +23,10 @@ using namespace plm;
 struct plm_probe {
   plm_handle* h = nullptr;       // probe handle (nodes = 2)
   double *x = nullptr, *p = nullptr, *g = nullptr, *J = nullptr;
+  double *rows6 = nullptr, *jac6 = nullptr;   // scratch of the base_vel / base_acc solves
   int32_t* map = nullptr;        // [rows_out][cols_out] -> position in the probe's J values (or -1)
   int rows_out = 0, cols_out = 0;
+  int map_kind = 0;              // which entry point built the map (1 value+jac export, 2 base solve)
 };
 
 __global__ void probe_pack_kernel(int batch, int n, int np, double* __restrict__ x, double* __restrict__ p,
@@ -68,9 +70,36 @@ __global__ void probe_jac_kernel(int batch, int nnz, int rows, int cols, const i
   out[i] = v;
 }
 
+// x = -A^-1 r for the 6x6 blocks A = jac[b][0:6][col0:col0+6] (row stride ld) and r = rows[b][0:6]; Gaussian elimination
+// with partial pivoting, one thread per instance.
+__global__ void solve6_kernel(int batch, const double* __restrict__ jac, int ld, int col0, const double* __restrict__ rows, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  double A[6][7];
+  for (int i = 0; i < 6; ++i) {
+    for (int j = 0; j < 6; ++j) A[i][j] = jac[((size_t)b * 6 + i) * ld + col0 + j];
+    A[i][6] = -rows[(size_t)b * 6 + i];
+  }
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < 6; ++i) if (fabs(A[i][k]) > fabs(A[piv][k])) piv = i;
+    for (int j = k; j < 7; ++j) { const double t = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = t; }
+    const double inv = 1.0 / A[k][k];
+    for (int i = k + 1; i < 6; ++i) {
+      const double f = A[i][k] * inv;
+      for (int j = k; j < 7; ++j) A[i][j] -= f * A[k][j];
+    }
+  }
+  for (int i = 5; i >= 0; --i) {
+    double v = A[i][6];
+    for (int j = i + 1; j < 6; ++j) v -= A[i][j] * out[(size_t)b * 6 + j];
+    out[(size_t)b * 6 + i] = v / A[i][i];
+  }
+}
+
 static void probe_free(plm_probe* pr) {
   if (!pr) return;
-  cudaFree(pr->x); cudaFree(pr->p); cudaFree(pr->g); cudaFree(pr->J); cudaFree(pr->map);
+  cudaFree(pr->x); cudaFree(pr->p); cudaFree(pr->g); cudaFree(pr->J); cudaFree(pr->map); cudaFree(pr->rows6); cudaFree(pr->jac6);
   if (pr->h) plm_destroy(pr->h);
   delete pr;
 }
@@ -139,6 +168,7 @@ static int set_map(plm_handle* h, plm_probe* pr, int node, int row0, int nrows, 
   DYN_CUDA(h, cudaMemcpy(pr->map, map.data(), map.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   pr->rows_out = nrows;
   pr->cols_out = (int)cols.size();
+  pr->map_kind = 1;
   return 0;
 }
 
@@ -193,7 +223,7 @@ int plm_rnea_dyn(plm_handle* h, const double* d_q, const double* d_v, const doub
   // rows: tau[:6] (row_dyn) and tau[6:] - tau_j (row_tauj, tau_j = 0); they are consecutive
   if (int rc = emit_rows(h, pr, batch, 0, T.row_dyn, M.nv, 1.0, d_tau, s)) return rc;
   if (d_jac) {
-    if (pr->rows_out != M.nv) if (int rc = set_map(h, pr, 0, T.row_dyn, M.nv, cols_qvaf(L, M.nv, M.nv))) return rc;
+    if (pr->map_kind != 1) if (int rc = set_map(h, pr, 0, T.row_dyn, M.nv, cols_qvaf(L, M.nv, M.nv))) return rc;
     if (int rc = emit_jac(h, pr, batch, 1.0, -1, 0.0, d_jac, s)) return rc;
   }
   return 0;
@@ -212,7 +242,7 @@ int plm_dyn_gaps(plm_handle* h, int32_t dynamics, const double* d_q, const doubl
   if (int rc = run_probe(h, pr, batch, d_q, M.nq, d_v, M.nv, d_a, M.nv, d_forces, L.nf, d_jac != nullptr, s)) return rc;
   if (int rc = emit_rows(h, pr, batch, 0, T.row_dyn, 6, 1.0, d_gaps, s)) return rc;
   if (d_jac) {
-    if (pr->rows_out != 6) if (int rc = set_map(h, pr, 0, T.row_dyn, 6, cols_qvaf(L, M.nv, M.nv))) return rc;
+    if (pr->map_kind != 1) if (int rc = set_map(h, pr, 0, T.row_dyn, 6, cols_qvaf(L, M.nv, M.nv))) return rc;
     if (int rc = emit_jac(h, pr, batch, 1.0, -1, 0.0, d_jac, s)) return rc;
   }
   return 0;
@@ -231,7 +261,7 @@ int plm_aba_dyn(plm_handle* h, const double* d_q, const double* d_v, const doubl
   // rows dv_next - (dv + a dt) with dv = dv_next = 0, dt = 1  =>  a = -row ; d a / d v = -(entry) - I
   if (int rc = emit_rows(h, pr, batch, 0, T.row_int + M.nv, M.nv, -1.0, d_a, s)) return rc;
   if (d_jac) {
-    if (pr->rows_out != M.nv) if (int rc = set_map(h, pr, 0, T.row_int + M.nv, M.nv, cols_qvaf(L, M.nv, M.nj))) return rc;
+    if (pr->map_kind != 1) if (int rc = set_map(h, pr, 0, T.row_int + M.nv, M.nv, cols_qvaf(L, M.nv, M.nj))) return rc;
     if (int rc = emit_jac(h, pr, batch, -1.0, M.nv, -1.0, d_jac, s)) return rc;
   }
   return 0;
@@ -246,6 +276,55 @@ int plm_centroidal_vel_gaps(plm_handle* h, const double* d_h, const double* d_q,
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = run_probe(h, pr, batch, d_h, 6, d_q, M.nq, d_v, M.nv, nullptr, L.nf, 0, s)) return rc;
   return emit_rows(h, pr, batch, 0, L.types[L.node_type[0]].row_dyn, 6, 1.0, d_gaps, s);
+}
+
+/* base_acc(q, v, a_j, forces) -> a_b (centroidal_acc / centroidal_vel: dynamics_centroidal_acc.py:43-82; whole_body_acc:
+ * dynamics_whole_body_acc.py:43-83) and base_vel(h, q, v_j) -> v_b (dynamics_centroidal_vel.py:73-89).  The path rows are
+ * affine in the base part of a (resp. v): rows(lead) = A_b lead_b + rows(lead_b = 0), so lead_b = -A_b^-1 rows(lead_b = 0)
+ * with A_b the base block of the analytic Jacobian -- the same 6x6 system the reference inverts symbolically. */
+int plm_base_solve(plm_handle* h, int32_t dynamics, const double* d_h, const double* d_q, const double* d_v, const double* d_lead_j,
+                   const double* d_forces, int32_t batch, double* d_base, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  if (dynamics != PLM_CENTROIDAL_ACC && dynamics != PLM_WHOLE_BODY_ACC && dynamics != PLM_CENTROIDAL_VEL) { h->error = "plm_base_solve: formulation without a base path constraint"; return 11; }
+  plm_probe* pr;
+  if (int rc = get_probe(h, dynamics, &pr)) return rc;
+  const PlmLayout& L = pr->h->host.layout;
+  const PlmModel& M = pr->h->host.model;
+  const PlmNodeType& T = L.types[L.node_type[0]];
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool cvel = dynamics == PLM_CENTROIDAL_VEL;
+  if (!pr->rows6) {
+    DYN_CUDA(h, cudaMalloc(&pr->rows6, (size_t)h->max_batch * 6 * 8));
+    DYN_CUDA(h, cudaMalloc(&pr->jac6, (size_t)h->max_batch * 6 * M.nv * 8));
+  }
+  // lead = [0 (6) | lead_j]: the probe packs two consecutive blocks, so pass a null first block of size 6
+  // (probe_pack writes ua (size 6, null -> zeros) then ub); forces follow only when the lead is exactly nv long, so the
+  // forces are packed by a second call-site below for the (a, f) formulations.
+  {
+    probe_pack_kernel<<<batch, 128, 0, s>>>(batch, L.n, L.np, pr->x, pr->p, L.p_x_init, cvel ? 6 : M.nq, cvel ? d_h : d_q,
+                                            cvel ? M.nq : M.nv, cvel ? d_q : d_v, L.ndx, 6, nullptr, M.nj, d_lead_j,
+                                            L.p_dt_min, L.p_dt_max, L.p_n_contacts, L.p_swing_period, L.p_contact, 4 * L.nodes);
+    PLM_LAUNCH_CHECK(h);
+    if (!cvel && d_forces) {
+      DYN_CUDA(h, cudaMemcpy2DAsync(pr->x + L.ndx + L.f_idx, (size_t)L.n * 8, d_forces, (size_t)L.nf * 8, (size_t)L.nf * 8, batch,
+                                    cudaMemcpyDeviceToDevice, s));
+    }
+    int rc = plm_launch_node_eval(pr->h, pr->x, pr->p, batch, pr->g, pr->J, 1, s);
+    if (rc) { h->error = pr->h->error; return rc; }
+    h->launches++;
+  }
+  if (int rc = emit_rows(h, pr, batch, 0, T.row_dyn, 6, 1.0, pr->rows6, s)) return rc;
+  // Jacobian of the 6 path rows w.r.t. the leading input block (a or v): local columns ndx .. ndx + nv
+  std::vector<int> cols;
+  for (int i = 0; i < M.nv; ++i) cols.push_back(L.ndx + i);
+  if (pr->map_kind != 2) {
+    if (int rc = set_map(h, pr, 0, T.row_dyn, 6, cols)) return rc;
+    pr->map_kind = 2;
+  }
+  if (int rc = emit_jac(h, pr, batch, 1.0, -1, 0.0, pr->jac6, s)) return rc;
+  solve6_kernel<<<(batch + 63) / 64, 64, 0, s>>>(batch, pr->jac6, M.nv, 0, pr->rows6, d_base);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
 }
 
 int plm_com_dyn(plm_handle* h, const double* d_q, const double* d_forces, int32_t batch, double* d_dh, void* stream) {

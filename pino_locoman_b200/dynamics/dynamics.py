@@ -130,6 +130,21 @@ class Dynamics:
         return _Fn("dyn_gaps", lambda q, v, a, forces: run(q, v, a, forces, False), lambda q, v, a, forces: run(q, v, a, forces, True))
 
 
+    def _base_solve(self, name, dyn_id, ext_force_frame):
+        """base_acc(q, v, a_j, forces) -> a_b: the 6x6 solve of the base rows of formulation ``dyn_id``."""
+        h = self.handle
+
+        def base_acc(q, v, a_j, forces):
+            f = self._forces(forces, ext_force_frame)
+            B = _check_in(q, (self.nq,), "q").shape[0]
+            _check_in(v, (self.nv,), "v")
+            _check_in(a_j, (self.nj,), "a_j")
+            out = torch.empty(B, 6, dtype=torch.float64, device=q.device)
+            h._rc(h.lib.plm_base_solve(h._h, dyn_id, None, _ptr(q), _ptr(v), _ptr(a_j), _ptr(f), B, _ptr(out), h._stream()))
+            return out
+        return _Fn(name, base_acc)
+
+
 class DynamicsWholeBodyTorque(Dynamics):
     """dynamics_whole_body_torque.py: rnea_dyn (inherited) and aba_dyn."""
 
@@ -155,7 +170,8 @@ class DynamicsWholeBodyAcc(Dynamics):
         return self._gaps(2, ext_force_frame)
 
     def base_acc_dynamics(self, ext_force_frame=None):
-        raise NotImplementedError("include_base=False variants are not built yet (SURVEY 8f rank 2)")
+        """dynamics_whole_body_acc.py:43-83."""
+        return self._base_solve("base_acc_dyn", 2, ext_force_frame)
 
 
 class DynamicsCentroidalAcc(Dynamics):
@@ -166,7 +182,8 @@ class DynamicsCentroidalAcc(Dynamics):
         return self._gaps(1, ext_force_frame)
 
     def base_acc_dynamics(self, ext_force_frame=None):
-        raise NotImplementedError("include_base=False variants are not built yet (SURVEY 8f rank 2)")
+        """dynamics_centroidal_acc.py:43-82."""
+        return self._base_solve("base_acc", 1, ext_force_frame)
 
 
 class DynamicsCentroidalVel(Dynamics):
@@ -197,7 +214,18 @@ class DynamicsCentroidalVel(Dynamics):
         return _Fn("dyn_gaps", dyn_gaps)
 
     def base_vel_dynamics(self):
-        raise NotImplementedError("include_base=False variants are not built yet (SURVEY 8f rank 2)")
+        """dynamics_centroidal_vel.py:73-89: v_b = A_b^-1 (m h - A_j v_j)."""
+        h = self.handle
+
+        def base_vel(hh, q, v_j):
+            B = _check_in(q, (self.nq,), "q").shape[0]
+            _check_in(hh, (6,), "h")
+            _check_in(v_j, (self.nj,), "v_j")
+            out = torch.empty(B, 6, dtype=torch.float64, device=q.device)
+            h._rc(h.lib.plm_base_solve(h._h, 0, _ptr(hh), _ptr(q), None, _ptr(v_j), None, B, _ptr(out), h._stream()))
+            return out
+        return _Fn("base_vel", base_vel)
 
     def base_acc_dynamics(self, ext_force_frame=None):
-        raise NotImplementedError("include_base=False variants are not built yet (SURVEY 8f rank 2)")
+        """dynamics_centroidal_vel.py:91-134 (the centroidal_acc base rows)."""
+        return self._base_solve("base_acc", 1, ext_force_frame)

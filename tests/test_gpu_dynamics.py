@@ -111,5 +111,24 @@ def test_centroidal_functions_match_oracle(robots):
         assert np.abs(g3[b].cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
         ref = ocv.com_dynamics(o.ext_force_frame)(q[b], f[b])
         assert np.abs(g4[b].cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
-    with pytest.raises(NotImplementedError):
-        dcv.base_vel_dynamics()
+    # base_vel / base_acc (the 6x6 solves of the base rows), interleaved with the gap Jacobians above on the same probes
+    oCA = odyn.DynamicsCentroidalAcc(o.model, o.mass, o.foot_frames, o.base_frame)
+    oWA = odyn.DynamicsWholeBodyAcc(o.model, o.mass, o.foot_frames, o.base_frame)
+    a_j, v_j = a[:, 6:], v[:, 6:]
+    ab1 = dca.base_acc_dynamics(ext)(_t(q), _t(v), _t(a_j), _t(f)).cpu().numpy()
+    ab2 = dwa.base_acc_dynamics(ext)(_t(q), _t(v), _t(a_j), _t(f)).cpu().numpy()
+    ab3 = dcv.base_acc_dynamics(ext)(_t(q), _t(v), _t(a_j), _t(f)).cpu().numpy()
+    vb = dcv.base_vel_dynamics()(_t(hst), _t(q), _t(v_j)).cpu().numpy()
+    g1b, j1b = dca.dynamics_gaps(ext).jacobian(_t(q), _t(v), _t(a), _t(f))       # map rebuilt after the solve
+    assert torch.equal(g1, g1b) and torch.equal(j1, j1b)
+    for b in range(B):
+        ref = oCA.base_acc_dynamics(o.ext_force_frame)(q[b], v[b], a_j[b], f[b])
+        assert np.abs(ab1[b] - ref).max() <= TOL * np.abs(ref).max()
+        assert np.abs(ab3[b] - ref).max() <= TOL * np.abs(ref).max()
+        ref = oWA.base_acc_dynamics(o.ext_force_frame)(q[b], v[b], a_j[b], f[b])
+        assert np.abs(ab2[b] - ref).max() <= TOL * np.abs(ref).max()
+        ref = ocv.base_vel_dynamics()(hst[b], q[b], v_j[b])
+        assert np.abs(vb[b] - ref).max() <= TOL * np.abs(ref).max()
+        # consistency: the solved base part zeroes the gaps
+        full_a = np.concatenate([ab1[b], a_j[b]])
+        assert np.abs(oca(q[b], v[b], full_a, f[b])).max() <= 1e-8 * max(1.0, np.abs(f[b]).max())
