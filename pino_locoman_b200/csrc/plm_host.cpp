@@ -435,14 +435,19 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
         const int start = o0 & ~1;                       // 16-byte aligned start (stage blocks start even)
         const int len = ((o1 - start) + 1) & ~1;
         sched.push_back(Q.fac_off[i] + start); sched.push_back(len); sched.push_back(r0); sched.push_back(r1);
-        sched.push_back(i); sched.push_back(dir); sched.push_back(k == 0); sched.push_back(k + 2 == cuts.size());
+        sched.push_back(i);
+        sched.push_back(dir | ((k == 0) << 1) | ((k + 2 == cuts.size()) << 2));
+        sched.push_back(start);
+        sched.push_back(s | (L.x_off[i] << 8));
       }
     };
     for (int i = 0; i <= N; ++i) add_stage(i, 0);
     for (int i = N - 1; i >= 0; --i) add_stage(i, 1);     // x_N = S_N^-1 r_N needs no backward work
     Q.n_sched = (int)sched.size() / PLM_SCHED_INTS;
+    while (out.qp_idx32.size() % 4) out.qp_idx32.push_back(0);     // schedule entries are read as two 16-byte words
     Q.f_sched = (int)out.qp_idx32.size();
     for (int v : sched) out.qp_idx32.push_back(v);
+    Q.g_doubles = 4 * ndx;                                         // compact coupling block of one stage: <= 4 entries per integrator row
     Q.panel_doubles = PLM_PANEL_DOUBLES + 2;
   }
   Q.max_iter = ocp.osqp_max_iter; Q.check_termination = ocp.osqp_check_termination; Q.scaling = ocp.osqp_scaling;

@@ -443,38 +443,68 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 //   backward stage i: x_i  = tv_i - S_i^-1 G_i^T x_{i+1}            (x_N = tv_N)
 #define ADMM_THREADS 384
 #define ADMM_MIN_CTAS 2
-#define NBUF 3
-#define SYM_J 4      // lane l owns the columns l + 32 j, j < SYM_J  (stage size <= 128)
+#define NBUF 4
+#define SYM_K 128    // threads per part: thread (k, part) owns output k of the stage (stage size <= SYM_K), part = tid / SYM_K
+#define SYM_PARTS (ADMM_THREADS / SYM_K)
+static_assert(SYM_PARTS == 3 && ADMM_THREADS % SYM_K == 0, "the column walk of sym_panel steps three rows at a time");
 
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// One warp per row of the panel.  inr[j] = in[lane + 32 j] (registers, loaded once per stage), colacc[j] accumulates the
-// column part of the lane's columns over every row this warp handles in the stage; rowres[t] receives the row part.
-__device__ __forceinline__ void sym_panel(const double* pan, int shift, int r0, int r1, const double* vin, const double (&inr)[SYM_J],
-                                          double (&colacc)[SYM_J], double* rowres) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int t = r0 + warp; t < r1; t += nw) {
-    const double* row = pan + (tri(t, 0) - shift);
-    const double in_t = vin[t];
-    const double diag = row[t];
-    // strictly-lower entries feed both parts unconditionally (zero beyond the row end); the diagonal only the row part
-    double a[SYM_J];
-#pragma unroll
-    for (int j = 0; j < SYM_J; ++j) {
-      const int k = lane + 32 * j;
-      a[j] = (k < t) ? row[k] : 0.0;
+// Thread (k, part) accumulates output k of out = S^-1 in over the resident panel rows [r0, r1): the column walk
+// S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k
+// (lane addresses tri(k) + e fall in distinct banks); both walks are split over the SYM_PARTS parts.  No cross-thread
+// reduction inside a stage: `acc` lives in a register across the panels of the stage.
+// `pan` points at the panel buffer (shared memory), `zp` at a 0.0 in shared memory: masked elements load the zero
+// instead of branching.  Each walk is a masked part (rows / columns around the diagonal block of the warp) and an
+// unmasked main part with two independent accumulators.
+__device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const double* __restrict__ zp, int shift, int r0, int r1,
+                                          const double* __restrict__ vin, double& acc0, double& acc1) {
+  const int k = threadIdx.x & (SYM_K - 1), part = threadIdx.x / SYM_K, kw = k & ~31;
+  {
+    // column walk: rows t = t0 + part, step SYM_PARTS, of the panel; element S[t][k] at tri(t) + k
+    int t = max(r0, kw + 1) + part;              // warp-uniform start; rows t <= k are masked
+    const double* pa = pan + (tri(t, 0) - shift + k);
+    const double* pv = vin + t;
+    int dd = 3 * t + 6;                          // tri(t + 3) - tri(t)
+    const int tm = min(r1, kw + 32);
+    for (; t < tm; t += SYM_PARTS) {             // masked: the diagonal block of the warp
+      const double* q = (t > k) ? pa : zp;
+      acc0 += *q * *pv;
+      pa += dd; dd += 9; pv += SYM_PARTS;
     }
-    double p = 0.0;
-#pragma unroll
-    for (int j = 0; j < SYM_J; ++j) {
-      p += a[j] * inr[j];
-      colacc[j] += a[j] * in_t;
+#pragma unroll 2
+    for (; t + SYM_PARTS < r1; t += 2 * SYM_PARTS) {
+      const double a0 = pa[0], a1 = pa[dd];
+      const double v0 = pv[0], v1 = pv[SYM_PARTS];
+      acc0 += a0 * v0;
+      acc1 += a1 * v1;
+      pa += 2 * dd + 9; dd += 18; pv += 2 * SYM_PARTS;
     }
-    p = warp_sum(p);
-    if (lane == 0) rowres[t] = p + diag * in_t;
+    if (t < r1) acc0 += pa[0] * pv[0];
+  }
+  if (kw < r1 && kw + 32 > r0) {                 // warp-uniform: some row of this warp is resident
+    // row walk: S[k][e], e <= k, e = part + SYM_PARTS j
+    const bool mine = k >= r0 && k < r1;
+    const double* row = pan + (tri(mine ? k : r0, 0) - shift);
+    const int kk = mine ? k : -1;
+    int e = part;
+    if (kw >= r0 && kw + 31 < r1) {              // every row of the warp is resident: columns e <= kw need no mask
+#pragma unroll 2
+      for (; e + SYM_PARTS <= kw; e += 2 * SYM_PARTS) {
+        const double a0 = row[e], a1 = row[e + SYM_PARTS];
+        const double v0 = vin[e], v1 = vin[e + SYM_PARTS];
+        acc0 += a0 * v0;
+        acc1 += a1 * v1;
+      }
+    }
+    const int kend = min(kw + 31, r1 - 1);
+    for (; e <= kend; e += SYM_PARTS) {
+      const double* q = (e <= kk) ? row + e : zp;
+      acc1 += *q * vin[e];
+    }
   }
 }
 
@@ -487,15 +517,19 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
   const int pdb = Q.panel_doubles;
-  // panel buffers first (16-byte aligned), then the mbarriers, then the gathered vectors
+  const int gd = Q.g_doubles;
+  const bool sparse = Q.sparse_coupling != 0;
+  // panel buffers and coupling-block buffers first (16-byte aligned), then the mbarriers, then the gathered vectors
   double* pbuf = sm;                                   // [NBUF][pdb]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + NBUF * pdb);   // [NBUF] (+1 pad)
-  double* xt = sm + NBUF * pdb + NBUF + 1;   // [n]  rhs -> forward solution y -> x~ -> delta_x
+  double* gbuf = sm + NBUF * pdb;                      // [NBUF][gd] compact coupling block travelling with a stage's first panel
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(gbuf + NBUF * gd);  // [NBUF] "panel landed" barriers
+  int* cnt = reinterpret_cast<int*>(gbuf + NBUF * gd + NBUF);                          // [NBUF] warps done with the panel (running count)
+  double* xt = gbuf + NBUF * gd + 2 * NBUF;   // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
-  double* tv = w + m;          // [smax] Linv^T y of the current stage (forward) / G^T x of the next stage (backward)
-  double* rv = tv + smax;      // [smax] panel-row results
-  double* cpart = rv + smax;   // [warps][smax] column parts of the symmetric product, one slice per warp
-  double* red = cpart + (ADMM_THREADS / 32) * smax;     // [32]
+  double* tv = w + m;          // [smax] G^T x of the next stage (backward sweep)
+  double* cpart = tv + smax;   // [SYM_PARTS][smax] partial sums of the symmetric product, one slice per part
+  double* red = cpart + SYM_PARTS * smax;     // [32]
+  double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
   FlatIdx F;
@@ -516,23 +550,44 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* z = W.z + (size_t)b * m;
   double* y = W.y + (size_t)b * m;
   const double alpha = Q.alpha, sigma = Q.sigma;
-  // ---- panel pipeline: `issued` / `used` count schedule steps modulo the per-iteration schedule
+  // ---- compact coupling blocks G_i[c][j] = rho_c n_c A_int[c][j-th own-stage entry] (the ADMM iterations only ever
+  // need these products); written once per solve, then streamed with the panels.
+  double* Gc = W.Gc + (size_t)b * N * gd;
+  if (sparse) {
+    for (int q = tid; q < N * ndx; q += nth) {
+      const int i = q / ndx, c2 = q - i * ndx;
+      const StageView sp = stage_view(L, Q, idx, i);
+      const double* Ap = Ah + L.nnz_off[i];
+      const int e0 = sp.rptr[c2], e1 = sp.rptr[c2 + 1] - 1;
+      const double coef = rho[L.row_off[i] + c2] * Ap[e1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Gc[(size_t)q * 4 + j] = (e0 + j < e1) ? coef * Ap[e0 + j] : 0.0;
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");     // the bulk copies below read Gc through the async proxy
+  }
+  // ---- panel pipeline.  `used` counts schedule steps (uniform across the CTA); step q lives in buffer q % NBUF.  Warps
+  // consume the panels of a stage at their own pace (no CTA barrier between panels): every warp waits on the buffer's
+  // mbarrier, and the last warp to finish step q refills the buffer with step q + NBUF.
   if (tid == 0) {
-    for (int k = 0; k < NBUF; ++k) mbar_init(&bars[k], 1);
+    for (int k = 0; k < NBUF; ++k) { mbar_init(&bars[k], 1); cnt[k] = 0; }
+    *zp = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  long long issued = 0, used = 0;      // global step counters (uniform across the CTA)
-  auto issue_next = [&]() {            // thread 0 only
-    const int32_t* S = sched + (issued % nsched) * PLM_SCHED_INTS;
-    const int bi_ = (int)(issued % NBUF);
-    const unsigned bytes = (unsigned)S[1] * 8u;
-    mbar_expect_tx(&bars[bi_], bytes);
-    bulk_g2s(pbuf + (size_t)bi_ * pdb, Lf + S[0], bytes, &bars[bi_]);
+  unsigned used = 0;
+  auto issue_step = [&](int st, int buf) {            // one thread: schedule step st into buffer buf
+    const int4 S0 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS));
+    const int4 S1 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS) + 1);
+    const unsigned bytes = (unsigned)S0.y * 8u;
+    const int i = S1.x, dir = S1.y & 1;
+    const bool with_g = sparse && (S1.y & 2) && (dir == 1 || i > 0);
+    mbar_expect_tx(&bars[buf], bytes + (with_g ? (unsigned)gd * 8u : 0u));
+    bulk_g2s(pbuf + (size_t)buf * pdb, Lf + S0.x, bytes, &bars[buf]);
+    if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(dir ? i : i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
   };
   if (tid == 0)
-    for (int k = 0; k < NBUF - 1; ++k) { issue_next(); ++issued; }
-  if (tid != 0) issued = NBUF - 1;
+    for (int k = 0; k < NBUF; ++k) issue_step(k, k);
+  constexpr int nwarps = ADMM_THREADS / 32;
   int status = 0, it = 0;
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
   PROF_T0();
@@ -560,89 +615,99 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     __syncthreads();
     PROF_ADD(0);
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
-    double inr[SYM_J], colacc[SYM_J];
-    if (it == 1) {       // later iterations: the last step of the previous iteration already waited for this panel
-      if (tid == 0) mbar_wait(&bars[used % NBUF], (unsigned)((used / NBUF) & 1));
-      __syncthreads();
-    }
+    double acc0 = 0.0, acc1 = 0.0;
     for (int st = 0; st < nsched; ++st) {
-      const int32_t* S = sched + st * PLM_SCHED_INTS;
-      const int r0 = S[2], r1 = S[3], i = S[4], dir = S[5], first = S[6], last = S[7];
-      const int s = (i < N) ? Q.type[L.node_type[i]].s : ndx;
-      const int shift = S[0] - Q.fac_off[i];
-      double* bi = xt + L.x_off[i];
+      const int4 S0 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS));
+      const int4 S1 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS) + 1);
+      const int r0 = S0.z, r1 = S0.w, i = S1.x, dir = S1.y & 1, first = S1.y & 2, last = S1.y & 4, shift = S1.z;
+      const int s = S1.w & 255;
+      double* bi = xt + (S1.w >> 8);
       const double* vin = (dir == 0) ? bi : tv;
+      const int bsel = (int)(used & (NBUF - 1));
+      mbar_wait(&bars[bsel], (used / NBUF) & 1u);
+      PROF_ADD(2);
       if (first) {
+        const double* g = gbuf + bsel * gd;
         if (dir == 0) {
           if (i > 0) {     // b_i -= G_{i-1} tv_{i-1}
             const StageView sp = stage_view(L, Q, idx, i - 1);
-            const double* Ap = Ah + L.nnz_off[i - 1];
-            const double* rp = rho + L.row_off[i - 1];
             const double* tprev = xt + L.x_off[i - 1];
-            for (int c2 = tid; c2 < ndx; c2 += nth) {
-              const int e1 = sp.rptr[c2 + 1] - 1;
-              double acc = 0.0;
-              for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tprev[sp.ccol[e]];
-              bi[c2] -= rp[c2] * Ap[e1] * acc;
+            if (sparse) {
+              if (tid < ndx) {
+                const int e0 = sp.rptr[tid], ne = sp.rptr[tid + 1] - 1 - e0;
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc += g[4 * tid + j] * tprev[sp.ccol[e0 + (j < ne ? j : 0)]];
+                bi[tid] -= acc;
+              }
+            } else {
+              const double* Ap = Ah + L.nnz_off[i - 1];
+              const double* rp = rho + L.row_off[i - 1];
+              for (int c2 = tid; c2 < ndx; c2 += nth) {
+                const int e1 = sp.rptr[c2 + 1] - 1;
+                double acc = 0.0;
+                for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tprev[sp.ccol[e]];
+                bi[c2] -= rp[c2] * Ap[e1] * acc;
+              }
             }
             __syncthreads();
           }
           PROF_ADD(1);
         } else {   // tv = G_i^T x_{i+1}: column gather over the integrator rows (rows < ndx come first in every column)
           const StageView sv = stage_view(L, Q, idx, i);
-          const double* An = Ah + L.nnz_off[i];
-          const double* rh = rho + L.row_off[i];
           const double* xn = xt + L.x_off[i + 1];
-          for (int k = tid; k < s; k += nth) {
-            double acc = 0.0;
-            for (int e = sv.cptr[k]; e < sv.cptr[k + 1]; ++e) {
-              const int r = sv.crow[e];
-              if (r >= ndx) break;
-              const int e1 = sv.rptr[r + 1] - 1;
-              acc += An[sv.cpos[e]] * rh[r] * An[e1] * xn[r];
+          if (sparse) {
+            if (tid < s) {
+              double acc = 0.0;
+              for (int e = sv.cptr[tid]; e < sv.cptr[tid + 1]; ++e) {
+                const int r = sv.crow[e];
+                if (r >= ndx) break;
+                acc += g[4 * r + (sv.cpos[e] - sv.rptr[r])] * xn[r];
+              }
+              tv[tid] = acc;
             }
-            tv[k] = acc;
+          } else {
+            const double* An = Ah + L.nnz_off[i];
+            const double* rh = rho + L.row_off[i];
+            for (int k = tid; k < s; k += nth) {
+              double acc = 0.0;
+              for (int e = sv.cptr[k]; e < sv.cptr[k + 1]; ++e) {
+                const int r = sv.crow[e];
+                if (r >= ndx) break;
+                const int e1 = sv.rptr[r + 1] - 1;
+                acc += An[sv.cpos[e]] * rh[r] * An[e1] * xn[r];
+              }
+              tv[k] = acc;
+            }
           }
           __syncthreads();
           PROF_ADD(5);
         }
-#pragma unroll
-        for (int j = 0; j < SYM_J; ++j) {
-          const int k = (tid & 31) + 32 * j;
-          inr[j] = (k < s) ? vin[k] : 0.0;
-          colacc[j] = 0.0;
+        acc0 = 0.0; acc1 = 0.0;
+      }
+      sym_panel(pbuf + bsel * pdb, zp, shift, r0, r1, vin, acc0, acc1);
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        __threadfence_block();
+        if ((atomicAdd(&cnt[bsel], 1) + 1) % nwarps == 0) {
+          const int nx = st + NBUF;
+          issue_step(nx >= nsched ? nx - nsched : nx, bsel);
         }
       }
-      // the panel has landed: thread 0 waited for it before the last barrier (see below)
-      const int bsel = (int)(used % NBUF);
-      PROF_ADD(2);
-      sym_panel(pbuf + (size_t)bsel * pdb, shift, r0, r1, vin, inr, colacc, rv);
       ++used;
       PROF_ADD(3);
       if (last) {
-        // combine: out[k] = rowres[k] + sum over warps of their column parts
-        const int warp = tid >> 5, lane = tid & 31;
+        // combine: out[k] = sum over the parts
+        if ((tid & (SYM_K - 1)) < s) cpart[(tid / SYM_K) * smax + (tid & (SYM_K - 1))] = acc0 + acc1;
+        __syncthreads();
+        if (tid < s) {
+          double o = cpart[tid];
 #pragma unroll
-        for (int j = 0; j < SYM_J; ++j) {
-          const int k = lane + 32 * j;
-          if (k < s) cpart[warp * smax + k] = colacc[j];
+          for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[w2 * smax + tid];
+          bi[tid] = (dir == 0) ? o : bi[tid] - o;
         }
-        __syncthreads();      // also: every thread is done with all panels of this stage
-        if (tid == 0) issue_next();
-        ++issued;
-        for (int k = tid; k < s; k += nth) {
-          double acc = rv[k];
-          for (int w2 = 0; w2 < (nth >> 5); ++w2) acc += cpart[w2 * smax + k];
-          bi[k] = (dir == 0) ? acc : bi[k] - acc;
-        }
-        if (tid == 0) mbar_wait(&bars[used % NBUF], (unsigned)((used / NBUF) & 1));    // next panel, single waiter
         __syncthreads();
         PROF_ADD(4);
-      } else {
-        if (tid == 0) mbar_wait(&bars[used % NBUF], (unsigned)((used / NBUF) & 1));    // next panel, single waiter
-        __syncthreads();      // the panel buffer may be refilled once every warp has left it
-        if (tid == 0) issue_next();
-        ++issued;
       }
     }
     // ---- z~ = A x~ ; relaxation, projection, dual update
@@ -799,7 +864,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     PROF_ADD(8);
     if (status != 0) break;
   }
-  for (long long k = used; k < issued; ++k) mbar_wait(&bars[k % NBUF], (unsigned)((k / NBUF) & 1));   // drain prefetches in flight
+  for (unsigned k = used; k < used + NBUF; ++k) mbar_wait(&bars[k & (NBUF - 1)], (k / NBUF) & 1u);   // drain prefetches in flight
   if (it > Q.max_iter) it = Q.max_iter;
   if (status == 0) status = -2;   // maximum iterations reached
   // failure detection beyond osqp's own codes: -10 the stage factorisation met a non-positive pivot, -11 NaN iterates
@@ -850,7 +915,7 @@ int plm_qp_alloc(plm_handle* h) {
   auto al = [&](double** p, size_t per) { return cudaMalloc(p, B * per * sizeof(double)); };
   QP_CUDA(h, al(&W.Ahat, L.nnz)); QP_CUDA(h, al(&W.AhatT, L.nnz)); QP_CUDA(h, al(&W.D, L.n)); QP_CUDA(h, al(&W.E, L.m)); QP_CUDA(h, al(&W.Eprev, L.m));
   QP_CUDA(h, al(&W.cscale, 1)); QP_CUDA(h, al(&W.Ph, L.n)); QP_CUDA(h, al(&W.qh, L.n)); QP_CUDA(h, al(&W.lh, L.m));
-  QP_CUDA(h, al(&W.uh, L.m)); QP_CUDA(h, al(&W.rho, L.m)); QP_CUDA(h, al(&W.Linv, Q.fac_total));
+  QP_CUDA(h, al(&W.uh, L.m)); QP_CUDA(h, al(&W.rho, L.m)); QP_CUDA(h, al(&W.Linv, Q.fac_total)); QP_CUDA(h, al(&W.Gc, (size_t)L.nodes * Q.g_doubles));
   QP_CUDA(h, al(&W.x, L.n)); QP_CUDA(h, al(&W.z, L.m)); QP_CUDA(h, al(&W.y, L.m));
   QP_CUDA(h, cudaMalloc(&h->d_qp_fail, B * sizeof(int)));
   QP_CUDA(h, cudaMemset(W.x, 0, B * L.n * sizeof(double)));
@@ -871,8 +936,8 @@ int plm_qp_alloc(plm_handle* h) {
   if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 2 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
-  h->smem_admm = (size_t)(NBUF * Q.panel_doubles + NBUF + 1 + L.n + L.m + (2 + ADMM_THREADS / 32) * smax + 32) * 8;
-  if (smax > 32 * SYM_J) { h->error = "stage size exceeds the lane-column capacity of the ADMM kernel"; return 7; }
+  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS) * smax + 32 + 2) * 8;
+  if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
     return 7;
@@ -886,7 +951,7 @@ int plm_qp_alloc(plm_handle* h) {
 void plm_qp_free(plm_handle* h) {
   QpWork& W = h->qp;
   cudaFree(W.d_ql); cudaFree(W.d_idx); cudaFree(W.d_idx32); cudaFree(W.AhatT); cudaFree(W.Ahat); cudaFree(W.D); cudaFree(W.E); cudaFree(W.Eprev);
-  cudaFree(W.cscale); cudaFree(W.Ph); cudaFree(W.qh); cudaFree(W.lh); cudaFree(W.uh); cudaFree(W.rho); cudaFree(W.Linv);
+  cudaFree(W.cscale); cudaFree(W.Ph); cudaFree(W.qh); cudaFree(W.lh); cudaFree(W.uh); cudaFree(W.rho); cudaFree(W.Linv); cudaFree(W.Gc);
   cudaFree(W.x); cudaFree(W.z); cudaFree(W.y); cudaFree(h->d_qp_fail);
 }
 

@@ -8,8 +8,9 @@ namespace plm {
 
 // A stage factor (packed lower triangle, row-major) is streamed through shared memory in panels of consecutive rows.
 #define PLM_PANEL_DOUBLES 2048        // 16 KB
-// schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage, direction
-// (0 forward, 1 backward), first panel of the stage, last panel of the stage}
+// schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage,
+// flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage),
+// offset of the copy inside the stage block, stage size | x_off << 8}
 #define PLM_SCHED_INTS 8
 #define PLM_LONG 8   // rows / columns with at least this many entries are multiplied by an 8-lane group
 
@@ -35,6 +36,7 @@ struct QpLayout {
   int32_t n_long_rows, n_long_cols;    // leading entries of rperm / cperm with at least PLM_LONG entries (lane-group products)            // int16 pool: rows / columns sorted by descending length (balanced warps)
   int32_t f_sched, n_sched;            // int32 pool: panel schedule of one ADMM iteration, 8 ints per step
   int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
+  int32_t g_doubles;                   // doubles of one stage's compact coupling block (4 per integrator row)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
   int32_t fac_total;
   int32_t smax;                        // largest stage size
@@ -60,7 +62,8 @@ struct QpWork {
   double* lh = nullptr;      // [m]     E l
   double* uh = nullptr;      // [m]     E u
   double* rho = nullptr;     // [m]     rho_vec
-  double* Linv = nullptr;    // [fac_total] packed lower-triangular inverses of the stage Cholesky factors
+  double* Linv = nullptr;    // [fac_total] packed inverse stage blocks S_i^-1
+  double* Gc = nullptr;      // [nodes][ndx][4] compact coupling blocks diag(rho n) A_int (sparse couplings only)
   double* x = nullptr;       // [n]     persistent scaled ADMM iterates
   double* z = nullptr;       // [m]
   double* y = nullptr;       // [m]
