@@ -401,6 +401,30 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     Q.n_long_rows = Q.n_long_cols = 0;
     for (int r : rperm) if (rptr[r + 1] - rptr[r] >= PLM_LONG) Q.n_long_rows++;
     for (int j : cperm) if (tptr[j + 1] - tptr[j] >= PLM_LONG) Q.n_long_cols++;
+    // sliced-ELL copies for the ADMM products: items (rows or columns) in order of decreasing length, 32 per slice, slot
+    // (j, lane) of a slice at base + 32 j + lane; src = CSR value position (-1 padding), ind = gathered index
+    auto build_ell = [&](const std::vector<int>& perm, const std::vector<int>& ptr, const std::vector<int>* srcmap, const std::vector<int>& indmap,
+                         int32_t& f_base, int32_t& f_src, int32_t& f_ind, int32_t& nsl, int32_t& total) {
+      const int nitems = (int)perm.size();
+      nsl = (nitems + 31) / 32;
+      std::vector<int> base(1, 0), src, ind;
+      for (int sl = 0; sl < nsl; ++sl) {
+        const int width = ptr[perm[32 * sl] + 1] - ptr[perm[32 * sl]];
+        for (int j = 0; j < width; ++j)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int it = 32 * sl + lane;
+            int e = -1;
+            if (it < nitems && j < ptr[perm[it] + 1] - ptr[perm[it]]) e = ptr[perm[it]] + j;
+            src.push_back(e < 0 ? -1 : (srcmap ? (*srcmap)[e] : e));
+            ind.push_back(e < 0 ? 0 : indmap[e]);
+          }
+        base.push_back((int)src.size());
+      }
+      total = (int)src.size();
+      f_base = push32(base); f_src = push32(src); f_ind = push(ind);
+    };
+    build_ell(rperm, rptr, nullptr, rcol, Q.f_rell_base, Q.f_rell_src, Q.f_rell_ind, Q.n_rslices, Q.rell_total);
+    build_ell(cperm, tptr, &tsrc, trow, Q.f_cell_base, Q.f_cell_src, Q.f_cell_ind, Q.n_cslices, Q.cell_total);
   }
   Q.sparse_coupling = 1;
   for (int t = 0; t < L.ntypes; ++t)
@@ -419,8 +443,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   {
     // panel schedule: forward sweep stages 0..N, backward sweep stages N-1..0, each stage cut into row panels
     std::vector<int> sched;
-    auto add_stage = [&](int i, int dir) {
-      const int s = (i < N) ? ndx + nu[i] : ndx;
+    auto stage_cuts = [&](int s) {
       std::vector<int> cuts(1, 0);
       int r = 0;
       while (r < s) {
@@ -429,6 +452,27 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
         cuts.push_back(r1);
         r = r1;
       }
+      return cuts;
+    };
+    // rows owned by each of the four warps of a part: ranges of <= 32 rows that do not straddle a panel when four
+    // warps suffice for that, else plain blocks of 32 (table id = node type, PLM_WR_TABLES - 1 for the final stage)
+    auto warp_ranges = [&](int s, int32_t* wr) {
+      const std::vector<int> cuts = stage_cuts(s);
+      std::vector<int> b(1, 0);
+      for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+        const int rows = cuts[k + 1] - cuts[k], nw = (rows + 31) / 32;
+        for (int q = 1; q <= nw; ++q) b.push_back(cuts[k] + (int)((long long)rows * q / nw));
+      }
+      if ((int)b.size() - 1 > 4) { b.assign(1, 0); for (int q = 1; q <= 4; ++q) b.push_back(std::min(s, 32 * q)); }
+      while ((int)b.size() < 5) b.push_back(s);
+      for (int q = 0; q < 5; ++q) wr[q] = b[q];
+    };
+    for (int t = 0; t < L.ntypes; ++t) warp_ranges(ndx + L.types[t].nu, Q.wr[t]);
+    warp_ranges(ndx, Q.wr[PLM_WR_TABLES - 1]);
+    auto add_stage = [&](int i, int dir) {
+      const int s = (i < N) ? ndx + nu[i] : ndx;
+      const std::vector<int> cuts = stage_cuts(s);
+      const int table = (i < N) ? L.node_type[i] : PLM_WR_TABLES - 1;
       for (size_t k = 0; k + 1 < cuts.size(); ++k) {
         const int r0 = cuts[k], r1 = cuts[k + 1];
         int o0 = r0 * (r0 + 1) / 2, o1 = r1 * (r1 + 1) / 2;
@@ -436,7 +480,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
         const int len = ((o1 - start) + 1) & ~1;
         sched.push_back(Q.fac_off[i] + start); sched.push_back(len); sched.push_back(r0); sched.push_back(r1);
         sched.push_back(i);
-        sched.push_back(dir | ((k == 0) << 1) | ((k + 2 == cuts.size()) << 2));
+        sched.push_back(dir | ((k == 0) << 1) | ((k + 2 == cuts.size()) << 2) | (table << 3));
         sched.push_back(start);
         sched.push_back(s | (L.x_off[i] << 8));
       }

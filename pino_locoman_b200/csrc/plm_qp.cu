@@ -137,6 +137,16 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
     W.qh[(size_t)b * n + j] = c * D[j] * q[j];
   }
   if (tid == 0) W.cscale[b] = c;
+  {
+    // sliced-ELL copies (same values, execution order of the ADMM products)
+    __syncthreads();
+    const int32_t* rsrc = idx32 + Q.f_rell_src;
+    const int32_t* csrc = idx32 + Q.f_cell_src;
+    double* AR = W.AhatR + (size_t)b * Q.rell_total;
+    double* AC = W.AhatC + (size_t)b * Q.cell_total;
+    for (int e = tid; e < Q.rell_total; e += nth) { const int sp = rsrc[e]; AR[e] = sp >= 0 ? Ah[sp] : 0.0; }
+    for (int e = tid; e < Q.cell_total; e += nth) { const int sp = csrc[e]; AC[e] = sp >= 0 ? Ah[sp] : 0.0; }
+  }
   const double* l = lin + (size_t)b * m;
   const double* u = uin + (size_t)b * m;
   for (int r = tid; r < m; r += nth) {
@@ -408,6 +418,38 @@ __device__ __forceinline__ void spmv_cols(const FlatIdx& F, int n, int nlong, co
   }
 }
 
+// Sliced-ELL product: warp per slice of 32 items, lane per item, coalesced value / index streams.
+//   out[perm[item]] = sum_j vals[slot] v[ind[slot]] (+ sigma x - q for the column product)
+#define ELL_B 8
+template <bool ADD>
+__device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const int16_t* __restrict__ ind, const int16_t* __restrict__ perm, int nitems,
+                                         int nsl, const double* __restrict__ vals, const double* v, double* out, double sigma,
+                                         const double* __restrict__ x, const double* __restrict__ q) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int sl = warp; sl < nsl; sl += nw) {
+    const int b0 = __ldg(base + sl) + lane, b1 = __ldg(base + sl + 1);
+    const int item = 32 * sl + lane;
+    const int o = item < nitems ? (int)__ldg(perm + item) : -1;
+    double add = 0.0;
+    if (ADD && o >= 0) add = sigma * __ldg(x + o) - __ldg(q + o);
+    double acc = 0.0;
+    for (int p = b0; p < b1; p += 32 * ELL_B) {
+      double a[ELL_B];
+      int c[ELL_B];
+#pragma unroll
+      for (int j = 0; j < ELL_B; ++j) {
+        const int pp = p + 32 * j;
+        const bool ok = pp < b1;
+        a[j] = ok ? __ldg(vals + pp) : 0.0;
+        c[j] = ok ? (int)__ldg(ind + pp) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < ELL_B; ++j) acc += a[j] * v[c[j]];
+    }
+    if (o >= 0) out[o] = acc + add;
+  }
+}
+
 // ---- 1-D bulk asynchronous copies global -> shared (TMA, UBLKCP) tracked by an mbarrier
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
@@ -441,12 +483,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // once and used twice (row part out[t] += S[t][k] in[k], column part out[k] += S[t][k] in[t], k < t):
 //   forward  stage i: tv_i = S_i^-1 (b_i - G_{i-1} tv_{i-1})
 //   backward stage i: x_i  = tv_i - S_i^-1 G_i^T x_{i+1}            (x_N = tv_N)
-#define ADMM_THREADS 384
-#define ADMM_MIN_CTAS 2
-#define NBUF 4
+#define ADMM_THREADS 256
+#define ADMM_MIN_CTAS 3
+#define NBUF 2
 #define SYM_K 128    // threads per part: thread (k, part) owns output k of the stage (stage size <= SYM_K), part = tid / SYM_K
 #define SYM_PARTS (ADMM_THREADS / SYM_K)
-static_assert(SYM_PARTS == 3 && ADMM_THREADS % SYM_K == 0, "the column walk of sym_panel steps three rows at a time");
+static_assert(ADMM_THREADS % SYM_K == 0 && (NBUF & (NBUF - 1)) == 0, "thread layout of sym_panel / buffer ring");
 
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -456,55 +498,74 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Thread (k, part) accumulates output k of out = S^-1 in over the resident panel rows [r0, r1): the column walk
 // S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k
 // (lane addresses tri(k) + e fall in distinct banks); both walks are split over the SYM_PARTS parts.  No cross-thread
-// reduction inside a stage: `acc` lives in a register across the panels of the stage.
+// reduction inside a stage: the sums live in registers across the panels of the stage.  A warp owns the rows
+// [ws, we) (host table: at most 32 rows, inside one panel whenever four warps suffice for that), k = ws + lane.
 // `pan` points at the panel buffer (shared memory), `zp` at a 0.0 in shared memory: masked elements load the zero
-// instead of branching.  Each walk is a masked part (rows / columns around the diagonal block of the warp) and an
-// unmasked main part with two independent accumulators.
+// instead of branching.  Each walk is a masked part (rows / columns of the warp's diagonal block) and an unmasked
+// main part; two independent accumulators.
 __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const double* __restrict__ zp, int shift, int r0, int r1,
-                                          const double* __restrict__ vin, double& acc0, double& acc1) {
-  const int k = threadIdx.x & (SYM_K - 1), part = threadIdx.x / SYM_K, kw = k & ~31;
-  {
-    // column walk: rows t = t0 + part, step SYM_PARTS, of the panel; element S[t][k] at tri(t) + k
-    int t = max(r0, kw + 1) + part;              // warp-uniform start; rows t <= k are masked
-    const double* pa = pan + (tri(t, 0) - shift + k);
+                                          const double* __restrict__ vin, int ws, int we, double& acc0, double& acc1) {
+  const int part = threadIdx.x / SYM_K;
+  const int k = ws + (threadIdx.x & 31);
+  const int kk = k < we ? k : 1 << 20;          // lanes beyond the warp's range own nothing: every row is "above" them
+  constexpr int P = SYM_PARTS;
+  if (ws + 1 < r1 && ws < we) {
+    // column walk: rows t = t0 + part, step P, of the panel; element S[t][k] at tri(t) + k
+    int t = max(r0, ws + 1) + part;              // warp-uniform start; rows t <= k are masked
+    const double* pa = pan + (tri(t, 0) - shift + min(k, we - 1));
     const double* pv = vin + t;
-    int dd = 3 * t + 6;                          // tri(t + 3) - tri(t)
-    const int tm = min(r1, kw + 32);
-    for (; t < tm; t += SYM_PARTS) {             // masked: the diagonal block of the warp
-      const double* q = (t > k) ? pa : zp;
-      acc0 += *q * *pv;
-      pa += dd; dd += 9; pv += SYM_PARTS;
-    }
+    int dd = P * t + P * (P + 1) / 2;            // tri(t + P) - tri(t)
+    const int tm = min(r1, we);
 #pragma unroll 2
-    for (; t + SYM_PARTS < r1; t += 2 * SYM_PARTS) {
-      const double a0 = pa[0], a1 = pa[dd];
-      const double v0 = pv[0], v1 = pv[SYM_PARTS];
+    for (; t < tm; t += 2 * P) {                 // masked: the diagonal block of the warp, two rows per trip
+      const bool in1 = t + P < r1;
+      const double* q0 = (t > kk) ? pa : zp;
+      const double* q1 = (in1 && t + P > kk) ? pa + dd : zp;
+      const double a0 = *q0, a1 = *q1;
+      const double v0 = pv[0], v1 = pv[in1 ? P : 0];
       acc0 += a0 * v0;
       acc1 += a1 * v1;
-      pa += 2 * dd + 9; dd += 18; pv += 2 * SYM_PARTS;
+      pa += 2 * dd + P * P; dd += 2 * P * P; pv += 2 * P;
     }
-    if (t < r1) acc0 += pa[0] * pv[0];
-  }
-  if (kw < r1 && kw + 32 > r0) {                 // warp-uniform: some row of this warp is resident
-    // row walk: S[k][e], e <= k, e = part + SYM_PARTS j
-    const bool mine = k >= r0 && k < r1;
-    const double* row = pan + (tri(mine ? k : r0, 0) - shift);
-    const int kk = mine ? k : -1;
-    int e = part;
-    if (kw >= r0 && kw + 31 < r1) {              // every row of the warp is resident: columns e <= kw need no mask
+    if (k < we) {
 #pragma unroll 2
-      for (; e + SYM_PARTS <= kw; e += 2 * SYM_PARTS) {
-        const double a0 = row[e], a1 = row[e + SYM_PARTS];
-        const double v0 = vin[e], v1 = vin[e + SYM_PARTS];
+      for (; t + P < r1; t += 2 * P) {
+        const double a0 = pa[0], a1 = pa[dd];
+        const double v0 = pv[0], v1 = pv[P];
         acc0 += a0 * v0;
         acc1 += a1 * v1;
+        pa += 2 * dd + P * P; dd += 2 * P * P; pv += 2 * P;
       }
+      if (t < r1) acc0 += pa[0] * pv[0];
     }
-    const int kend = min(kw + 31, r1 - 1);
-    for (; e <= kend; e += SYM_PARTS) {
-      const double* q = (e <= kk) ? row + e : zp;
-      acc1 += *q * vin[e];
+  }
+  if (ws < r1 && we > r0) {                      // warp-uniform: some row of this warp is resident
+    // row walk: S[k][e], e <= k, e = part + P j.  Lanes whose row is not resident walk a resident row and drop the sums.
+    const int lo = max(ws, r0), hi = min(we, r1);           // resident rows of the warp
+    const bool mine = k >= lo && k < hi;
+    const double* row = pan + (tri(min(max(k, lo), hi - 1), 0) - shift);
+    double ra0 = 0.0, ra1 = 0.0;
+    int e = part;
+#pragma unroll 2
+    for (; e + P <= lo; e += 2 * P) {            // columns e <= lo: below the diagonal block for every lane
+      const double a0 = row[e], a1 = row[e + P];
+      const double v0 = vin[e], v1 = vin[e + P];
+      ra0 += a0 * v0;
+      ra1 += a1 * v1;
     }
+    const int kend = hi - 1;
+    const int km = mine ? k : -1;
+#pragma unroll 2
+    for (; e <= kend; e += 2 * P) {              // the diagonal block, masked
+      const int e1 = min(e + P, kend);
+      const double* q0 = (e <= km) ? row + e : zp;
+      const double* q1 = (e + P <= km) ? row + e + P : zp;
+      const double a0 = *q0, a1 = *q1;
+      const double v0 = vin[e], v1 = vin[e1];
+      ra0 += a0 * v0;
+      ra1 += a1 * v1;
+    }
+    if (mine) { acc0 += ra0; acc1 += ra1; }
   }
 }
 
@@ -524,7 +585,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* gbuf = sm + NBUF * pdb;                      // [NBUF][gd] compact coupling block travelling with a stage's first panel
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(gbuf + NBUF * gd);  // [NBUF] "panel landed" barriers
   int* cnt = reinterpret_cast<int*>(gbuf + NBUF * gd + NBUF);                          // [NBUF] warps done with the panel (running count)
-  double* xt = gbuf + NBUF * gd + 2 * NBUF;   // [n]  rhs -> forward solution y -> x~ -> delta_x
+  int* wrs = cnt + NBUF;                                                                // [PLM_WR_TABLES][5] warp row ranges
+  double* xt = gbuf + NBUF * gd + 2 * NBUF + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   double* tv = w + m;          // [smax] G^T x of the next stage (backward sweep)
   double* cpart = tv + smax;   // [SYM_PARTS][smax] partial sums of the symmetric product, one slice per part
@@ -532,6 +594,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
+  const double* AR = W.AhatR + (size_t)b * Q.rell_total;
+  const double* AC = W.AhatC + (size_t)b * Q.cell_total;
   FlatIdx F;
   F.rptr = idx32 + Q.f_rptr; F.tptr = idx32 + Q.f_tptr; F.rcol = idx + Q.f_rcol; F.trow = idx + Q.f_trow; F.rperm = idx + Q.f_rperm; F.cperm = idx + Q.f_cperm;
   const int32_t* sched = idx32 + Q.f_sched;
@@ -570,6 +634,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   // mbarrier, and the last warp to finish step q refills the buffer with step q + NBUF.
   if (tid == 0) {
     for (int k = 0; k < NBUF; ++k) { mbar_init(&bars[k], 1); cnt[k] = 0; }
+    for (int k = 0; k < PLM_WR_TABLES * 5; ++k) wrs[k] = Q.wr[k / 5][k % 5];
     *zp = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -611,20 +676,35 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       }
     }
     __syncthreads();
-    spmv_cols(F, n, Q.n_long_cols, AT, w, xt, sigma, x, qh);
+    spmv_ell<true>(idx32 + Q.f_cell_base, idx + Q.f_cell_ind, F.cperm, n, Q.n_cslices, AC, w, xt, sigma, x, qh);
     __syncthreads();
     PROF_ADD(0);
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
     double acc0 = 0.0, acc1 = 0.0;
+    int ws = 0, we = 0;                       // rows of the current stage owned by this warp
+    int pend = -1, pend_st = 0;               // lane 0: deferred refill check of the previous step
+    int4 S0 = __ldg(reinterpret_cast<const int4*>(sched));
+    int4 S1 = __ldg(reinterpret_cast<const int4*>(sched) + 1);
     for (int st = 0; st < nsched; ++st) {
-      const int4 S0 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS));
-      const int4 S1 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS) + 1);
       const int r0 = S0.z, r1 = S0.w, i = S1.x, dir = S1.y & 1, first = S1.y & 2, last = S1.y & 4, shift = S1.z;
       const int s = S1.w & 255;
       double* bi = xt + (S1.w >> 8);
       const double* vin = (dir == 0) ? bi : tv;
       const int bsel = (int)(used & (NBUF - 1));
+      if (first) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
+      {   // schedule entry of the next step (consumed at the end of this one)
+        const int nst = st + 1 < nsched ? st + 1 : 0;
+        S0 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS));
+        S1 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS) + 1);
+      }
       mbar_wait(&bars[bsel], (used / NBUF) & 1u);
+      if (pend >= 0) {      // the previous step's buffer: refill it if this warp was the last one out
+        if ((pend + 1) % nwarps == 0) {
+          const int nx = pend_st + NBUF;
+          issue_step(nx >= nsched ? nx - nsched : nx, (int)((used - 1) & (NBUF - 1)));
+        }
+        pend = -1;
+      }
       PROF_ADD(2);
       if (first) {
         const double* g = gbuf + bsel * gd;
@@ -685,21 +765,34 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         }
         acc0 = 0.0; acc1 = 0.0;
       }
-      sym_panel(pbuf + bsel * pdb, zp, shift, r0, r1, vin, acc0, acc1);
-      __syncwarp();
-      if ((tid & 31) == 0) {
-        __threadfence_block();
-        if ((atomicAdd(&cnt[bsel], 1) + 1) % nwarps == 0) {
-          const int nx = st + NBUF;
-          issue_step(nx >= nsched ? nx - nsched : nx, bsel);
+      sym_panel(pbuf + bsel * pdb, zp, shift, r0, r1, vin, ws, we, acc0, acc1);
+      PROF_ADD(9);
+      {
+        // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
+        // shared-memory read of the panel by this warp has returned; the refill check is deferred past the next wait
+        const double sum = acc0 + acc1;
+        int zero;
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(__double2loint(sum)));
+        __syncwarp();
+        if ((tid & 31) == 0) { pend = atomicAdd(&cnt[bsel], 1 + zero); pend_st = st; }
+        ++used;
+        PROF_ADD(3);
+        if (last) {
+          // combine: out[k] = sum over the parts
+          const int k = ws + (tid & 31);
+          if (k < we) cpart[(tid / SYM_K) * smax + k] = sum;
         }
       }
-      ++used;
-      PROF_ADD(3);
       if (last) {
-        // combine: out[k] = sum over the parts
-        if ((tid & (SYM_K - 1)) < s) cpart[(tid / SYM_K) * smax + (tid & (SYM_K - 1))] = acc0 + acc1;
+        if (pend >= 0) {
+          if ((pend + 1) % nwarps == 0) {
+            const int nx = pend_st + NBUF;
+            issue_step(nx >= nsched ? nx - nsched : nx, bsel);
+          }
+          pend = -1;
+        }
         __syncthreads();
+        PROF_ADD(10);
         if (tid < s) {
           double o = cpart[tid];
 #pragma unroll
@@ -711,7 +804,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       }
     }
     // ---- z~ = A x~ ; relaxation, projection, dual update
-    spmv_rows(F, m, Q.n_long_rows, Ah, xt, w);
+    spmv_ell<false>(idx32 + Q.f_rell_base, idx + Q.f_rell_ind, F.rperm, m, Q.n_rslices, AR, xt, w, 0.0, nullptr, nullptr);
     __syncthreads();
     PROF_ADD(6);
     double mdx = 0.0;
@@ -913,7 +1006,7 @@ int plm_qp_alloc(plm_handle* h) {
   QP_CUDA(h, cudaMalloc(&W.d_idx32, h->host.qp_idx32.size() * sizeof(int32_t)));
   QP_CUDA(h, cudaMemcpy(W.d_idx32, h->host.qp_idx32.data(), h->host.qp_idx32.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   auto al = [&](double** p, size_t per) { return cudaMalloc(p, B * per * sizeof(double)); };
-  QP_CUDA(h, al(&W.Ahat, L.nnz)); QP_CUDA(h, al(&W.AhatT, L.nnz)); QP_CUDA(h, al(&W.D, L.n)); QP_CUDA(h, al(&W.E, L.m)); QP_CUDA(h, al(&W.Eprev, L.m));
+  QP_CUDA(h, al(&W.Ahat, L.nnz)); QP_CUDA(h, al(&W.AhatT, L.nnz)); QP_CUDA(h, al(&W.AhatR, Q.rell_total)); QP_CUDA(h, al(&W.AhatC, Q.cell_total)); QP_CUDA(h, al(&W.D, L.n)); QP_CUDA(h, al(&W.E, L.m)); QP_CUDA(h, al(&W.Eprev, L.m));
   QP_CUDA(h, al(&W.cscale, 1)); QP_CUDA(h, al(&W.Ph, L.n)); QP_CUDA(h, al(&W.qh, L.n)); QP_CUDA(h, al(&W.lh, L.m));
   QP_CUDA(h, al(&W.uh, L.m)); QP_CUDA(h, al(&W.rho, L.m)); QP_CUDA(h, al(&W.Linv, Q.fac_total)); QP_CUDA(h, al(&W.Gc, (size_t)L.nodes * Q.g_doubles));
   QP_CUDA(h, al(&W.x, L.n)); QP_CUDA(h, al(&W.z, L.m)); QP_CUDA(h, al(&W.y, L.m));
@@ -936,7 +1029,7 @@ int plm_qp_alloc(plm_handle* h) {
   if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 2 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
-  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS) * smax + 32 + 2) * 8;
+  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS) * smax + 32 + 2 + 16) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
@@ -951,7 +1044,7 @@ int plm_qp_alloc(plm_handle* h) {
 void plm_qp_free(plm_handle* h) {
   QpWork& W = h->qp;
   cudaFree(W.d_ql); cudaFree(W.d_idx); cudaFree(W.d_idx32); cudaFree(W.AhatT); cudaFree(W.Ahat); cudaFree(W.D); cudaFree(W.E); cudaFree(W.Eprev);
-  cudaFree(W.cscale); cudaFree(W.Ph); cudaFree(W.qh); cudaFree(W.lh); cudaFree(W.uh); cudaFree(W.rho); cudaFree(W.Linv); cudaFree(W.Gc);
+  cudaFree(W.cscale); cudaFree(W.Ph); cudaFree(W.qh); cudaFree(W.lh); cudaFree(W.uh); cudaFree(W.rho); cudaFree(W.Linv); cudaFree(W.Gc); cudaFree(W.AhatR); cudaFree(W.AhatC);
   cudaFree(W.x); cudaFree(W.z); cudaFree(W.y); cudaFree(h->d_qp_fail);
 }
 

@@ -9,9 +9,11 @@ namespace plm {
 // A stage factor (packed lower triangle, row-major) is streamed through shared memory in panels of consecutive rows.
 #define PLM_PANEL_DOUBLES 2048        // 16 KB
 // schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage,
-// flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage),
+// flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage,
+// bits 3.. warp row-range table),
 // offset of the copy inside the stage block, stage size | x_off << 8}
 #define PLM_SCHED_INTS 8
+#define PLM_WR_TABLES 5   // warp row-range tables: one per node type + the final stage
 #define PLM_LONG 8   // rows / columns with at least this many entries are multiplied by an 8-lane group
 
 // Per node-type local sparsity tables (offsets into one int16 pool).  Local columns of a node block are
@@ -34,8 +36,12 @@ struct QpLayout {
   int32_t f_rperm, f_cperm;
   int32_t sparse_coupling;             // every integrator row has at most 4 entries in its own stage (all but whole_body_aba / centroidal_vel)
   int32_t n_long_rows, n_long_cols;    // leading entries of rperm / cperm with at least PLM_LONG entries (lane-group products)            // int16 pool: rows / columns sorted by descending length (balanced warps)
+  // sliced-ELL copies of A^ for the ADMM products (see plm_host.cpp): slice bases / source positions (int32 pool), indices (int16 pool)
+  int32_t f_rell_base, f_rell_src, f_rell_ind, n_rslices, rell_total;
+  int32_t f_cell_base, f_cell_src, f_cell_ind, n_cslices, cell_total;
   int32_t f_sched, n_sched;            // int32 pool: panel schedule of one ADMM iteration, 8 ints per step
   int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
+  int32_t wr[PLM_WR_TABLES][5];        // rows [wr[q], wr[q+1]) of a stage are owned by warp q of each part (ADMM kernel)
   int32_t g_doubles;                   // doubles of one stage's compact coupling block (4 per integrator row)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
   int32_t fac_total;
@@ -53,6 +59,8 @@ struct QpWork {
   // per instance, [max_batch][...]
   double* Ahat = nullptr;    // [nnz]   E A D, CSR order (value order of J)
   double* AhatT = nullptr;   // [nnz]   the same values in CSC order
+  double* AhatR = nullptr;   // [rell_total] sliced-ELL by rows (z~ = A x~)
+  double* AhatC = nullptr;   // [cell_total] sliced-ELL by columns (A^T w)
   double* D = nullptr;       // [n]
   double* E = nullptr;       // [m]
   double* Eprev = nullptr;   // [m]     row scaling in force when the bounds are classified (osqp update order)
