@@ -251,7 +251,10 @@ class OCP:
             raise ValueError(f"Solver {self.solver} not supported")
 
     def solve(self, retract_all=True):
-        """One SQP iteration for every instance: sqp_data -> OSQP update/solve -> Armijo (optimization/ocp.py:375-422)."""
+        """One SQP iteration for every instance: sqp_data -> OSQP update/solve -> Armijo (optimization/ocp.py:375-422).
+
+        Returns the stacked solution [batch, n] (the reference returns nothing): a view of a pinned host buffer that the
+        call after next reuses; ``DX_prev`` / ``U_prev`` are views of the same buffer."""
         if self.solver != "osqp":
             raise ValueError(f"Solver {self.solver} not supported")
         h = self.handle
@@ -259,18 +262,28 @@ class OCP:
         start_time = time.time()
         if getattr(self, "_pin_x", None) is None:     # pinned staging buffers for the host <-> device copies
             self._pin_x = torch.empty(self.batch, self.n, dtype=torch.float64).pin_memory()
-            self._pin_out = torch.empty(self.batch, self.n + 8, dtype=torch.float64).pin_memory()
+            # two result buffers, used alternately: the solution returned by one call stays valid (and pinned, so
+            # it is the next call's input without a staging copy) while the next call writes the other
+            self._pin_out = [torch.empty(self.batch, self.n + 8, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._pin_sel = 0
             self._dev_out = torch.empty(self.batch, self.n + 8, dtype=torch.float64, device=h.device)
-        self._pin_x.numpy()[:] = current_x
-        xd = self._pin_x.to(h.device, non_blocking=True)
+        prev = self._pin_out[self._pin_sel ^ 1]
+        if isinstance(current_x, np.ndarray) and current_x.base is not None and np.shares_memory(current_x, prev.numpy()) \
+                and current_x.shape == (self.batch, self.n):
+            xd = prev[:, :self.n].to(h.device, non_blocking=True)       # previous solution: already in pinned memory
+        else:
+            self._pin_x.numpy()[:] = current_x
+            xd = self._pin_x.to(h.device, non_blocking=True)
         pd = self._p_device()
         x_new, stats = h.sqp_step(xd, pd)
         self._dev_out[:, :self.n] = x_new
         self._dev_out[:, self.n:] = stats
-        self._pin_out.copy_(self._dev_out, non_blocking=True)
+        pin_out = self._pin_out[self._pin_sel]
+        self._pin_sel ^= 1
+        pin_out.copy_(self._dev_out, non_blocking=True)
         torch.cuda.current_stream(h.device).synchronize()
-        out = self._pin_out.numpy()
-        sol_x = out[:, :self.n].copy()
+        out = pin_out.numpy()
+        sol_x = out[:, :self.n]
         self.stats = out[:, self.n:].copy()
         self.solve_time = time.time() - start_time
         self._x0 = sol_x
@@ -296,12 +309,12 @@ class OCP:
             o = h.x_off[i]
             dx_sol = sol_x[:, o:o + self.ndx_opt]
             u_sol = sol_x[:, o + self.ndx_opt:o + self.ndx_opt + self.nu_opt[i]]
-            self.DX_prev.append(np.array(dx_sol))
-            self.U_prev.append(np.array(u_sol))
+            self.DX_prev.append(dx_sol)      # views of the solution (a fresh buffer per solve)
+            self.U_prev.append(u_sol)
             if i == 0 or retract_all:
                 self._append_solution(self.state_integrate(x_init, dx_sol), u_sol)
         dx_last = sol_x[:, h.x_off[self.nodes]:]
-        self.DX_prev.append(np.array(dx_last))
+        self.DX_prev.append(dx_last)
         if retract_all:
             self._append_state(self.state_integrate(x_init, dx_last))
 
