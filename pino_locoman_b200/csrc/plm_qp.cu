@@ -184,7 +184,9 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   double* gsc = K + ndx * (ndx + 1) / 2;   // [ndx]  rho_r * (next entry)^2 of the integrator rows
   double* colk = gsc + ndx;            // [smax] current Cholesky column
   double* rowk = colk + smax;          // [smax] current row of the inverse
-  double* As = rowk + smax;            // [max_nnz] scaled A values of the node block
+  double* col1 = rowk + smax;          // [smax] second column / row of a rank-2 step
+  double* row1 = col1 + smax;
+  double* As = row1 + smax;            // [max_nnz] scaled A values of the node block
   double* rs = As + L.max_nnz;         // [max_rows] rho of the node rows
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* Ph = W.Ph + (size_t)b * n;
@@ -231,16 +233,55 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       }
     }
     __syncthreads();
-    // ---- right-looking Cholesky fused with the inversion of the factor, in place: after step k the columns <= k of the
-    // buffer hold X = L^-1 (rows > k partially applied), the columns > k the trailing matrix.  Two barriers per column.
-    for (int k = 0; k < s; ++k) {
+    // ---- right-looking Cholesky fused with the inversion of the factor, in place: after the step of column k the
+    // columns <= k of the buffer hold X = L^-1 (rows > k partially applied: Y[r][c] = -sum_{j<=k} L[r][j] X[j][c]), the
+    // columns > k the trailing matrix.  Two columns per step (rank-2 updates: half the barriers, two thirds of the
+    // shared-memory traffic of rank-1 steps); a single column is left over when s is odd.
+    const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
+    int k = 0;
+    for (; k + 1 < s; k += 2) {
+      const double piv0 = H[tri(k, k)];
+      const double d0 = 1.0 / sqrt(piv0 > 0.0 ? piv0 : 1.0);
+      const double l10 = H[tri(k + 1, k)] * d0;                    // L[k+1][k]
+      const double piv1 = H[tri(k + 1, k + 1)] - l10 * l10;
+      const double d1 = 1.0 / sqrt(piv1 > 0.0 ? piv1 : 1.0);
+      if (!(piv0 > 0.0 && piv1 > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
+      if (tid < s) {
+        const int r = tid;
+        if (r > k + 1) {                                           // columns k, k+1 of L
+          const double* Hr = H + tri(r, 0);
+          const double c0 = Hr[k] * d0;
+          colk[r] = c0;
+          col1[r] = (Hr[k + 1] - c0 * l10) * d1;
+        }
+        if (r <= k + 1) {                                          // rows k, k+1 of X (final)
+          const double x0 = (r == k) ? d0 : (r < k ? H[tri(k, r)] * d0 : 0.0);
+          rowk[r] = x0;
+          row1[r] = (r == k + 1) ? d1 : ((r < k ? H[tri(k + 1, r)] : 0.0) - l10 * x0) * d1;
+        }
+      }
+      __syncthreads();
+      for (int r = k + 2 + slot; r < s; r += nslot) {
+        const double a0 = colk[r], a1 = col1[r];
+        double* Hr = H + tri(r, 0);
+        for (int c2 = k + 2 + lane8; c2 <= r; c2 += 8) Hr[c2] -= a0 * colk[c2] + a1 * col1[c2];     // trailing matrix
+        for (int c2 = lane8; c2 < k; c2 += 8) Hr[c2] -= a0 * rowk[c2] + a1 * row1[c2];              // Y, columns < k
+        if (lane8 == 0) Hr[k] = -(a0 * rowk[k] + a1 * row1[k]);                                     // Y, column k
+        if (lane8 == 1) Hr[k + 1] = -a1 * row1[k + 1];                                              // Y, column k+1
+      }
+      if (tid <= k + 1) {
+        if (tid <= k) H[tri(k, tid)] = rowk[tid];
+        H[tri(k + 1, tid)] = row1[tid];
+      }
+      __syncthreads();
+    }
+    for (; k < s; ++k) {
       const double piv = H[tri(k, k)];
       if (!(piv > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
       const double dinv = 1.0 / sqrt(piv > 0.0 ? piv : 1.0);
       for (int r = k + 1 + tid; r < s; r += nth) colk[r] = H[tri(r, k)] * dinv;
       for (int c2 = tid; c2 <= k; c2 += nth) rowk[c2] = (c2 == k) ? dinv : H[tri(k, c2)] * dinv;   // row k of X is final
       __syncthreads();
-      const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
       for (int r = k + 1 + slot; r < s; r += nslot) {
         const double lrk = colk[r];
         double* Hr = H + tri(r, 0);
@@ -259,8 +300,14 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       const int c2 = e - tri(r, 0);
       double a0 = 0.0, a1 = 0.0;
       int t = r;
-      for (; t + 1 < s; t += 2) { a0 += H[tri(t, r)] * H[tri(t, c2)]; a1 += H[tri(t + 1, r)] * H[tri(t + 1, c2)]; }
-      if (t < s) a0 += H[tri(t, r)] * H[tri(t, c2)];
+      const double* Ht = H + tri(t, 0);          // row t of X; rows t, t+1 start t+1 apart
+      for (; t + 1 < s; t += 2) {
+        const double* Hu = Ht + t + 1;
+        a0 += Ht[r] * Ht[c2];
+        a1 += Hu[r] * Hu[c2];
+        Ht = Hu + t + 2;
+      }
+      if (t < s) a0 += Ht[r] * Ht[c2];
       Lout[Q.fac_off[i] + e] = a0 + a1;
     }
     if (last) break;
@@ -1027,7 +1074,7 @@ int plm_qp_alloc(plm_handle* h) {
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
   h->scale_stage_A = 0;
   if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
-  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 2 * smax + L.max_nnz + L.max_rows + 2) * 8;
+  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 4 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
   h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS) * smax + 32 + 2 + 16) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
