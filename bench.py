@@ -285,6 +285,29 @@ def main():
     ms_eval = e0.elapsed_time(e1) / reps
     launches += reps
     del g, J
+    # ---- closed loop: device-resident receding-horizon steps of every instance (gait update, warm
+    # start, one SQP iteration, state advance), nominal start states, extra key
+    from pino_locoman_b200.mpc import BatchedMPC
+    p_saved = ocp._p.copy()                 # the end-to-end leg below runs on the synthetic parameters again
+    ocp.update_initial_state(ocp.x_nom)
+    ocp._x0 = None
+    mpc = BatchedMPC(ocp, warm_start=True, t0=np.arange(B) % 80 * 0.01)
+    for _ in range(2):
+        mpc.step()
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mpc_steps = 3
+    m0.record()
+    for _ in range(mpc_steps):
+        mpc.step()
+    m1.record()
+    torch.cuda.synchronize()
+    ms_mpc = m0.elapsed_time(m1) / mpc_steps
+    mpc_iters = float(mpc.stats[:, 0].mean())
+    launches += h.launch_count() - launches0 - launches
+    del mpc
+    ocp._p[:] = p_saved
+    ocp._p_dirty = True
     # ---- BASELINE configs[1]: single B2 whole_body_rnea instance, latency of one SQP iteration (parity-test case, extra key)
     single_ms = None
     if rank == 0:
@@ -370,6 +393,8 @@ def main():
         "roofline_node_eval": {"kernel": "node_eval_kernel", "bound": "hbm", "achieved": ach_eval, "peak": peak, "unit": "GB/s",
                                "frac": ach_eval / peak, "traffic": traffic.get("node_eval_kernel"),
                                "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval},
+        "mpc": {"workload": "closed loop from the nominal state: gait update + warm start + 1 SQP iteration + state advance, device resident",
+                "mpc_steps_per_s": B / (ms_mpc / 1e3), "ms_per_step": ms_mpc, "admm_iters_avg": mpc_iters},
         "e2e": {"value": total_inst / (ms_e2e / 1e3), "unit": "SQP iters/s", "h2d_bytes_per_step": int(B * (n + h.np) * 8),
                 "d2h_bytes_per_step": int(B * (n + 8) * 8)},
         "single_instance": {"workload": "b2 whole_body_rnea trot N=20, 1 instance (BASELINE configs[1])", "ms_per_sqp_iter": single_ms},

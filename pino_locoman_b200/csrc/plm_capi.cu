@@ -111,6 +111,7 @@ void plm_destroy(plm_handle* h) {
   cudaFree(h->d_lut);
   cudaFree(h->d_consts);
   cudaFree(h->d_tgt);
+  cudaFree(h->d_mpc_dts);
   delete h;
 }
 

@@ -1,0 +1,61 @@
+"""GPU: the device-resident receding-horizon step (plm_mpc_step / BatchedMPC) against the same loop driven through the
+plugin surface from the host (run_mpc.py:115-143), whose parity with the oracle tests/test_gpu_ocp_api.py establishes."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _configure(o, kind, x_init, t, dt_min):
+    o.set_time_params(dt_min, 0.08)
+    o.set_swing_params(0.07, [0.1, -0.2])
+    o.set_tracking_targets(np.array([0.2, 0, 0, 0, 0, 0]), np.zeros(3), np.zeros(3))
+    o.update_initial_state(x_init)
+    o.update_gait_sequence(t)
+    if kind == "whole_body_rnea":
+        o.update_previous_torques(np.zeros(o.nj))
+
+
+@pytest.mark.parametrize("rn,kind,N,gait", [("b2g", "whole_body_rnea", 6, "trot"), ("go2", "centroidal_vel", 5, "walk"),
+                                            ("b2", "whole_body_acc", 5, "stand")])
+def test_device_resident_mpc_matches_host_loop(rn, kind, N, gait):
+    from pino_locoman_b200 import OCP_ARGS
+    from pino_locoman_b200.mpc import BatchedMPC
+    from pino_locoman_b200.optimization import make_ocp
+    from pino_locoman_b200.utils import robot as prob
+    B, loops, dt_min = 3, 4, 0.01
+    t0 = np.array([0.0, 0.21, 0.4])
+
+    def make():
+        r = {"b2g": prob.B2G, "go2": prob.Go2, "b2": prob.B2}[rn]()
+        r.set_gait_sequence(gait, 0.8)
+        return make_ocp(dynamics=kind, default_args=OCP_ARGS[kind], robot=r, nodes=N, solver="osqp", batch=B)
+
+    host, dev = make(), make()
+    x_init = np.stack([host.x_nom] * B)
+    x_init[1, 7:host.nq] += 0.05          # instances differ
+    _configure(host, kind, x_init, t0, dt_min)
+    _configure(dev, kind, x_init, t0, dt_min)
+    host.init_solver()
+    dev.init_solver()
+    mpc = BatchedMPC(dev, warm_start=True, t0=t0)
+    co, so = host.handle.p_off["contact_schedule"], host.handle.p_off["swing_schedule"]
+    for k in range(loops):
+        t = t0 + k * dt_min
+        host.update_initial_state(x_init)
+        host.update_gait_sequence(t)
+        host.warm_start()
+        sol = host.solve(retract_all=False)
+        x_init = host.state_integrate(x_init, host.DX_prev[1])
+        stats = mpc.step().cpu().numpy()
+        p_dev = mpc.p.cpu().numpy()
+        # gait schedules: bit for bit
+        assert np.array_equal(p_dev[:, co:co + 4 * N], host._p[:, co:co + 4 * N]), k
+        assert np.array_equal(p_dev[:, so:so + 4 * N], host._p[:, so:so + 4 * N]), k
+        x_dev = mpc.solution().cpu().numpy()
+        scale = max(1.0, np.abs(sol).max())
+        assert np.abs(x_dev - sol).max() <= 1e-9 * scale, (k, np.abs(x_dev - sol).max())
+        assert np.array_equal(stats[:, :2], host.stats[:, :2])          # ADMM iterations and status
+        assert np.abs(mpc.x_init().cpu().numpy() - x_init).max() <= 1e-9
+    assert mpc.k == loops
