@@ -75,3 +75,35 @@ def test_sqp_iterations_match_oracle(robots, rn, kind, N, iters):
             assert abs(stats[b, 7] - info["violation_max"]) <= 1e-6 * max(1.0, info["violation_max"])
     ms = h.last_phase_ms()
     assert len(ms) == 4 and all(v >= 0 for v in ms)
+
+
+def test_full_size_sqp_step_is_deterministic(robots):
+    """Bench workload (B2G whole_body_rnea, N=20) on 1332 instances = three full waves of the ADMM kernel: instances are
+    independent, so copies of one problem at different batch positions (different CTAs, different co-resident
+    neighbours, different waves) must produce bit-identical steps, ADMM iteration counts and statuses -- the
+    lock-free panel pipeline of the ADMM kernel must not depend on timing -- and two runs must agree bit for bit."""
+    from pino_locoman_b200.handle import Handle
+    prod, ora = robots
+    rng = np.random.default_rng(11)
+    o = OracleOCP(ora["b2g"], "whole_body_rnea", 20)
+    B, nbase = 1332, 6
+    h = Handle(prod["b2g"], "whole_body_rnea", 20, max_batch=B)
+    base = [random_problem(o, rng) for _ in range(nbase)]
+    idx = rng.integers(0, nbase, B)
+    x = torch.tensor(np.stack([base[i][0] for i in idx]), device="cuda")
+    p = torch.tensor(np.stack([base[i][1] for i in idx]), device="cuda")
+    h.qp_setup(h.hess_diag(p))
+    x1, s1 = h.sqp_step(x, p)
+    x1, s1 = x1.clone(), s1.clone()
+    first = {int(i): int(np.argmax(idx == i)) for i in set(idx.tolist())}
+    ref = torch.tensor([first[int(i)] for i in idx], device="cuda")
+    assert torch.equal(x1, x1[ref])
+    assert torch.equal(s1, s1[ref])
+    assert torch.isfinite(x1).all()
+    # a second handle from scratch (fresh workspaces, cold ADMM warm start) reproduces the step bit for bit
+    h2 = Handle(prod["b2g"], "whole_body_rnea", 20, max_batch=B)
+    h2.qp_setup(h2.hess_diag(p))
+    x2, s2 = h2.sqp_step(x, p)
+    assert torch.equal(x1, x2) and torch.equal(s1, s2)
+    # every instance ran the ADMM loop at least to its first termination check
+    assert (s1[:, 0] >= 25).all()
