@@ -551,7 +551,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // instead of branching.  Each walk is a masked part (rows / columns of the warp's diagonal block) and an unmasked
 // main part; two independent accumulators.
 __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const double* __restrict__ zp, int shift, int r0, int r1,
-                                          const double* __restrict__ vin, int ws, int we, double& acc0, double& acc1) {
+                                          const double* __restrict__ vin, int ws, int we, double& acc0, double& acc1, double& racc) {
   const int part = threadIdx.x / SYM_K;
   const int k = ws + (threadIdx.x & 31);
   const int kk = k < we ? k : 1 << 20;          // lanes beyond the warp's range own nothing: every row is "above" them
@@ -588,7 +588,11 @@ __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const 
   }
   if (ws < r1 && we > r0) {                      // warp-uniform: some row of this warp is resident
     // row walk: S[k][e], e <= k, e = part + P j.  Lanes whose row is not resident walk a resident row and drop the sums.
+    // The row walk uses its own lane-to-row map (even rows in lanes 0-15, odd rows in lanes 16-31): the addresses
+    // tri(ws + 2 l) + e of a half-warp then fall in 16 distinct 8-byte banks for every ws.
     const int lo = max(ws, r0), hi = min(we, r1);           // resident rows of the warp
+    const int lane = threadIdx.x & 31;
+    const int k = ws + ((lane & 15) << 1) + (lane >> 4);
     const bool mine = k >= lo && k < hi;
     const double* row = pan + (tri(min(max(k, lo), hi - 1), 0) - shift);
     double ra0 = 0.0, ra1 = 0.0;
@@ -612,7 +616,7 @@ __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const 
       ra0 += a0 * v0;
       ra1 += a1 * v1;
     }
-    if (mine) { acc0 += ra0; acc1 += ra1; }
+    if (mine) racc += ra0 + ra1;
   }
 }
 
@@ -727,7 +731,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     __syncthreads();
     PROF_ADD(0);
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
-    double acc0 = 0.0, acc1 = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, racc = 0.0;
     int ws = 0, we = 0;                       // rows of the current stage owned by this warp
     int pend = -1, pend_st = 0;               // lane 0: deferred refill check of the previous step
     int4 S0 = __ldg(reinterpret_cast<const int4*>(sched));
@@ -810,24 +814,30 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           __syncthreads();
           PROF_ADD(5);
         }
-        acc0 = 0.0; acc1 = 0.0;
+        acc0 = 0.0; acc1 = 0.0; racc = 0.0;
       }
-      sym_panel(pbuf + bsel * pdb, zp, shift, r0, r1, vin, ws, we, acc0, acc1);
+      sym_panel(pbuf + bsel * pdb, zp, shift, r0, r1, vin, ws, we, acc0, acc1, racc);
       PROF_ADD(9);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
         // shared-memory read of the panel by this warp has returned; the refill check is deferred past the next wait
         const double sum = acc0 + acc1;
         int zero;
-        asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(__double2loint(sum)));
+        // (racc depends on the row-walk loads the same way: fold it into the dependency)
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(__double2loint(sum) ^ __double2loint(racc)));
         __syncwarp();
         if ((tid & 31) == 0) { pend = atomicAdd(&cnt[bsel], 1 + zero); pend_st = st; }
         ++used;
         PROF_ADD(3);
         if (last) {
-          // combine: out[k] = sum over the parts
-          const int k = ws + (tid & 31);
-          if (k < we) cpart[(tid / SYM_K) * smax + k] = sum;
+          // combine: out[k] = sum over the parts; the column-walk sums and the row-walk sums of a warp cover the same
+          // rows in two lane orders
+          const int lane = tid & 31;
+          const int k = ws + lane, kr = ws + ((lane & 15) << 1) + (lane >> 4);
+          double* cp = cpart + (tid / SYM_K) * smax;
+          if (k < we) cp[k] = sum;
+          __syncwarp();
+          if (kr < we) cp[kr] += racc;
         }
       }
       if (last) {
