@@ -543,78 +543,91 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Thread (k, part) accumulates output k of out = S^-1 in over the resident panel rows [r0, r1): the column walk
-// S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k
-// (lane addresses tri(k) + e fall in distinct banks); both walks are split over the SYM_PARTS parts.  No cross-thread
-// reduction inside a stage: the sums live in registers across the panels of the stage.  A warp owns the rows
-// [ws, we) (host table: at most 32 rows, inside one panel whenever four warps suffice for that), k = ws + lane.
-// `pan` points at the panel buffer (shared memory), `zp` at a 0.0 in shared memory: masked elements load the zero
-// instead of branching.  Each walk is a masked part (rows / columns of the warp's diagonal block) and an unmasked
-// main part; two independent accumulators.
+// S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k;
+// both walks are split over the SYM_PARTS parts.  No cross-thread reduction inside a stage: the sums live in registers
+// across the panels of the stage.  A warp owns the rows [ws, we) (host table: at most 32 rows, inside one panel
+// whenever four warps suffice for that); the column walk maps lane l to k = ws + l, the row walk to even rows in lanes
+// 0-15 and odd rows in lanes 16-31 (the addresses tri(ws + 2 l) + e of a half-warp fall in 16 distinct 8-byte banks).
+// Both walks advance two rows / columns at a time so that the pair in[t], in[t+1] is one 16-byte load (the walk starts
+// on the 16-byte boundary of `vin`; a leading odd element is handled alone).  `pan` points at the panel buffer,
+// `zp` at a 0.0 in shared memory: masked elements load the zero instead of branching.
+__device__ __forceinline__ double2 lds_pair(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
 __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const double* __restrict__ zp, int shift, int r0, int r1,
                                           const double* __restrict__ vin, int ws, int we, double& acc0, double& acc1, double& racc) {
-  const int part = threadIdx.x / SYM_K;
-  const int k = ws + (threadIdx.x & 31);
-  const int kk = k < we ? k : 1 << 20;          // lanes beyond the warp's range own nothing: every row is "above" them
+  const int part = threadIdx.x / SYM_K, lane = threadIdx.x & 31;
   constexpr int P = SYM_PARTS;
+  const int vodd = (int)((reinterpret_cast<size_t>(vin) >> 3) & 1);      // vin + t is 16-byte aligned iff (t + vodd) is even
   if (ws + 1 < r1 && ws < we) {
-    // column walk: rows t = t0 + part, step P, of the panel; element S[t][k] at tri(t) + k
-    int t = max(r0, ws + 1) + part;              // warp-uniform start; rows t <= k are masked
-    const double* pa = pan + (tri(t, 0) - shift + min(k, we - 1));
-    const double* pv = vin + t;
-    int dd = P * t + P * (P + 1) / 2;            // tri(t + P) - tri(t)
+    // ---- column walk: element S[t][k] at tri(t) + k, rows t > k of the panel
+    const int k = ws + lane;
+    const int kk = k < we ? k : 1 << 20;        // lanes beyond the warp's range own nothing: every row is "above" them
+    const int kc = min(k, we - 1);
+    int t = max(r0, ws + 1);                    // warp-uniform start; rows t <= k are masked
+    if ((t + vodd) & 1) {                       // leading row off the 16-byte grid of vin: part 0 takes it alone
+      if (part == 0) {
+        const double* q = (t > kk) ? pan + (tri(t, 0) - shift + kc) : zp;
+        acc0 += *q * vin[t];
+      }
+      ++t;
+    }
+    t += 2 * part;
+    const double* pa = pan + (tri(t, 0) - shift + kc);
+    int dd = 2 * P * t + P * (2 * P + 1);       // tri(t + 2P) - tri(t)
     const int tm = min(r1, we);
 #pragma unroll 2
-    for (; t < tm; t += 2 * P) {                 // masked: the diagonal block of the warp, two rows per trip
-      const bool in1 = t + P < r1;
+    for (; t < tm; t += 2 * P) {                // masked: the diagonal block of the warp
+      const bool in1 = t + 1 < r1;
       const double* q0 = (t > kk) ? pa : zp;
-      const double* q1 = (in1 && t + P > kk) ? pa + dd : zp;
+      const double* q1 = (in1 && t + 1 > kk) ? pa + t + 1 : zp;
       const double a0 = *q0, a1 = *q1;
-      const double v0 = pv[0], v1 = pv[in1 ? P : 0];
-      acc0 += a0 * v0;
-      acc1 += a1 * v1;
-      pa += 2 * dd + P * P; dd += 2 * P * P; pv += 2 * P;
+      const double2 v = lds_pair(vin + t);      // v.y is finite even beyond the panel (the vectors are zero-initialised)
+      acc0 += a0 * v.x;
+      acc1 += a1 * v.y;
+      pa += dd; dd += 4 * P * P;
     }
     if (k < we) {
 #pragma unroll 2
-      for (; t + P < r1; t += 2 * P) {
-        const double a0 = pa[0], a1 = pa[dd];
-        const double v0 = pv[0], v1 = pv[P];
-        acc0 += a0 * v0;
-        acc1 += a1 * v1;
-        pa += 2 * dd + P * P; dd += 2 * P * P; pv += 2 * P;
+      for (; t + 1 < r1; t += 2 * P) {
+        const double a0 = pa[0], a1 = pa[t + 1];
+        const double2 v = lds_pair(vin + t);
+        acc0 += a0 * v.x;
+        acc1 += a1 * v.y;
+        pa += dd; dd += 4 * P * P;
       }
-      if (t < r1) acc0 += pa[0] * pv[0];
+      if (t < r1) acc0 += pa[0] * vin[t];
     }
   }
   if (ws < r1 && we > r0) {                      // warp-uniform: some row of this warp is resident
-    // row walk: S[k][e], e <= k, e = part + P j.  Lanes whose row is not resident walk a resident row and drop the sums.
-    // The row walk uses its own lane-to-row map (even rows in lanes 0-15, odd rows in lanes 16-31): the addresses
-    // tri(ws + 2 l) + e of a half-warp then fall in 16 distinct 8-byte banks for every ws.
+    // ---- row walk: S[k][e], e <= k.  Lanes whose row is not resident walk a resident row and drop the sums.
     const int lo = max(ws, r0), hi = min(we, r1);           // resident rows of the warp
-    const int lane = threadIdx.x & 31;
     const int k = ws + ((lane & 15) << 1) + (lane >> 4);
     const bool mine = k >= lo && k < hi;
+    const int km = mine ? k : -1;
     const double* row = pan + (tri(min(max(k, lo), hi - 1), 0) - shift);
     double ra0 = 0.0, ra1 = 0.0;
-    int e = part;
+    int e = 0;
+    if (vodd) {                                  // column 0 off the 16-byte grid of vin
+      if (part == 0) ra0 += *((0 <= km) ? row : zp) * vin[0];
+      e = 1;
+    }
+    e += 2 * part;
 #pragma unroll 2
-    for (; e + P <= lo; e += 2 * P) {            // columns e <= lo: below the diagonal block for every lane
-      const double a0 = row[e], a1 = row[e + P];
-      const double v0 = vin[e], v1 = vin[e + P];
-      ra0 += a0 * v0;
-      ra1 += a1 * v1;
+    for (; e + 1 <= lo; e += 2 * P) {            // columns e, e+1 <= lo: below the diagonal block for every lane
+      const double a0 = row[e], a1 = row[e + 1];
+      const double2 v = lds_pair(vin + e);
+      ra0 += a0 * v.x;
+      ra1 += a1 * v.y;
     }
     const int kend = hi - 1;
-    const int km = mine ? k : -1;
 #pragma unroll 2
     for (; e <= kend; e += 2 * P) {              // the diagonal block, masked
-      const int e1 = min(e + P, kend);
       const double* q0 = (e <= km) ? row + e : zp;
-      const double* q1 = (e + P <= km) ? row + e + P : zp;
+      const double* q1 = (e + 1 <= km) ? row + e + 1 : zp;
       const double a0 = *q0, a1 = *q1;
-      const double v0 = vin[e], v1 = vin[e1];
-      ra0 += a0 * v0;
-      ra1 += a1 * v1;
+      const double2 v = lds_pair(vin + e);
+      ra0 += a0 * v.x;
+      ra1 += a1 * v.y;
     }
     if (mine) racc += ra0 + ra1;
   }
@@ -687,8 +700,11 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     for (int k = 0; k < NBUF; ++k) { mbar_init(&bars[k], 1); cnt[k] = 0; }
     for (int k = 0; k < PLM_WR_TABLES * 5; ++k) wrs[k] = Q.wr[k / 5][k % 5];
     *zp = 0.0;
+    zp[1] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // 16-byte loads of sym_panel may read one element past a stage vector: keep every shared vector finite
+  for (int j = tid; j < (int)(zp + 2 - xt); j += nth) xt[j] = 0.0;
   __syncthreads();
   unsigned used = 0;
   auto issue_step = [&](int st, int buf) {            // one thread: schedule step st into buffer buf
