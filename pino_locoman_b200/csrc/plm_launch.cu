@@ -81,8 +81,11 @@ int plm_line_search_impl(plm_handle* h, const double* x, const double* p, const 
   PLM_LAUNCH_CHECK(h);
   armijo_init_kernel<<<(batch + 127) / 128, 128, 0, s>>>(batch, W.f0, W.viol, W.gdot, W.state, W.accepted);
   PLM_LAUNCH_CHECK(h);
-  const int ranges[3] = {0, 1, T};
-  for (int k = 0; k < 2; ++k) {
+  // trials are evaluated in rounds: every instance tries the full step, then the instances not yet accepted try the
+  // next candidates (most accept within the first two); the remaining ones evaluate all remaining step sizes at once
+  const int ranges[5] = {0, 1, 2, 4 < T ? 4 : T, T};
+  for (int k = 0; k < 4; ++k) {
+    if (ranges[k + 1] <= ranges[k]) continue;
     const int t0 = ranges[k], cnt = ranges[k + 1] - ranges[k];
     TrialArgs tr;
     tr.dxs = dx; tr.alphas = W.alphas; tr.t0 = t0; tr.ntrial = cnt; tr.ntot = T;
