@@ -79,6 +79,8 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   const int32_t* tsrc = idx32 + Q.f_tsrc;
   const int16_t* rcol = idx + Q.f_rcol;
   const int16_t* trow = idx + Q.f_trow;
+  const int16_t* rperm = idx + Q.f_rperm;      // rows / columns by decreasing length: the lanes of a warp get equal work
+  const int16_t* cperm = idx + Q.f_cperm;
   const double* P = hess + (size_t)b * n;
   const double* Ag = Jv ? Jv + (size_t)b * nnz : nullptr;     // mode 1: A = ones on the pattern
   const double* q = qin ? qin + (size_t)b * n : nullptr;
@@ -95,12 +97,14 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   __syncthreads();
   for (int pass = 0; pass < Q.scaling; ++pass) {
     // row norms of the current scaled A: E_r * max_k |A_rk| D_col ; column norms: max(|P^_jj|, D_j * max_r E_r |A_rj|)
-    for (int r = tid; r < m; r += nth) {
+    for (int i = tid; i < m; i += nth) {
+      const int r = rperm[i];
       double v = 0.0;
       for (int e = rptr[r]; e < rptr[r + 1]; ++e) v = fmax(v, (A ? fabs(A[e]) : 1.0) * D[rcol[e]]);
       Eg[r] = E[r] / sqrt(limit_scaling(E[r] * v));
     }
-    for (int j = tid; j < n; j += nth) {
+    for (int i = tid; i < n; i += nth) {
+      const int j = cperm[i];
       double v = 0.0;
       for (int e = tptr[j]; e < tptr[j + 1]; ++e) v = fmax(v, (A ? fabs(A[tsrc[e]]) : 1.0) * E[trow[e]]);
       v = fmax(D[j] * v, c * D[j] * D[j] * fabs(P[j]));
@@ -128,10 +132,14 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   // scaled data: CSR-ordered and CSC-ordered copies of E A D
   double* Ah = W.Ahat + (size_t)b * nnz;
   double* AT = W.AhatT + (size_t)b * nnz;
-  for (int r = tid; r < m; r += nth)
+  for (int i = tid; i < m; i += nth) {
+    const int r = rperm[i];
     for (int e = rptr[r]; e < rptr[r + 1]; ++e) Ah[e] = E[r] * A[e] * D[rcol[e]];
-  for (int j = tid; j < n; j += nth)
+  }
+  for (int i = tid; i < n; i += nth) {
+    const int j = cperm[i];
     for (int e = tptr[j]; e < tptr[j + 1]; ++e) AT[e] = E[trow[e]] * A[tsrc[e]] * D[j];
+  }
   for (int j = tid; j < n; j += nth) {
     W.Ph[(size_t)b * n + j] = c * D[j] * D[j] * P[j];
     W.qh[(size_t)b * n + j] = c * D[j] * q[j];
