@@ -248,13 +248,13 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
     int k = 0;
     for (; k + 1 < s; k += 2) {
-      const double piv0 = H[tri(k, k)];
-      const double d0 = 1.0 / sqrt(piv0 > 0.0 ? piv0 : 1.0);
-      const double l10 = H[tri(k + 1, k)] * d0;                    // L[k+1][k]
-      const double piv1 = H[tri(k + 1, k + 1)] - l10 * l10;
-      const double d1 = 1.0 / sqrt(piv1 > 0.0 ? piv1 : 1.0);
-      if (!(piv0 > 0.0 && piv1 > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
-      if (tid < s) {
+      if (tid < s) {                                               // (warps beyond the stage size skip the square roots)
+        const double piv0 = H[tri(k, k)];
+        const double d0 = 1.0 / sqrt(piv0 > 0.0 ? piv0 : 1.0);
+        const double l10 = H[tri(k + 1, k)] * d0;                  // L[k+1][k]
+        const double piv1 = H[tri(k + 1, k + 1)] - l10 * l10;
+        const double d1 = 1.0 / sqrt(piv1 > 0.0 ? piv1 : 1.0);
+        if (!(piv0 > 0.0 && piv1 > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
         const int r = tid;
         if (r > k + 1) {                                           // columns k, k+1 of L
           const double* Hr = H + tri(r, 0);
