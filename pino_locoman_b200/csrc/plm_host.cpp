@@ -398,9 +398,6 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     std::stable_sort(rperm.begin(), rperm.end(), [&](int a, int b) { return rptr[a + 1] - rptr[a] > rptr[b + 1] - rptr[b]; });
     std::stable_sort(cperm.begin(), cperm.end(), [&](int a, int b) { return tptr[a + 1] - tptr[a] > tptr[b + 1] - tptr[b]; });
     Q.f_rperm = push(rperm); Q.f_cperm = push(cperm);
-    Q.n_long_rows = Q.n_long_cols = 0;
-    for (int r : rperm) if (rptr[r + 1] - rptr[r] >= PLM_LONG) Q.n_long_rows++;
-    for (int j : cperm) if (tptr[j + 1] - tptr[j] >= PLM_LONG) Q.n_long_cols++;
     // sliced-ELL copies for the ADMM products: items (rows or columns) in order of decreasing length, 32 per slice, slot
     // (j, lane) of a slice at base + 32 j + lane; src = CSR value position (-1 padding), ind = gathered index
     auto build_ell = [&](const std::vector<int>& perm, const std::vector<int>& ptr, const std::vector<int>* srcmap, const std::vector<int>& indmap,

@@ -64,7 +64,7 @@ __device__ __forceinline__ StageView stage_view(const PlmLayout& L, const QpLayo
 __global__ void __launch_bounds__(QP_THREADS)
 qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, int mode,
                 const double* __restrict__ hess, const double* __restrict__ qin, const double* __restrict__ Jv,
-                const double* __restrict__ lin, const double* __restrict__ uin, QpWork W, int stage_A) {
+                const double* __restrict__ lin, const double* __restrict__ uin, QpWork W) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
   const QpLayout& Q = *Qp;
@@ -73,7 +73,6 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   double* D = sm;            // [n]
   double* E = D + n;         // [m]
   double* red = E + m;       // [32]
-  double* As = red + 32;     // [nnz] when the values fit in shared memory
   const int32_t* rptr = idx32 + Q.f_rptr;
   const int32_t* tptr = idx32 + Q.f_tptr;
   const int32_t* tsrc = idx32 + Q.f_tsrc;
@@ -86,11 +85,7 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   const double* q = qin ? qin + (size_t)b * n : nullptr;
   double* Dg = W.D + (size_t)b * n;      // also the exchange buffers of the Jacobi-style update
   double* Eg = W.E + (size_t)b * m;
-  const double* A = Ag;
-  if (stage_A && Ag) {
-    for (int e = tid; e < nnz; e += nth) As[e] = Ag[e];
-    A = As;
-  }
+  const double* A = Ag;     // read from L2 in every pass: staging 160 KB of values would leave one CTA per SM
   for (int j = tid; j < n; j += nth) D[j] = 1.0;
   for (int r = tid; r < m; r += nth) E[r] = 1.0;
   double c = 1.0;
@@ -389,89 +384,11 @@ __device__ long long g_admm_prof[16];
 #define PROF_ADD(k)
 #endif
 
-struct AdmmVec {
-  double *x, *z, *y, *xt, *w, *t, *yv;   // shared-memory vectors
-};
-
 // Flat index tables of the whole pattern (shared by all instances).
 struct FlatIdx {
   const int32_t *rptr, *tptr;
   const int16_t *rcol, *trow, *rperm, *cperm;
 };
-
-__device__ __forceinline__ double group8_sum(double v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v;
-}
-
-// Sparse products.  All global loads of a work item are issued before the first use (the SM issues in order: a
-// load that is consumed immediately serialises the DRAM latencies of the loop).
-#define SPMV_B 6   // entries fetched per lane and batch
-__device__ __forceinline__ double dot_batch(const double* __restrict__ vals, const int16_t* __restrict__ ind, int e0, int e1, int stride,
-                                            const double* v) {
-  double acc = 0.0;
-  for (int e = e0; e < e1; e += SPMV_B * stride) {
-    double a[SPMV_B];
-    int c[SPMV_B];
-#pragma unroll
-    for (int j = 0; j < SPMV_B; ++j) {
-      const int ee = e + j * stride;
-      const bool ok = ee < e1;
-      a[j] = ok ? __ldg(vals + ee) : 0.0;
-      c[j] = ok ? (int)__ldg(ind + ee) : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < SPMV_B; ++j) acc += a[j] * v[c[j]];
-  }
-  return acc;
-}
-
-// out[r] = sum_k A_rk v[col]  for all rows (CSR order values), v indexed by global column.
-// Rows are visited in order of decreasing length: the long ones by 8-lane groups (coalesced value / index loads),
-// the short ones one per thread.
-__device__ __forceinline__ void spmv_rows(const FlatIdx& F, int m, int nlong, const double* __restrict__ Ah, const double* v, double* out) {
-  const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7, ngrp = blockDim.x >> 3;
-  for (int i0 = 0; i0 < nlong; i0 += ngrp) {
-    const int i = i0 + grp;
-    double acc = 0.0;
-    int r = 0;
-    if (i < nlong) {
-      r = F.rperm[i];
-      acc = dot_batch(Ah, F.rcol, F.rptr[r] + l8, F.rptr[r + 1], 8, v);
-    }
-    acc = group8_sum(acc);
-    if (i < nlong && l8 == 0) out[r] = acc;
-  }
-  for (int i = nlong + threadIdx.x; i < m; i += blockDim.x) {
-    const int r = F.rperm[i];
-    out[r] = dot_batch(Ah, F.rcol, F.rptr[r], F.rptr[r + 1], 1, v);
-  }
-}
-
-// out[j] = sum_r A_rj w[r] + sigma x[j] - q[j]  for all columns (CSC order values)
-__device__ __forceinline__ void spmv_cols(const FlatIdx& F, int n, int nlong, const double* __restrict__ AT, const double* w, double* out,
-                                          double sigma, const double* __restrict__ x, const double* __restrict__ q) {
-  const int grp = threadIdx.x >> 3, l8 = threadIdx.x & 7, ngrp = blockDim.x >> 3;
-  for (int i0 = 0; i0 < nlong; i0 += ngrp) {
-    const int i = i0 + grp;
-    double acc = 0.0, add = 0.0;
-    int j = 0;
-    if (i < nlong) {
-      j = F.cperm[i];
-      if (l8 == 0) add = sigma * __ldg(x + j) - __ldg(q + j);
-      acc = dot_batch(AT, F.trow, F.tptr[j] + l8, F.tptr[j + 1], 8, w);
-    }
-    acc = group8_sum(acc);
-    if (i < nlong && l8 == 0) out[j] = acc + add;
-  }
-  for (int i = nlong + threadIdx.x; i < n; i += blockDim.x) {
-    const int j = F.cperm[i];
-    const double add = sigma * __ldg(x + j) - __ldg(q + j);
-    out[j] = dot_batch(AT, F.trow, F.tptr[j], F.tptr[j + 1], 1, w) + add;
-  }
-}
 
 // Sliced-ELL product: warp per slice of 32 items, lane per item, coalesced value / index streams.
 //   out[perm[item]] = sum_j vals[slot] v[ind[slot]] (+ sigma x - q for the column product)
@@ -479,14 +396,14 @@ __device__ __forceinline__ void spmv_cols(const FlatIdx& F, int n, int nlong, co
 template <bool ADD>
 __device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const int16_t* __restrict__ ind, const int16_t* __restrict__ perm, int nitems,
                                          int nsl, const double* __restrict__ vals, const double* v, double* out, double sigma,
-                                         const double* __restrict__ x, const double* __restrict__ q) {
+                                         const double* x, const double* __restrict__ q) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int sl = warp; sl < nsl; sl += nw) {
     const int b0 = __ldg(base + sl) + lane, b1 = __ldg(base + sl + 1);
     const int item = 32 * sl + lane;
     const int o = item < nitems ? (int)__ldg(perm + item) : -1;
     double add = 0.0;
-    if (ADD && o >= 0) add = sigma * __ldg(x + o) - __ldg(q + o);
+    if (ADD && o >= 0) add = sigma * x[o] - __ldg(q + o);      // x is rewritten by this kernel: coherent load
     double acc = 0.0;
     for (int p = b0; p < b1; p += 32 * ELL_B) {
       double a[ELL_B];
@@ -544,11 +461,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #define SYM_K 128    // threads per part: thread (k, part) owns output k of the stage (stage size <= SYM_K), part = tid / SYM_K
 #define SYM_PARTS (ADMM_THREADS / SYM_K)
 static_assert(ADMM_THREADS % SYM_K == 0 && (NBUF & (NBUF - 1)) == 0, "thread layout of sym_panel / buffer ring");
-
-__device__ __forceinline__ double warp_sum(double v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // Thread (k, part) accumulates output k of out = S^-1 in over the resident panel rows [r0, r1): the column walk
 // S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k;
@@ -1106,8 +1018,6 @@ int plm_qp_alloc(plm_handle* h) {
   const int smax = Q.smax, ndx = L.ndx;
   h->smem_scale = (size_t)(L.n + L.m + 32) * 8;
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
-  h->scale_stage_A = 0;
-  if (h->scale_stage_A) h->smem_scale += (size_t)L.nnz * 8;
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 4 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
   h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS) * smax + 32 + 2 + 16) * 8;
@@ -1135,7 +1045,7 @@ int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream
   QP_CUDA(h, cudaMemsetAsync(W.x, 0, (size_t)batch * L.n * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.z, 0, (size_t)batch * L.m * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.y, 0, (size_t)batch * L.m * sizeof(double), s));
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W, 0);
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1143,7 +1053,7 @@ int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J,
                        const double* d_l, const double* d_u, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, d_hess, d_q, d_J, d_l, d_u, W, h->scale_stage_A);
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, d_hess, d_q, d_J, d_l, d_u, W);
   PLM_LAUNCH_CHECK(h);
   qp_factor_kernel<<<batch, QP_THREADS, h->smem_factor, s>>>(h->tab, W.d_ql, W.d_idx, W, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);

@@ -14,7 +14,6 @@ namespace plm {
 // offset of the copy inside the stage block, stage size | x_off << 8}
 #define PLM_SCHED_INTS 8
 #define PLM_WR_TABLES 5   // warp row-range tables: one per node type + the final stage
-#define PLM_LONG 8   // rows / columns with at least this many entries are multiplied by an 8-lane group
 
 // Per node-type local sparsity tables (offsets into one int16 pool).  Local columns of a node block are
 // [0, s) = this stage (DX_i | U_i) and [s, s + ndx) = DX_{i+1}; local rows are the node's rows in g order.
@@ -33,9 +32,8 @@ struct QpLayout {
   // flat (whole-problem) index tables, offsets into the int32 pool: CSR row pointers, CSC column pointers,
   // CSC source positions (into the CSR value order); and into the int16 pool: CSR global columns, CSC global rows
   int32_t f_rptr, f_tptr, f_tsrc, f_rcol, f_trow;
-  int32_t f_rperm, f_cperm;
+  int32_t f_rperm, f_cperm;            // int16 pool: rows / columns sorted by descending length (balanced warps)
   int32_t sparse_coupling;             // every integrator row has at most 4 entries in its own stage (all but whole_body_aba / centroidal_vel)
-  int32_t n_long_rows, n_long_cols;    // leading entries of rperm / cperm with at least PLM_LONG entries (lane-group products)            // int16 pool: rows / columns sorted by descending length (balanced warps)
   // sliced-ELL copies of A^ for the ADMM products (see plm_host.cpp): slice bases / source positions (int32 pool), indices (int16 pool)
   int32_t f_rell_base, f_rell_src, f_rell_ind, n_rslices, rell_total;
   int32_t f_cell_base, f_cell_src, f_cell_ind, n_cslices, cell_total;
