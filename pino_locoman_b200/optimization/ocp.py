@@ -262,29 +262,27 @@ class OCP:
         start_time = time.time()
         if getattr(self, "_pin_x", None) is None:     # pinned staging buffers for the host <-> device copies
             self._pin_x = torch.empty(self.batch, self.n, dtype=torch.float64).pin_memory()
-            # two result buffers, used alternately: the solution returned by one call stays valid (and pinned, so
-            # it is the next call's input without a staging copy) while the next call writes the other
-            self._pin_out = [torch.empty(self.batch, self.n + 8, dtype=torch.float64).pin_memory() for _ in range(2)]
+            # two result buffers, used alternately: the solution returned by one call stays valid (and pinned and
+            # contiguous, so it is the next call's input without a staging copy) while the next call writes the other
+            self._pin_out = [torch.empty(self.batch, self.n, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._pin_stats = torch.empty(self.batch, 8, dtype=torch.float64).pin_memory()
             self._pin_sel = 0
-            self._dev_out = torch.empty(self.batch, self.n + 8, dtype=torch.float64, device=h.device)
         prev = self._pin_out[self._pin_sel ^ 1]
-        if isinstance(current_x, np.ndarray) and current_x.base is not None and np.shares_memory(current_x, prev.numpy()) \
-                and current_x.shape == (self.batch, self.n):
-            xd = prev[:, :self.n].to(h.device, non_blocking=True)       # previous solution: already in pinned memory
+        if isinstance(current_x, np.ndarray) and current_x.shape == (self.batch, self.n) and np.shares_memory(current_x, prev.numpy()) \
+                and current_x.ctypes.data == prev.data_ptr():
+            xd = prev.to(h.device, non_blocking=True)       # previous solution: already in pinned memory
         else:
             self._pin_x.numpy()[:] = current_x
             xd = self._pin_x.to(h.device, non_blocking=True)
         pd = self._p_device()
         x_new, stats = h.sqp_step(xd, pd)
-        self._dev_out[:, :self.n] = x_new
-        self._dev_out[:, self.n:] = stats
         pin_out = self._pin_out[self._pin_sel]
         self._pin_sel ^= 1
-        pin_out.copy_(self._dev_out, non_blocking=True)
+        pin_out.copy_(x_new, non_blocking=True)
+        self._pin_stats.copy_(stats, non_blocking=True)
         torch.cuda.current_stream(h.device).synchronize()
-        out = pin_out.numpy()
-        sol_x = out[:, :self.n]
-        self.stats = out[:, self.n:].copy()
+        sol_x = pin_out.numpy()
+        self.stats = self._pin_stats.numpy().copy()
         self.solve_time = time.time() - start_time
         self._x0 = sol_x
         self.retract_stacked_sol(sol_x, retract_all)
