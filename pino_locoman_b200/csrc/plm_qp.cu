@@ -173,6 +173,14 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
+// D = A B + C on the FP64 tensor cores (DMMA m8n8k4).  Lane l holds A[l/4][l%4] (8x4, row major), B[l%4][l/4] (4x8,
+// column major) and C / D [l/4][2 (l%4) + {0, 1}] (8x8).
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
 __global__ void __launch_bounds__(QP_THREADS, 3)
 qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, QpWork W, int* __restrict__ fail) {
   extern __shared__ double sm[];
@@ -189,7 +197,9 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   double* rowk = colk + smax;          // [smax] current row of the inverse
   double* col1 = rowk + smax;          // [smax] second column / row of a rank-2 step
   double* row1 = col1 + smax;
-  double* As = row1 + smax;            // [max_nnz] scaled A values of the node block
+  double* La = row1 + smax;            // [4][smax] rank-4 step: minus the four new columns of L (rows below the block)
+  double* Wv = colk;                   // [4][smax] rank-4 step: right factors (X rows | inverse block | L columns), aliases the vectors above
+  double* As = La + 4 * smax;          // [max_nnz] scaled A values of the node block
   double* rs = As + L.max_nnz;         // [max_rows] rho of the node rows
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* Ph = W.Ph + (size_t)b * n;
@@ -242,6 +252,82 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     // shared-memory traffic of rank-1 steps); a single column is left over when s is odd.
     const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
     int k = 0;
+    // Four columns per step on the FP64 tensor cores.  Phase A (one thread per row / column): Cholesky of the 4x4
+    // diagonal block, the four new columns of L, the four new rows of X and the inverse of the block; the block
+    // columns of the rows below are zeroed.  Phase B: one rank-4 update H[r][c] -= sum_j L[r][k+j] W_j[c] of every
+    // row below the block over ALL columns c <= r, with W_j[c] = X[k+j][c] (c < k), the inverse block (k <= c < k+4)
+    // and L[c][k+j] (c >= k+4): the Y part, the block columns and the trailing matrix in one pass of 8x8 tiles.
+    for (; k + 3 < s; k += 4) {
+      if (tid < s) {
+        const double* H0 = H + tri(k, k);
+        const double* H1 = H + tri(k + 1, k);
+        const double* H2 = H + tri(k + 2, k);
+        const double* H3 = H + tri(k + 3, k);
+        const double p0 = H0[0];
+        const double i0 = 1.0 / sqrt(p0 > 0.0 ? p0 : 1.0);
+        const double l10 = H1[0] * i0, l20 = H2[0] * i0, l30 = H3[0] * i0;
+        const double p1 = H1[1] - l10 * l10;
+        const double i1 = 1.0 / sqrt(p1 > 0.0 ? p1 : 1.0);
+        const double l21 = (H2[1] - l20 * l10) * i1, l31 = (H3[1] - l30 * l10) * i1;
+        const double p2 = H2[2] - l20 * l20 - l21 * l21;
+        const double i2 = 1.0 / sqrt(p2 > 0.0 ? p2 : 1.0);
+        const double l32 = (H3[2] - l30 * l20 - l31 * l21) * i2;
+        const double p3 = H3[3] - l30 * l30 - l31 * l31 - l32 * l32;
+        const double i3 = 1.0 / sqrt(p3 > 0.0 ? p3 : 1.0);
+        if (!(p0 > 0.0 && p1 > 0.0 && p2 > 0.0 && p3 > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
+        const int r = tid;
+        double w0, w1, w2, w3;
+        if (r > k + 3) {                         // row r of the four new columns of L
+          double* Hr = H + tri(r, k);
+          w0 = Hr[0] * i0;
+          w1 = (Hr[1] - w0 * l10) * i1;
+          w2 = (Hr[2] - w0 * l20 - w1 * l21) * i2;
+          w3 = (Hr[3] - w0 * l30 - w1 * l31 - w2 * l32) * i3;
+          La[r] = -w0; La[smax + r] = -w1; La[2 * smax + r] = -w2; La[3 * smax + r] = -w3;
+          Hr[0] = 0.0; Hr[1] = 0.0; Hr[2] = 0.0; Hr[3] = 0.0;
+        } else if (r < k) {                      // column r of the four new rows of X
+          w0 = H[tri(k, r)] * i0;
+          w1 = (H[tri(k + 1, r)] - l10 * w0) * i1;
+          w2 = (H[tri(k + 2, r)] - l20 * w0 - l21 * w1) * i2;
+          w3 = (H[tri(k + 3, r)] - l30 * w0 - l31 * w1 - l32 * w2) * i3;
+        } else {                                 // column q = r - k of the inverse of the diagonal block
+          const int q = r - k;
+          w0 = (q == 0) ? i0 : 0.0;
+          w1 = (q == 1) ? i1 : (q < 1 ? -(l10 * w0) * i1 : 0.0);
+          w2 = (q == 2) ? i2 : (q < 2 ? -(l20 * w0 + l21 * w1) * i2 : 0.0);
+          w3 = (q == 3) ? i3 : -(l30 * w0 + l31 * w1 + l32 * w2) * i3;
+        }
+        Wv[r] = w0; Wv[smax + r] = w1; Wv[2 * smax + r] = w2; Wv[3 * smax + r] = w3;
+      }
+      __syncthreads();
+      {
+        const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+        const int R0 = k + 4, ntr = (s - R0 + 7) >> 3, ntc = (s + 7) >> 3;
+        const int fr = lane >> 2, fk = lane & 3;
+        for (int t = warp; t < ntr * ntc; t += nw) {
+          const int tr = t / ntc, tc = t - tr * ntc;
+          const int r0 = R0 + 8 * tr, c0 = 8 * tc;
+          if (c0 > r0 + 7) continue;             // tile above the diagonal (warp-uniform)
+          const int ar = r0 + fr, bc = c0 + fr;
+          const double a = ar < s ? La[fk * smax + ar] : 0.0;
+          const double bv = bc < s ? Wv[fk * smax + bc] : 0.0;
+          const int cc = c0 + 2 * fk;
+          double* Hc = H + tri(ar < s ? ar : 0, 0) + cc;
+          const bool v0 = ar < s && cc <= ar, v1 = ar < s && cc + 1 <= ar;
+          const double e0 = v0 ? Hc[0] : 0.0, e1 = v1 ? Hc[1] : 0.0;
+          double d0, d1;
+          dmma884(d0, d1, a, bv, e0, e1);
+          if (v0) Hc[0] = d0;
+          if (v1) Hc[1] = d1;
+        }
+        // rows k .. k+3 of X are final (phase B touches only the rows below)
+        if (tid <= k + 3) {
+          for (int j = 0; j < 4; ++j)
+            if (tid <= k + j) H[tri(k + j, tid)] = Wv[j * smax + tid];
+        }
+      }
+      __syncthreads();
+    }
     for (; k + 1 < s; k += 2) {
       if (tid < s) {                                               // (warps beyond the stage size skip the square roots)
         const double piv0 = H[tri(k, k)];
@@ -1018,7 +1104,7 @@ int plm_qp_alloc(plm_handle* h) {
   const int smax = Q.smax, ndx = L.ndx;
   h->smem_scale = (size_t)(L.n + L.m + 32) * 8;
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
-  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 4 * smax + L.max_nnz + L.max_rows + 2) * 8;
+  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 8 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
   h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS) * smax + 32 + 2 + 16) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
