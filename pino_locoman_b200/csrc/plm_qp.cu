@@ -381,23 +381,32 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       for (int c2 = tid; c2 <= k; c2 += nth) H[tri(k, c2)] = rowk[c2];
       __syncthreads();
     }
-    // ---- S_i^-1 = X^T X (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit)
-    for (int e = tid; e < s * (s + 1) / 2; e += nth) {
-      int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while (tri(r + 1, 0) <= e) ++r;
-      while (tri(r, 0) > e) --r;
-      const int c2 = e - tri(r, 0);
-      double a0 = 0.0, a1 = 0.0;
-      int t = r;
-      const double* Ht = H + tri(t, 0);          // row t of X; rows t, t+1 start t+1 apart
-      for (; t + 1 < s; t += 2) {
-        const double* Hu = Ht + t + 1;
-        a0 += Ht[r] * Ht[c2];
-        a1 += Hu[r] * Hu[c2];
-        Ht = Hu + t + 2;
+    // ---- S_i^-1 = X^T X (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit).
+    // 8x8 output tiles on the FP64 tensor cores: S[r][c] = sum_{t >= r} X[t][r] X[t][c], four rows t of X per DMMA.
+    {
+      const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+      const int nt8 = (s + 7) >> 3;
+      const int fr = lane >> 2, fk = lane & 3;
+      double* So = Lout + Q.fac_off[i];
+      for (int t8 = warp; t8 < nt8 * nt8; t8 += nw) {
+        const int tr = t8 / nt8, tc = t8 - tr * nt8;
+        if (tc > tr) continue;                   // upper tiles (warp-uniform)
+        const int r0 = 8 * tr, c0 = 8 * tc;
+        const int ra = r0 + fr, cb = c0 + fr;    // this lane's column of X in the A / B fragments
+        double d0 = 0.0, d1 = 0.0;
+        for (int t = r0; t < s; t += 4) {
+          const int tt = t + fk;
+          const double* Xt = H + tri(tt < s ? tt : 0, 0);
+          const double a = (tt < s && ra <= tt) ? Xt[ra] : 0.0;
+          const double bv = (tt < s && cb <= tt) ? Xt[cb] : 0.0;
+          dmma884(d0, d1, a, bv, d0, d1);
+        }
+        const int cc = c0 + 2 * fk;
+        if (ra < s) {
+          if (cc <= ra) So[tri(ra, cc)] = d0;
+          if (cc + 1 <= ra) So[tri(ra, cc + 1)] = d1;
+        }
       }
-      if (t < s) a0 += Ht[r] * Ht[c2];
-      Lout[Q.fac_off[i] + e] = a0 + a1;
     }
     if (last) break;
     // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = X G^T ; K = W^T W
