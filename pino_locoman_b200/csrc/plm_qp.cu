@@ -264,16 +264,16 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
         const double* H2 = H + tri(k + 2, k);
         const double* H3 = H + tri(k + 3, k);
         const double p0 = H0[0];
-        const double i0 = 1.0 / sqrt(p0 > 0.0 ? p0 : 1.0);
+        const double i0 = rsqrt(p0 > 0.0 ? p0 : 1.0);
         const double l10 = H1[0] * i0, l20 = H2[0] * i0, l30 = H3[0] * i0;
         const double p1 = H1[1] - l10 * l10;
-        const double i1 = 1.0 / sqrt(p1 > 0.0 ? p1 : 1.0);
+        const double i1 = rsqrt(p1 > 0.0 ? p1 : 1.0);
         const double l21 = (H2[1] - l20 * l10) * i1, l31 = (H3[1] - l30 * l10) * i1;
         const double p2 = H2[2] - l20 * l20 - l21 * l21;
-        const double i2 = 1.0 / sqrt(p2 > 0.0 ? p2 : 1.0);
+        const double i2 = rsqrt(p2 > 0.0 ? p2 : 1.0);
         const double l32 = (H3[2] - l30 * l20 - l31 * l21) * i2;
         const double p3 = H3[3] - l30 * l30 - l31 * l31 - l32 * l32;
-        const double i3 = 1.0 / sqrt(p3 > 0.0 ? p3 : 1.0);
+        const double i3 = rsqrt(p3 > 0.0 ? p3 : 1.0);
         if (!(p0 > 0.0 && p1 > 0.0 && p2 > 0.0 && p3 > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
         const int r = tid;
         double w0, w1, w2, w3;
@@ -302,12 +302,16 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       __syncthreads();
       {
         const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
-        const int R0 = k + 4, ntr = (s - R0 + 7) >> 3, ntc = (s + 7) >> 3;
+        const int R0 = k + 4, ntr = (s - R0 + 7) >> 3;
         const int fr = lane >> 2, fk = lane & 3;
-        for (int t = warp; t < ntr * ntc; t += nw) {
-          const int tr = t / ntc, tc = t - tr * ntc;
-          const int r0 = R0 + 8 * tr, c0 = 8 * tc;
-          if (c0 > r0 + 7) continue;             // tile above the diagonal (warp-uniform)
+        // tiles of the lower triangle, dealt round robin to the warps (running tile count, no division)
+        int turn = warp;                         // tiles until this warp's next one
+        for (int tr = 0; tr < ntr; ++tr) {
+         const int r0 = R0 + 8 * tr, nc = ((r0 + 7 < s ? r0 + 7 : s - 1) >> 3) + 1;
+         int tc = turn;
+         turn = (turn >= nc) ? turn - nc : (nw - 1) - ((nc - 1 - turn) % nw);
+         for (; tc < nc; tc += nw) {
+          const int c0 = 8 * tc;
           const int ar = r0 + fr, bc = c0 + fr;
           const double a = ar < s ? La[fk * smax + ar] : 0.0;
           const double bv = bc < s ? Wv[fk * smax + bc] : 0.0;
@@ -319,6 +323,7 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
           dmma884(d0, d1, a, bv, e0, e1);
           if (v0) Hc[0] = d0;
           if (v1) Hc[1] = d1;
+         }
         }
         // rows k .. k+3 of X are final (phase B touches only the rows below)
         if (tid <= k + 3) {
@@ -388,9 +393,12 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       const int nt8 = (s + 7) >> 3;
       const int fr = lane >> 2, fk = lane & 3;
       double* So = Lout + Q.fac_off[i];
-      for (int t8 = warp; t8 < nt8 * nt8; t8 += nw) {
-        const int tr = t8 / nt8, tc = t8 - tr * nt8;
-        if (tc > tr) continue;                   // upper tiles (warp-uniform)
+      int turn = warp;                           // lower tiles dealt round robin to the warps (see the rank-4 update)
+      for (int tr = 0; tr < nt8; ++tr) {
+       const int nc = tr + 1;
+       int tc = turn;
+       turn = (turn >= nc) ? turn - nc : (nw - 1) - ((nc - 1 - turn) % nw);
+       for (; tc < nc; tc += nw) {
         const int r0 = 8 * tr, c0 = 8 * tc;
         const int ra = r0 + fr, cb = c0 + fr;    // this lane's column of X in the A / B fragments
         double d0 = 0.0, d1 = 0.0;
@@ -406,6 +414,7 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
           if (cc <= ra) So[tri(ra, cc)] = d0;
           if (cc + 1 <= ra) So[tri(ra, cc + 1)] = d1;
         }
+       }
       }
     }
     if (last) break;
