@@ -965,7 +965,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const double eps_abs = Q.eps_abs * kk, eps_rel = Q.eps_rel * kk, eps_pinf = Q.eps_prim_inf * kk, eps_dinf = Q.eps_dual_inf * kk;
       // primal residual ||E^-1 (A x - z)||, norms of E^-1 z and E^-1 A x
       double pr = 0.0, nz = 0.0, nax = 0.0;
-      for (int r = tid; r < m; r += nth) {
+      for (int i2 = tid; i2 < m; i2 += nth) {       // rows by decreasing length: balanced warps (max-reductions only)
+        const int r = F.rperm[i2];
         double ax = 0.0;
         for (int e = F.rptr[r]; e < F.rptr[r + 1]; ++e) ax += Ah[e] * x[F.rcol[e]];
         const double ei = 1.0 / Ev[r];
@@ -978,7 +979,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       nax = block_reduce(nax, red, true);
       // dual residual ||D^-1 (P x + q + A^T y)|| / c
       double dr = 0.0, nq = 0.0, naty = 0.0, npx = 0.0;
-      for (int j = tid; j < n; j += nth) {
+      for (int i2 = tid; i2 < n; i2 += nth) {
+        const int j = F.cperm[i2];
         double acc = 0.0;
         for (int e = F.tptr[j]; e < F.tptr[j + 1]; ++e) acc += AT[e] * y[F.trow[e]];
         const double di = 1.0 / Dv[j];
