@@ -169,3 +169,60 @@ def test_oracle_jacobian_vs_finite_differences(robots):
     fm, _ = o.f_data(x - eps * d, p)
     assert abs((fp - fm) / (2 * eps) - grad @ d) < 1e-6 * abs(grad @ d)
     assert np.allclose(np.diag(np.diag(o.hess_diag(p))) @ d * 0 + o.hess_diag(p) * d, (o.f_data(x + d, p)[1] - grad), rtol=1e-9, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["go2", "b2g"])
+def test_rnea_against_lagrangian_mechanics(name):
+    """Independent derivation: the oracle's RNEA against Lagrange's equations built from forward kinematics and the
+    link inertial parameters only (no spatial-algebra recursion): kinetic energy T = 1/2 sum m |v_c|^2 + w^T I w from
+    finite-differenced link poses, potential U = sum m g z_c.
+      * v^T M(q) v = 2 T(q, v) with M taken from RNEA columns,
+      * gravity torques rnea(q, 0, 0) = dU/dq along every tangent direction,
+      * power balance: v^T (M a + nle) = d/dt (T + U) along the motion."""
+    r = OracleRobot(name)
+    m = r.model
+    rng = np.random.default_rng(21)
+    q, v, a, _ = _random_state(r, rng)
+    z = np.zeros(m.nv)
+    kin = rbd.Kin(m, q)
+
+    def link_poses(qq):
+        k = rbd.Kin(m, qq)
+        return [(k.oR[i], k.op[i] + k.oR[i] @ m.com[i]) for i in range(1, m.njoints)]
+
+    def inertia_world(i, R):
+        return R @ np.asarray(m.Ic[i]) @ R.T
+
+    def energies(qq, vv):
+        """T from central differences of the link poses along vv; U from the CoM heights."""
+        eps = 1e-6
+        pp, pm, p0 = link_poses(rbd.integrate(m, qq, eps * vv)), link_poses(rbd.integrate(m, qq, -eps * vv)), link_poses(qq)
+        T = U = 0.0
+        for i in range(1, m.njoints):
+            (Rp, cp), (Rm, cm), (R0, c0) = pp[i - 1], pm[i - 1], p0[i - 1]
+            vc = (cp - cm) / (2 * eps)
+            W = (Rp - Rm) / (2 * eps) @ R0.T                 # [w]x in the world frame
+            w = np.array([W[2, 1], W[0, 2], W[1, 0]])
+            T += 0.5 * m.mass[i] * vc @ vc + 0.5 * w @ inertia_world(i, R0) @ w
+            U += m.mass[i] * 9.81 * c0[2]
+        return T, U
+
+    M = np.stack([rbd.rnea(m, kin, z, e, {}) - rbd.rnea(m, kin, z, z, {}) for e in np.eye(m.nv)], -1)
+    T, _ = energies(q, v)
+    assert abs(v @ M @ v - 2 * T) <= 1e-6 * abs(2 * T)
+    grav = rbd.rnea(m, kin, z, z, {})
+    eps = 1e-6
+    for d in range(m.nv):
+        e = np.zeros(m.nv)
+        e[d] = 1.0
+        dU = (energies(rbd.integrate(m, q, eps * e), z)[1] - energies(rbd.integrate(m, q, -eps * e), z)[1]) / (2 * eps)
+        assert abs(grav[d] - dU) <= 1e-5 * max(1.0, np.abs(grav).max()), d
+    # power balance along q(t) = q (+) (v t + a t^2 / 2), v(t) = v + a t
+    tau = rbd.rnea(m, kin, v, a, {})
+    h = 1e-4
+
+    def total(t):
+        Tt, Ut = energies(rbd.integrate(m, q, v * t + 0.5 * a * t * t), v + a * t)
+        return Tt + Ut
+    power = (total(h) - total(-h)) / (2 * h)
+    assert abs(v @ tau - power) <= 1e-4 * max(1.0, abs(power))
