@@ -226,3 +226,48 @@ def test_rnea_against_lagrangian_mechanics(name):
         return Tt + Ut
     power = (total(h) - total(-h)) / (2 * h)
     assert abs(v @ tau - power) <= 1e-4 * max(1.0, abs(power))
+
+
+def test_osqp_restatement_against_independent_solver():
+    """The oracle's ADMM (Ruiz scaling, rho_vec, relaxation) against an independent method on random convex QPs
+    min 1/2 x^T P x + q^T x, l <= A x <= u with equality, inequality and free rows: run to tight tolerances it must
+    reach the optimum that scipy's trust-constr interior-point method finds, and the returned duals must satisfy the
+    KKT conditions; an infeasible problem must be reported as such."""
+    from scipy import sparse
+    from scipy.optimize import Bounds, LinearConstraint, minimize
+    from oracle.osqp_admm import OSQP
+    rng = np.random.default_rng(17)
+    for trial in range(3):
+        n, m = 12, 18
+        P = rng.uniform(0.5, 3.0, n)
+        q = rng.normal(size=n)
+        A = sparse.random(m, n, density=0.35, random_state=int(rng.integers(1 << 30)), data_rvs=rng.standard_normal).tocsc()
+        A = (A + sparse.csc_matrix((np.full(n, 1e-3), (np.arange(n), np.arange(n))), shape=(m, n))).tocsc()
+        x_feas = rng.normal(size=n)
+        Ax = A @ x_feas
+        l, u = Ax - rng.uniform(0.1, 1.0, m), Ax + rng.uniform(0.1, 1.0, m)
+        l[:4] = u[:4] = Ax[:4]                      # equality rows
+        l[4:7], u[4:7] = -np.inf, np.inf            # free rows
+        l[7:9] = -np.inf                            # one-sided rows
+        s = OSQP()
+        s.setup(P, np.ones(n), sparse.csc_matrix((np.ones_like(A.data), A.indices, A.indptr), shape=A.shape), -np.ones(m), np.ones(m),
+                max_iter=20000, alpha=1.4, rho=2e-2, eps_abs=1e-9, eps_rel=1e-9)
+        s.update(q=q, Ax=A.data, l=l, u=u)
+        xs = s.solve()
+        assert s.status == "solved"
+        ref = minimize(lambda x: 0.5 * x @ (P * x) + q @ x, x_feas, jac=lambda x: P * x + q, hess=lambda x: np.diag(P),
+                       method="trust-constr", constraints=[LinearConstraint(A.toarray(), l, u)], bounds=Bounds(-np.inf, np.inf),
+                       options={"gtol": 1e-10, "xtol": 1e-12, "maxiter": 3000})
+        assert np.abs(xs - ref.x).max() < 1e-5 * max(1.0, np.abs(ref.x).max())
+        # KKT with the ADMM duals: stationarity, primal feasibility, complementarity signs
+        y = s.E * s.y / s.c                         # unscaled duals
+        assert np.abs(P * xs + q + A.T @ y).max() < 1e-6
+        Axs = A @ xs
+        assert (Axs >= l - 1e-6).all() and (Axs <= u + 1e-6).all()
+        assert (y[(Axs > l + 1e-5) & (Axs < u - 1e-5)].__abs__() < 1e-6).all()
+    # primal infeasible: x0 >= 1 and x0 <= 0
+    s = OSQP()
+    Ai = sparse.csc_matrix(np.array([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]))
+    s.setup(np.ones(2), np.zeros(2), Ai, np.array([1.0, -np.inf, -1.0]), np.array([np.inf, 0.0, 1.0]), max_iter=4000, alpha=1.4, rho=2e-2)
+    out = s.solve()
+    assert s.status == "primal infeasible" and np.isnan(out).all()
