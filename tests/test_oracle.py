@@ -271,3 +271,35 @@ def test_osqp_restatement_against_independent_solver():
     s.setup(np.ones(2), np.zeros(2), Ai, np.array([1.0, -np.inf, -1.0]), np.array([np.inf, 0.0, 1.0]), max_iter=4000, alpha=1.4, rho=2e-2)
     out = s.solve()
     assert s.status == "primal infeasible" and np.isnan(out).all()
+
+
+@pytest.mark.parametrize("name", ["go2", "b2g"])
+def test_frame_velocity_against_finite_differences(name):
+    """getFrameVelocity(LOCAL_WORLD_ALIGNED) of the oracle against the time derivative of the frame placement obtained
+    by forward kinematics alone; base-relative variant (dynamics/dynamics.py:86-113) against its definition."""
+    r = OracleRobot(name)
+    m = r.model
+    rng = np.random.default_rng(5)
+    q, v, _, _ = _random_state(r, rng)
+    dyn = DynamicsWholeBodyTorque(m, r.mass, r.foot_frames)
+    eps = 1e-6
+    frames = list(r.foot_frames) + ([r.arm_ee_frame] if r.arm_ee_frame else [])
+    for fid in frames:
+        Rp, pp = rbd.Kin(m, rbd.integrate(m, q, eps * v)).frame_placement(fid)
+        Rm, pm = rbd.Kin(m, rbd.integrate(m, q, -eps * v)).frame_placement(fid)
+        R0, _ = rbd.Kin(m, q).frame_placement(fid)
+        W = (Rp - Rm) / (2 * eps) @ R0.T
+        ref = np.concatenate([(pp - pm) / (2 * eps), [W[2, 1], W[0, 2], W[1, 0]]])
+        got = dyn.get_frame_velocity(fid)(q, v)
+        assert np.abs(got - ref).max() < 1e-6 * max(1.0, np.abs(ref).max())
+    if r.arm_ee_frame:
+        kin = rbd.Kin(m, q)
+        vf = dyn.get_frame_velocity(r.arm_ee_frame)(q, v)
+        vb = dyn.get_frame_velocity(dyn.base_frame)(q, v)
+        Rb, pb = kin.frame_placement(dyn.base_frame)
+        _, pf = kin.frame_placement(r.arm_ee_frame)
+        lin = Rb.T @ (vf[:3] - vb[:3] - np.cross(vb[3:], pf - pb))
+        ang = Rb.T @ (vf[3:] - vb[3:])
+        ref = np.array([lin[0], lin[1], vf[2], ang[0], ang[1], vf[5]])
+        got = dyn.get_frame_velocity(r.arm_ee_frame, relative_to_base=True)(q, v)
+        assert np.abs(got - ref).max() < 1e-10
