@@ -62,6 +62,11 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
     h->error = "no CUDA device: pino_locoman_b200 has no CPU path";
     return 3;
   }
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      h->num_sms = sms;
+  }
   PLM_CHECK_CUDA(h, cudaMalloc(&h->d_model, sizeof(PlmModel)));
   PLM_CHECK_CUDA(h, cudaMalloc(&h->d_layout, sizeof(PlmLayout)));
   PLM_CHECK_CUDA(h, cudaMalloc(&h->d_lut, h->host.lut.size() * sizeof(int16_t)));

@@ -61,6 +61,7 @@ struct plm_handle {
   int sqp_alloc_done = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double* d_mpc_dts = nullptr;   // [PLM_MAXNODES] horizon step sizes of plm_mpc_step
+  int num_sms = 148;             // multiprocessors of the device (kernel variant selection)
 };
 
 int plm_setup_node_kernels(plm_handle* h);

@@ -559,12 +559,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // once and used twice (row part out[t] += S[t][k] in[k], column part out[k] += S[t][k] in[t], k < t):
 //   forward  stage i: tv_i = S_i^-1 (b_i - G_{i-1} tv_{i-1})
 //   backward stage i: x_i  = tv_i - S_i^-1 G_i^T x_{i+1}            (x_N = tv_N)
+// Two instantiations: throughput (256 threads, 3 CTAs per SM) and, for batches that leave SMs idle, latency (512
+// threads, one CTA per SM, no register pressure).
 #define ADMM_THREADS 256
 #define ADMM_MIN_CTAS 3
+#define ADMM_THREADS_LAT 512
 #define NBUF 2
 #define SYM_K 128    // threads per part: thread (k, part) owns output k of the stage (stage size <= SYM_K), part = tid / SYM_K
-#define SYM_PARTS (ADMM_THREADS / SYM_K)
-static_assert(ADMM_THREADS % SYM_K == 0 && (NBUF & (NBUF - 1)) == 0, "thread layout of sym_panel / buffer ring");
+#define SYM_PARTS_MAX (ADMM_THREADS_LAT / SYM_K)
+static_assert(ADMM_THREADS % SYM_K == 0 && ADMM_THREADS_LAT % SYM_K == 0 && (NBUF & (NBUF - 1)) == 0, "thread layout of sym_panel / buffer ring");
 
 // Thread (k, part) accumulates output k of out = S^-1 in over the resident panel rows [r0, r1): the column walk
 // S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k;
@@ -577,10 +580,10 @@ static_assert(ADMM_THREADS % SYM_K == 0 && (NBUF & (NBUF - 1)) == 0, "thread lay
 // `zp` at a 0.0 in shared memory: masked elements load the zero instead of branching.
 __device__ __forceinline__ double2 lds_pair(const double* p) { return *reinterpret_cast<const double2*>(p); }
 
+template <int P>
 __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const double* __restrict__ zp, int shift, int r0, int r1,
                                           const double* __restrict__ vin, int ws, int we, double& acc0, double& acc1, double& racc) {
   const int part = threadIdx.x / SYM_K, lane = threadIdx.x & 31;
-  constexpr int P = SYM_PARTS;
   const int vodd = (int)((reinterpret_cast<size_t>(vin) >> 3) & 1);      // vin + t is 16-byte aligned iff (t + vodd) is even
   if (ws + 1 < r1 && ws < we) {
     // ---- column walk: element S[t][k] at tri(t) + k, rows t > k of the panel
@@ -657,7 +660,8 @@ __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const 
   }
 }
 
-__global__ void __launch_bounds__(ADMM_THREADS, ADMM_MIN_CTAS)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
                double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out, const int* __restrict__ fail) {
   extern __shared__ double sm[];
@@ -677,6 +681,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* xt = gbuf + NBUF * gd + 2 * NBUF + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   double* tv = w + m;          // [smax] G^T x of the next stage (backward sweep)
+  constexpr int SYM_PARTS = NT / SYM_K;
   double* cpart = tv + smax;   // [SYM_PARTS][smax] partial sums of the symmetric product, one slice per part
   double* red = cpart + SYM_PARTS * smax;     // [32]
   double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
@@ -743,7 +748,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   };
   if (tid == 0)
     for (int k = 0; k < NBUF; ++k) issue_step(k, k);
-  constexpr int nwarps = ADMM_THREADS / 32;
+  constexpr int nwarps = NT / 32;
   int status = 0, it = 0;
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
   PROF_T0();
@@ -856,7 +861,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         }
         acc0 = 0.0; acc1 = 0.0; racc = 0.0;
       }
-      sym_panel(pbuf + bsel * pdb, zp, shift, r0, r1, vin, ws, we, acc0, acc1, racc);
+      sym_panel<SYM_PARTS>(pbuf + bsel * pdb, zp, shift, r0, r1, vin, ws, we, acc0, acc1, racc);
       PROF_ADD(9);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
@@ -1126,7 +1131,7 @@ int plm_qp_alloc(plm_handle* h) {
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 8 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
-  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS) * smax + 32 + 2 + 16) * 8;
+  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS_MAX) * smax + 32 + 2 + 16) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
@@ -1134,7 +1139,8 @@ int plm_qp_alloc(plm_handle* h) {
   }
   QP_CUDA(h, cudaFuncSetAttribute(qp_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   QP_CUDA(h, cudaFuncSetAttribute(qp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel<ADMM_THREADS, ADMM_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel<ADMM_THREADS_LAT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 
@@ -1168,7 +1174,14 @@ int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const dou
 
 int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int* d_status, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_admm_kernel<<<batch, ADMM_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
+  // fewer instances than SMs: one 512-thread CTA per instance (latency); else three 256-thread CTAs per SM (throughput)
+  // (PLM_ADMM_LATENCY_MAX_BATCH overrides the switch-over: 0 forces the throughput kernel; used by the tests)
+  int lat_max = h->num_sms;
+  if (const char* ev = getenv("PLM_ADMM_LATENCY_MAX_BATCH")) lat_max = atoi(ev);
+  if (batch <= lat_max)
+    qp_admm_kernel<ADMM_THREADS_LAT, 1><<<batch, ADMM_THREADS_LAT, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
+  else
+    qp_admm_kernel<ADMM_THREADS, ADMM_MIN_CTAS><<<batch, ADMM_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }

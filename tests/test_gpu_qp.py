@@ -21,10 +21,14 @@ def _nominal_problem(o, rng, k):
     return o.initial_guess(), o.p_vector()
 
 
+@pytest.mark.parametrize("variant", ["throughput", "latency"])
 @pytest.mark.parametrize("rn,kind,N", [("b2", "whole_body_rnea", 6), ("b2g", "whole_body_rnea", 5), ("b2", "centroidal_acc", 6),
                                        ("go2", "centroidal_vel", 5), ("b2g", "whole_body_aba", 4)])
-def test_qp_matches_oracle_osqp(robots, rn, kind, N):
+def test_qp_matches_oracle_osqp(robots, rn, kind, N, variant, monkeypatch):
+    """Both instantiations of the ADMM kernel: the 256-thread one used for large batches and the 512-thread one that
+    small batches get (the library reads PLM_ADMM_LATENCY_MAX_BATCH at every solve)."""
     from pino_locoman_b200.handle import Handle
+    monkeypatch.setenv("PLM_ADMM_LATENCY_MAX_BATCH", "0" if variant == "throughput" else "1000000")
     prod, ora = robots
     rng = np.random.default_rng(3)
     B = 3

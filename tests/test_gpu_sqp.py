@@ -77,12 +77,13 @@ def test_sqp_iterations_match_oracle(robots, rn, kind, N, iters):
     assert len(ms) == 4 and all(v >= 0 for v in ms)
 
 
-def test_full_size_sqp_step_is_deterministic(robots):
+def test_full_size_sqp_step_is_deterministic(robots, monkeypatch):
     """Bench workload (B2G whole_body_rnea, N=20) on 1332 instances = three full waves of the ADMM kernel: instances are
     independent, so copies of one problem at different batch positions (different CTAs, different co-resident
     neighbours, different waves) must produce bit-identical steps, ADMM iteration counts and statuses -- the
     lock-free panel pipeline of the ADMM kernel must not depend on timing -- and two runs must agree bit for bit."""
     from pino_locoman_b200.handle import Handle
+    monkeypatch.delenv("PLM_ADMM_LATENCY_MAX_BATCH", raising=False)
     prod, ora = robots
     rng = np.random.default_rng(11)
     o = OracleOCP(ora["b2g"], "whole_body_rnea", 20)
