@@ -334,6 +334,7 @@ def main():
             torch.cuda.synchronize()
             ts.append(a0.elapsed_time(a1))
         single_ms = float(np.median(ts[1:]))
+        single_phase = [float(v) for v in o1.handle.last_phase_ms()]
         launches += o1.handle.launch_count()
         del o1
     # ---- end to end through the plugin surface: host buffers in, host buffers out
@@ -398,7 +399,8 @@ def main():
                 "mpc_steps_per_s": B / (ms_mpc / 1e3), "ms_per_step": ms_mpc, "admm_iters_avg": mpc_iters},
         "e2e": {"value": total_inst / (ms_e2e / 1e3), "unit": "SQP iters/s", "h2d_bytes_per_step": int(B * (n + h.np) * 8),
                 "d2h_bytes_per_step": int(B * (n + 8) * 8)},
-        "single_instance": {"workload": "b2 whole_body_rnea trot N=20, 1 instance (BASELINE configs[1])", "ms_per_sqp_iter": single_ms},
+        "single_instance": {"workload": "b2 whole_body_rnea trot N=20, 1 instance (BASELINE configs[1])", "ms_per_sqp_iter": single_ms,
+                            "phase_ms": dict(zip(("eval", "qp_update", "qp_solve", "line_search"), single_phase))},
         "gpu_launches": int(launches_timed), "gpu_launches_all_legs": int(launches),
         "clocks": sampler.summary(),
     }
