@@ -51,7 +51,7 @@ struct plm_handle {
   plm::QpWork qp;
   int qp_factor_doubles = 0;
   int* d_qp_fail = nullptr;   // [max_batch] stage index (+1) of a non-positive Cholesky pivot, 0 = ok
-  size_t smem_scale = 0, smem_factor = 0, smem_admm = 0;
+  size_t smem_scale = 0, smem_factor = 0, smem_admm = 0, smem_admm_lat = 0;
   // line search / SQP step workspaces, timing
   plm::LsWork ls;
   // lazily created two-node probe problems backing the Dynamics* entry points (one per formulation)

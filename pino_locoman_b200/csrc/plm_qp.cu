@@ -564,10 +564,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #define ADMM_THREADS 256
 #define ADMM_MIN_CTAS 3
 #define ADMM_THREADS_LAT 512
-#define NBUF 2
+#define NBUF 2        // ring of panel buffers, throughput kernel
+#define NBUF_LAT 3    // latency kernel (whole stages)
 #define SYM_K 128    // threads per part: thread (k, part) owns output k of the stage (stage size <= SYM_K), part = tid / SYM_K
 #define SYM_PARTS_MAX (ADMM_THREADS_LAT / SYM_K)
-static_assert(ADMM_THREADS % SYM_K == 0 && ADMM_THREADS_LAT % SYM_K == 0 && (NBUF & (NBUF - 1)) == 0, "thread layout of sym_panel / buffer ring");
+static_assert(ADMM_THREADS % SYM_K == 0 && ADMM_THREADS_LAT % SYM_K == 0 && true, "thread layout of sym_panel");
 
 // Thread (k, part) accumulates output k of out = S^-1 in over the resident panel rows [r0, r1): the column walk
 // S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k;
@@ -660,7 +661,7 @@ __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const 
   }
 }
 
-template <int NT, int MINB>
+template <int NT, int MINB, int NB, bool LAT>
 __global__ void __launch_bounds__(NT, MINB)
 qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
                double* __restrict__ dx_out, int* __restrict__ iters_out, int* __restrict__ status_out, const int* __restrict__ fail) {
@@ -669,16 +670,16 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const QpLayout& Q = *Qp;
   const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
-  const int pdb = Q.panel_doubles;
+  const int pdb = LAT ? Q.panel_doubles_lat : Q.panel_doubles;
   const int gd = Q.g_doubles;
   const bool sparse = Q.sparse_coupling != 0;
   // panel buffers and coupling-block buffers first (16-byte aligned), then the mbarriers, then the gathered vectors
-  double* pbuf = sm;                                   // [NBUF][pdb]
-  double* gbuf = sm + NBUF * pdb;                      // [NBUF][gd] compact coupling block travelling with a stage's first panel
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(gbuf + NBUF * gd);  // [NBUF] "panel landed" barriers
-  int* cnt = reinterpret_cast<int*>(gbuf + NBUF * gd + NBUF);                          // [NBUF] warps done with the panel (running count)
-  int* wrs = cnt + NBUF;                                                                // [PLM_WR_TABLES][5] warp row ranges
-  double* xt = gbuf + NBUF * gd + 2 * NBUF + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
+  double* pbuf = sm;                                   // [NB][pdb]
+  double* gbuf = sm + NB * pdb;                      // [NB][gd] compact coupling block travelling with a stage's first panel
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(gbuf + NB * gd);  // [NB] "panel landed" barriers
+  int* cnt = reinterpret_cast<int*>(gbuf + NB * gd + NB);                          // [NB] warps done with the panel (running count)
+  int* wrs = cnt + NB;                                                                // [PLM_WR_TABLES][5] warp row ranges
+  double* xt = gbuf + NB * gd + 2 * NB + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   double* tv = w + m;          // [smax] G^T x of the next stage (backward sweep)
   constexpr int SYM_PARTS = NT / SYM_K;
@@ -691,8 +692,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const double* AC = W.AhatC + (size_t)b * Q.cell_total;
   FlatIdx F;
   F.rptr = idx32 + Q.f_rptr; F.tptr = idx32 + Q.f_tptr; F.rcol = idx + Q.f_rcol; F.trow = idx + Q.f_trow; F.rperm = idx + Q.f_rperm; F.cperm = idx + Q.f_cperm;
-  const int32_t* sched = idx32 + Q.f_sched;
-  const int nsched = Q.n_sched;
+  const int32_t* sched = idx32 + (LAT ? Q.f_sched_lat : Q.f_sched);
+  const int nsched = LAT ? Q.n_sched_lat : Q.n_sched;
   const double* Ph = W.Ph + (size_t)b * n;
   const double* qh = W.qh + (size_t)b * n;
   const double* lh = W.lh + (size_t)b * m;
@@ -722,12 +723,12 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     }
     asm volatile("fence.proxy.async;" ::: "memory");     // the bulk copies below read Gc through the async proxy
   }
-  // ---- panel pipeline.  `used` counts schedule steps (uniform across the CTA); step q lives in buffer q % NBUF.  Warps
+  // ---- panel pipeline.  `used` counts schedule steps (uniform across the CTA); step q lives in buffer q % NB.  Warps
   // consume the panels of a stage at their own pace (no CTA barrier between panels): every warp waits on the buffer's
-  // mbarrier, and the last warp to finish step q refills the buffer with step q + NBUF.
+  // mbarrier, and the last warp to finish step q refills the buffer with step q + NB.
   if (tid == 0) {
-    for (int k = 0; k < NBUF; ++k) { mbar_init(&bars[k], 1); cnt[k] = 0; }
-    for (int k = 0; k < PLM_WR_TABLES * 5; ++k) wrs[k] = Q.wr[k / 5][k % 5];
+    for (int k = 0; k < NB; ++k) { mbar_init(&bars[k], 1); cnt[k] = 0; }
+    for (int k = 0; k < PLM_WR_TABLES * 5; ++k) wrs[k] = LAT ? Q.wr_lat[k / 5][k % 5] : Q.wr[k / 5][k % 5];
     *zp = 0.0;
     zp[1] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -747,7 +748,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(dir ? i : i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
   };
   if (tid == 0)
-    for (int k = 0; k < NBUF; ++k) issue_step(k, k);
+    for (int k = 0; k < NB; ++k) issue_step(k, k);
   constexpr int nwarps = NT / 32;
   int status = 0, it = 0;
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
@@ -786,18 +787,18 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const int s = S1.w & 255;
       double* bi = xt + (S1.w >> 8);
       const double* vin = (dir == 0) ? bi : tv;
-      const int bsel = (int)(used & (NBUF - 1));
+      const int bsel = (int)(used % NB);
       if (first) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
       {   // schedule entry of the next step (consumed at the end of this one)
         const int nst = st + 1 < nsched ? st + 1 : 0;
         S0 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS));
         S1 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS) + 1);
       }
-      mbar_wait(&bars[bsel], (used / NBUF) & 1u);
+      mbar_wait(&bars[bsel], (used / NB) & 1u);
       if (pend >= 0) {      // the previous step's buffer: refill it if this warp was the last one out
         if ((pend + 1) % nwarps == 0) {
-          const int nx = pend_st + NBUF;
-          issue_step(nx >= nsched ? nx - nsched : nx, (int)((used - 1) & (NBUF - 1)));
+          const int nx = pend_st + NB;
+          issue_step(nx >= nsched ? nx - nsched : nx, (int)((used - 1) % NB));
         }
         pend = -1;
       }
@@ -888,7 +889,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (last) {
         if (pend >= 0) {
           if ((pend + 1) % nwarps == 0) {
-            const int nx = pend_st + NBUF;
+            const int nx = pend_st + NB;
             issue_step(nx >= nsched ? nx - nsched : nx, bsel);
           }
           pend = -1;
@@ -1061,7 +1062,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     PROF_ADD(8);
     if (status != 0) break;
   }
-  for (unsigned k = used; k < used + NBUF; ++k) mbar_wait(&bars[k & (NBUF - 1)], (k / NBUF) & 1u);   // drain prefetches in flight
+  for (unsigned k = used; k < used + NB; ++k) mbar_wait(&bars[k % NB], (k / NB) & 1u);   // drain prefetches in flight
   if (it > Q.max_iter) it = Q.max_iter;
   if (status == 0) status = -2;   // maximum iterations reached
   // failure detection beyond osqp's own codes: -10 the stage factorisation met a non-positive pivot, -11 NaN iterates
@@ -1132,15 +1133,16 @@ int plm_qp_alloc(plm_handle* h) {
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 8 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
   h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS_MAX) * smax + 32 + 2 + 16) * 8;
+  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + (1 + SYM_PARTS_MAX) * smax + 32 + 2 + 16) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
-  if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024) {
+  if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024 || h->smem_admm_lat > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
     return 7;
   }
   QP_CUDA(h, cudaFuncSetAttribute(qp_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   QP_CUDA(h, cudaFuncSetAttribute(qp_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel<ADMM_THREADS, ADMM_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel<ADMM_THREADS_LAT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel<ADMM_THREADS, ADMM_MIN_CTAS, NBUF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  QP_CUDA(h, cudaFuncSetAttribute(qp_admm_kernel<ADMM_THREADS_LAT, 1, NBUF_LAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 
@@ -1179,9 +1181,9 @@ int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int*
   int lat_max = h->num_sms;
   if (const char* ev = getenv("PLM_ADMM_LATENCY_MAX_BATCH")) lat_max = atoi(ev);
   if (batch <= lat_max)
-    qp_admm_kernel<ADMM_THREADS_LAT, 1><<<batch, ADMM_THREADS_LAT, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
+    qp_admm_kernel<ADMM_THREADS_LAT, 1, NBUF_LAT, true><<<batch, ADMM_THREADS_LAT, h->smem_admm_lat, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
   else
-    qp_admm_kernel<ADMM_THREADS, ADMM_MIN_CTAS><<<batch, ADMM_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
+    qp_admm_kernel<ADMM_THREADS, ADMM_MIN_CTAS, NBUF, false><<<batch, ADMM_THREADS, h->smem_admm, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, W, d_dx, d_iters, d_status, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }

@@ -40,6 +40,9 @@ struct QpLayout {
   int32_t f_sched, n_sched;            // int32 pool: panel schedule of one ADMM iteration, 8 ints per step
   int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
   int32_t wr[PLM_WR_TABLES][5];        // rows [wr[q], wr[q+1]) of a stage are owned by warp q of each part (ADMM kernel)
+  // the same for the latency kernel (whole stages as panels)
+  int32_t f_sched_lat, n_sched_lat, panel_doubles_lat;
+  int32_t wr_lat[PLM_WR_TABLES][5];
   int32_t g_doubles;                   // doubles of one stage's compact coupling block (4 per integrator row)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
   int32_t fac_total;
