@@ -405,7 +405,7 @@ def main():
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:
-        n_cpu = 2
+        n_cpu = 8          # ~10 s of CPU work on one core
         wall, t_eval, t_all = cpu_oracle_timing(x_host, p_host, n_cpu, 1, 1)
         line["cpu_baseline"] = {"value": n_cpu / t_all, "unit": "SQP iters/s", "cores": 1, "kind": "port",
                                 "node_evals_per_s": n_cpu * NODES / t_eval,
