@@ -172,10 +172,12 @@ int plm_sqp_step(plm_handle* h, const double* d_x, const double* d_p, int32_t ba
  * optimization/ocp.py:71-74, host memory), then warm_start() when warm_start != 0 (forces in d_x reset to the
  * contact-masked f_des, the rest of the previous solution kept: ocp_whole_body_rnea.py:207-235; mass = robot mass of
  * f_des), one SQP iteration d_x -> d_x_new (plm_sqp_step), and x_init <- integrate(x_init, DX_1 of d_x_new) inside d_p
- * (run_mpc.py:141).  d_x and d_p are updated in place; the caller swaps d_x / d_x_new between steps. */
+ * (run_mpc.py:141); with update_tau_prev != 0 (whole_body_rnea, tau_nodes > 1) also tau_prev <- tau of node 1, as the
+ * compiled-solver branch of the loop does (run_mpc.py:108-111; the generic branch keeps tau_prev).  d_x and d_p are
+ * updated in place; the caller swaps d_x / d_x_new between steps. */
 int plm_mpc_step(plm_handle* h, double* d_x, double* d_p, const double* d_t0, double t_add, int32_t gait, double gait_period,
-                 const double* dts_host, double mass, int32_t warm_start, int32_t batch, double* d_x_new, double* d_stats,
-                 void* stream);
+                 const double* dts_host, double mass, int32_t warm_start, int32_t update_tau_prev, int32_t batch,
+                 double* d_x_new, double* d_stats, void* stream);
 
 /* Per-phase device times (ms) of the last plm_sqp_step on this handle: eval, qp_update, qp_solve, line_search.
  * Synchronises the stream. */

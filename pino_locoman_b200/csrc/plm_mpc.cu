@@ -68,8 +68,10 @@ __global__ void mpc_prepare_kernel(const PlmLayout* __restrict__ Lp, int batch, 
   }
 }
 
-// x_init <- integrate(x_init, DX_1) in place inside p (one thread per instance)
-__global__ void mpc_advance_kernel(const PlmLayout* __restrict__ Lp, int batch, int nq, int nv, const double* __restrict__ x, double* __restrict__ p) {
+// x_init <- integrate(x_init, DX_1) in place inside p (one thread per instance); optionally tau_prev <- tau of node 1
+// (the compiled-solver branch of the reference loop, run_mpc.py:108-111; the generic branch leaves tau_prev alone)
+__global__ void mpc_advance_kernel(const PlmLayout* __restrict__ Lp, int batch, int nq, int nv, int update_tau_prev, const double* __restrict__ x,
+                                   double* __restrict__ p) {
   const PlmLayout& L = *Lp;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
@@ -84,6 +86,11 @@ __global__ void mpc_advance_kernel(const PlmLayout* __restrict__ Lp, int batch, 
   for (int j = 0; j < nq - 7; ++j) xi[qo + 7 + j] += d[qo + 6 + j];
   if (cvel) { for (int i = 0; i < 6; ++i) xi[i] += d[i]; }
   else { for (int i = 0; i < nv; ++i) xi[nq + i] += d[nv + i]; }
+  if (update_tau_prev && L.dynamics == PLM_WHOLE_BODY_RNEA && L.tau_nodes > 1) {
+    const double* tau1 = x + (size_t)b * L.n + L.x_off[1] + L.ndx + L.tau_idx;
+    double* tp = p + (size_t)b * L.np + L.p_tau_prev;
+    for (int j = 0; j < nq - 7; ++j) tp[j] = tau1[j];
+  }
 }
 
 }  // namespace
@@ -91,7 +98,8 @@ __global__ void mpc_advance_kernel(const PlmLayout* __restrict__ Lp, int batch, 
 extern "C" {
 
 int plm_mpc_step(plm_handle* h, double* d_x, double* d_p, const double* d_t0, double t_add, int32_t gait, double gait_period,
-                 const double* dts_host, double mass, int32_t warm_start, int32_t batch, double* d_x_new, double* d_stats, void* stream) {
+                 const double* dts_host, double mass, int32_t warm_start, int32_t update_tau_prev, int32_t batch, double* d_x_new,
+                 double* d_stats, void* stream) {
   if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
   if (gait < 0 || gait > 2) { h->error = "plm_mpc_step: gait 0 trot, 1 walk, 2 stand"; return 11; }
   const PlmLayout& L = h->host.layout;
@@ -112,7 +120,7 @@ int plm_mpc_step(plm_handle* h, double* d_x, double* d_p, const double* d_t0, do
   PLM_LAUNCH_CHECK(h);
   h->launches++;
   if (int rc = plm_sqp_step(h, d_x, d_p, batch, d_x_new, d_stats, stream)) return rc;
-  mpc_advance_kernel<<<(batch + 63) / 64, 64, 0, s>>>(h->d_layout, batch, M.nq, M.nv, d_x_new, d_p);
+  mpc_advance_kernel<<<(batch + 63) / 64, 64, 0, s>>>(h->d_layout, batch, M.nq, M.nv, update_tau_prev, d_x_new, d_p);
   PLM_LAUNCH_CHECK(h);
   h->launches++;
   return 0;

@@ -22,13 +22,14 @@ _GAIT_ID = {"trot": 0, "walk": 1, "stand": 2}
 
 
 class BatchedMPC:
-    def __init__(self, ocp, warm_start=True, t0=None):
+    def __init__(self, ocp, warm_start=True, t0=None, update_tau_prev=False):
         if ocp.solver != "osqp":
             raise ValueError(f"Solver {ocp.solver} not supported")
         if getattr(ocp, "hess_diag", None) is None:
             ocp.init_solver()
         self.ocp, self.h = ocp, ocp.handle
         self.warm_start = bool(warm_start)
+        self.update_tau_prev = bool(update_tau_prev)     # run_mpc.py:108-111 (compiled-solver branch of the loop)
         self.k = 0
         dev = self.h.device
         gs = ocp.gait_sequence
@@ -45,7 +46,7 @@ class BatchedMPC:
         """One MPC step for every instance; returns the device tensor of SQP statistics [B, 8]."""
         h = self.h
         rc = h.lib.plm_mpc_step(h._h, _ptr(self.x), _ptr(self.p), _ptr(self._t0), self.k * self._dt_min, self._gait, self._period,
-                                self._dts, float(self.ocp.mass), int(self.warm_start and self.k > 0), self.ocp.batch,
+                                self._dts, float(self.ocp.mass), int(self.warm_start and self.k > 0), int(self.update_tau_prev), self.ocp.batch,
                                 _ptr(self.x_new), _ptr(self.stats), h._stream())
         h._rc(rc)
         self.x, self.x_new = self.x_new, self.x

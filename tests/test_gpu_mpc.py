@@ -59,3 +59,43 @@ def test_device_resident_mpc_matches_host_loop(rn, kind, N, gait):
         assert np.array_equal(stats[:, :2], host.stats[:, :2])          # ADMM iterations and status
         assert np.abs(mpc.x_init().cpu().numpy() - x_init).max() <= 1e-9
     assert mpc.k == loops
+
+
+def test_device_resident_mpc_updates_previous_torques():
+    """update_tau_prev: tau_prev <- tau of node 1 after every step (compiled-solver branch, run_mpc.py:108-111)."""
+    from pino_locoman_b200 import OCP_ARGS
+    from pino_locoman_b200.mpc import BatchedMPC
+    from pino_locoman_b200.optimization import make_ocp
+    from pino_locoman_b200.utils import robot as prob
+    kind, B, N, loops, dt_min = "whole_body_rnea", 2, 5, 3, 0.01
+    t0 = np.array([0.0, 0.3])
+    args = dict(OCP_ARGS[kind], tau_nodes=3)
+
+    def make():
+        r = prob.B2G()
+        r.set_gait_sequence("trot", 0.8)
+        return make_ocp(dynamics=kind, default_args=args, robot=r, nodes=N, solver="osqp", batch=B)
+
+    host, dev = make(), make()
+    x_init = np.stack([host.x_nom] * B)
+    x_init[1, 7:host.nq] -= 0.04
+    _configure(host, kind, x_init, t0, dt_min)
+    _configure(dev, kind, x_init, t0, dt_min)
+    for o in (host, dev):
+        o._set("W_diag", np.full(o.nj, 1e-3))       # the tau_prev term must matter
+        o.init_solver()
+    mpc = BatchedMPC(dev, warm_start=True, t0=t0, update_tau_prev=True)
+    to = host.handle.p_off["tau_prev"]
+    for k in range(loops):
+        host.update_initial_state(x_init)
+        host.update_gait_sequence(t0 + k * dt_min)
+        host.warm_start()
+        sol = host.solve(retract_all=False)
+        x_init = host.state_integrate(x_init, host.DX_prev[1])
+        tau1 = host.get_tau_sol(1).copy()
+        host.update_previous_torques(tau1)
+        mpc.step()
+        x_dev = mpc.solution().cpu().numpy()
+        assert np.abs(x_dev - sol).max() <= 1e-9 * max(1.0, np.abs(sol).max()), k
+        assert np.array_equal(mpc.p.cpu().numpy()[:, to:to + host.nj], x_dev[:, host.handle.x_off[1] + host.ndx_opt + host.tau_idx:][:, :host.nj])
+        assert np.abs(mpc.p.cpu().numpy()[:, to:to + host.nj] - tau1).max() <= 1e-9 * max(1.0, np.abs(tau1).max())
