@@ -436,10 +436,15 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     Q.smax = std::max(Q.smax, s);
   }
   Q.fac_off[N + 1] = fo;
+  for (int i = 0; i < N; ++i) {         // B_i = S_i^-1 G_i^T: ndx columns of sp doubles
+    Q.bk_off[i] = fo;
+    fo += ndx * ((ndx + nu[i] + 1) & ~1);
+  }
+  Q.bk_off[N] = fo;
   Q.fac_total = fo;
   {
-    // panel schedules: forward sweep stages 0..N, backward sweep stages N-1..0, each stage cut into row panels of at
-    // most `capacity` doubles.  Two schedules: 16 KB panels for the throughput kernel (three CTAs per SM), whole stages
+    // panel schedules: forward sweep stages 0..N (row panels of the packed S_i^-1), backward sweep stages N-1..0
+    // (column panels of B_i), panels of at most `capacity` doubles.  Two schedules: 16 KB panels for the throughput kernel (three CTAs per SM), whole stages
     // for the latency kernel (one CTA per SM, shared memory to spare).
     auto build = [&](int capacity, int32_t wr[PLM_WR_TABLES][5], int32_t& f_sched, int32_t& n_sched, int32_t& panel_doubles) {
       std::vector<int> sched;
@@ -487,8 +492,24 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
           sched.push_back(s | (L.x_off[i] << 8));
         }
       };
+      // backward stage i: x_i = tv_i - B_i x_{i+1}[0:ndx]; equal column panels
+      auto add_back = [&](int i) {
+        const int s = ndx + nu[i], sp = (s + 1) & ~1;
+        const int maxcols = std::max(1, capacity / sp);
+        const int npan = (ndx + maxcols - 1) / maxcols;
+        for (int k = 0; k < npan; ++k) {
+          const int j0 = (int)((long long)ndx * k / npan), j1 = (int)((long long)ndx * (k + 1) / npan);
+          const int len = (j1 - j0) * sp;
+          maxlen = std::max(maxlen, len);
+          sched.push_back(Q.bk_off[i] + j0 * sp); sched.push_back(len); sched.push_back(j0); sched.push_back(j1);
+          sched.push_back(i);
+          sched.push_back(1 | ((k == 0) << 1) | ((k + 1 == npan) << 2) | (L.node_type[i] << 3));
+          sched.push_back(sp);
+          sched.push_back(s | (L.x_off[i] << 8));
+        }
+      };
       for (int i = 0; i <= N; ++i) add_stage(i, 0);
-      for (int i = N - 1; i >= 0; --i) add_stage(i, 1);     // x_N = S_N^-1 r_N needs no backward work
+      for (int i = N - 1; i >= 0; --i) add_back(i);         // x_N = S_N^-1 r_N needs no backward work
       n_sched = (int)sched.size() / PLM_SCHED_INTS;
       while (out.qp_idx32.size() % 4) out.qp_idx32.push_back(0);     // schedule entries are read as two 16-byte words
       f_sched = (int)out.qp_idx32.size();

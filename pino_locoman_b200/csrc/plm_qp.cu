@@ -444,6 +444,25 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
         }
         K[o] = rs[r] * As[ea1] * rs[c2] * As[eb1] * acc;
       }
+      // back-substitution block B_i = S_i^-1 G_i^T (column major [ndx][sp]): the backward sweep of the ADMM
+      // iterations is x_i = tv_i - B_i x_{i+1}[0:ndx], a plain product in which every stored element is used once
+      {
+        const int sp = (s + 1) & ~1;
+        double* Bo = Lout + Q.bk_off[i];
+        for (int o = tid; o < ndx * sp; o += nth) {
+          const int c2 = o / sp, kk = o - c2 * sp;
+          double acc = 0.0;
+          if (kk < s) {
+            const int e0 = sv.rptr[c2], e1 = sv.rptr[c2 + 1] - 1;
+            for (int e = e0; e < e1; ++e) {
+              const int j = sv.ccol[e];
+              acc += As[e] * Sg[kk >= j ? tri(kk, j) : tri(j, kk)];
+            }
+            acc *= rs[c2] * As[e1];
+          }
+          Bo[o] = acc;
+        }
+      }
       __syncthreads();
       continue;
     }
@@ -460,6 +479,20 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       Wm[o] = g * acc;
     }
     __syncthreads();
+    {   // B_i = S_i^-1 G_i^T = X^T W (see the sparse branch)
+      const int sp = (s + 1) & ~1;
+      double* Bo = Lout + Q.bk_off[i];
+      for (int o = tid; o < ndx * sp; o += nth) {
+        const int c2 = o / sp, kk = o - c2 * sp;
+        double a0 = 0.0, a1 = 0.0;
+        if (kk < s) {
+          int t = kk;
+          for (; t + 1 < s; t += 2) { a0 += H[tri(t, kk)] * Wm[t * ndx + c2]; a1 += H[tri(t + 1, kk)] * Wm[(t + 1) * ndx + c2]; }
+          if (t < s) a0 += H[tri(t, kk)] * Wm[t * ndx + c2];
+        }
+        Bo[o] = a0 + a1;
+      }
+    }
     for (int o = tid; o < ndx * (ndx + 1) / 2; o += nth) {
       int r = (int)((sqrt(8.0 * o + 1.0) - 1.0) * 0.5);
       while (tri(r + 1, 0) <= o) ++r;
@@ -558,7 +591,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // of one ADMM iteration.  A sweep step is one symmetric product out = S_i^-1 in; each stored element S[t][k] is read
 // once and used twice (row part out[t] += S[t][k] in[k], column part out[k] += S[t][k] in[t], k < t):
 //   forward  stage i: tv_i = S_i^-1 (b_i - G_{i-1} tv_{i-1})
-//   backward stage i: x_i  = tv_i - S_i^-1 G_i^T x_{i+1}            (x_N = tv_N)
+//   backward stage i: x_i  = tv_i - B_i x_{i+1}[0:ndx],  B_i = S_i^-1 G_i^T (s x ndx, from the factor kernel; x_N = tv_N):
+//                     a plain product, column panels of B_i, every element read from shared memory once
 // Two instantiations: throughput (256 threads, 3 CTAs per SM) and, for batches that leave SMs idle, latency (512
 // threads, one CTA per SM, no register pressure).
 #define ADMM_THREADS 256
@@ -661,6 +695,24 @@ __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const 
   }
 }
 
+// Backward step: out[k] += sum_j B[k][j] in[j] over the resident columns [j0, j1) of B_i (column major, stride sp).  Warp
+// (chunk, part) owns the outputs k = 32 chunk + lane and every np-th resident column starting at j0 + part; the sums
+// live in registers across the panels of the stage.  Lanes read consecutive addresses, `in` is a broadcast.
+__device__ __forceinline__ void rect_panel(const double* __restrict__ pan, int sp, int j0, int j1, const double* __restrict__ vin, int k,
+                                           int part, int np, double& acc0, double& acc1) {
+  const double* a = pan + k + (size_t)part * sp;
+  const int st = np * sp;
+  int j = j0 + part;
+#pragma unroll 2
+  for (; j + np < j1; j += 2 * np) {
+    const double a0 = a[0], a1 = a[st];
+    acc0 += a0 * vin[j];
+    acc1 += a1 * vin[j + np];
+    a += 2 * st;
+  }
+  if (j < j1) acc0 += a[0] * vin[j];
+}
+
 template <int NT, int MINB, int NB, bool LAT>
 __global__ void __launch_bounds__(NT, MINB)
 qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
@@ -681,10 +733,10 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   int* wrs = cnt + NB;                                                                // [PLM_WR_TABLES][5] warp row ranges
   double* xt = gbuf + NB * gd + 2 * NB + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
-  double* tv = w + m;          // [smax] G^T x of the next stage (backward sweep)
   constexpr int SYM_PARTS = NT / SYM_K;
-  double* cpart = tv + smax;   // [SYM_PARTS][smax] partial sums of the symmetric product, one slice per part
-  double* red = cpart + SYM_PARTS * smax;     // [32]
+  constexpr int CP_SLICES = 2 * SYM_PARTS;    // column parts of a backward step (at most)
+  double* cpart = w + m;       // [CP_SLICES][smax] partial sums of a stage product, one slice per part
+  double* red = cpart + CP_SLICES * smax;     // [32]
   double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
@@ -740,12 +792,16 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   auto issue_step = [&](int st, int buf) {            // one thread: schedule step st into buffer buf
     const int4 S0 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS));
     const int4 S1 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS) + 1);
+#ifdef PLM_EXP_HALF_BYTES
+    const unsigned bytes = (((unsigned)S0.y * 8u) / PLM_EXP_HALF_BYTES + 15u) & ~15u;     // timing experiment only (wrong results)
+#else
     const unsigned bytes = (unsigned)S0.y * 8u;
+#endif
     const int i = S1.x, dir = S1.y & 1;
-    const bool with_g = sparse && (S1.y & 2) && (dir == 1 || i > 0);
+    const bool with_g = sparse && (S1.y & 2) && dir == 0 && i > 0;     // forward coupling b_i -= G_{i-1} tv_{i-1}
     mbar_expect_tx(&bars[buf], bytes + (with_g ? (unsigned)gd * 8u : 0u));
     bulk_g2s(pbuf + (size_t)buf * pdb, Lf + S0.x, bytes, &bars[buf]);
-    if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(dir ? i : i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
+    if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
   };
   if (tid == 0)
     for (int k = 0; k < NB; ++k) issue_step(k, k);
@@ -779,6 +835,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
     double acc0 = 0.0, acc1 = 0.0, racc = 0.0;
     int ws = 0, we = 0;                       // rows of the current stage owned by this warp
+    int bk = -1, bpart = 0, bnp = 1;          // backward steps: output, column part, parts of this thread's chunk
     int pend = -1, pend_st = 0;               // lane 0: deferred refill check of the previous step
     int4 S0 = __ldg(reinterpret_cast<const int4*>(sched));
     int4 S1 = __ldg(reinterpret_cast<const int4*>(sched) + 1);
@@ -786,9 +843,18 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const int r0 = S0.z, r1 = S0.w, i = S1.x, dir = S1.y & 1, first = S1.y & 2, last = S1.y & 4, shift = S1.z;
       const int s = S1.w & 255;
       double* bi = xt + (S1.w >> 8);
-      const double* vin = (dir == 0) ? bi : tv;
       const int bsel = (int)(used % NB);
-      if (first) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
+      if (first) {
+        if (dir == 0) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
+        else {          // backward: warp -> (chunk of 32 outputs, column part)
+          const int nch = (s + 31) >> 5, wp = tid >> 5;
+          bpart = wp / nch;
+          const int chunk = wp - bpart * nch;
+          bnp = min(CP_SLICES, (nwarps - chunk + nch - 1) / nch);
+          bk = 32 * chunk + (tid & 31);
+          if (bpart >= CP_SLICES || bk >= s) bk = -1;
+        }
+      }
       {   // schedule entry of the next step (consumed at the end of this one)
         const int nst = st + 1 < nsched ? st + 1 : 0;
         S0 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS));
@@ -830,39 +896,11 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
             __syncthreads();
           }
           PROF_ADD(1);
-        } else {   // tv = G_i^T x_{i+1}: column gather over the integrator rows (rows < ndx come first in every column)
-          const StageView sv = stage_view(L, Q, idx, i);
-          const double* xn = xt + L.x_off[i + 1];
-          if (sparse) {
-            if (tid < s) {
-              double acc = 0.0;
-              for (int e = sv.cptr[tid]; e < sv.cptr[tid + 1]; ++e) {
-                const int r = sv.crow[e];
-                if (r >= ndx) break;
-                acc += g[4 * r + (sv.cpos[e] - sv.rptr[r])] * xn[r];
-              }
-              tv[tid] = acc;
-            }
-          } else {
-            const double* An = Ah + L.nnz_off[i];
-            const double* rh = rho + L.row_off[i];
-            for (int k = tid; k < s; k += nth) {
-              double acc = 0.0;
-              for (int e = sv.cptr[k]; e < sv.cptr[k + 1]; ++e) {
-                const int r = sv.crow[e];
-                if (r >= ndx) break;
-                const int e1 = sv.rptr[r + 1] - 1;
-                acc += An[sv.cpos[e]] * rh[r] * An[e1] * xn[r];
-              }
-              tv[k] = acc;
-            }
-          }
-          __syncthreads();
-          PROF_ADD(5);
         }
         acc0 = 0.0; acc1 = 0.0; racc = 0.0;
       }
-      sym_panel<SYM_PARTS>(pbuf + bsel * pdb, zp, shift, r0, r1, vin, ws, we, acc0, acc1, racc);
+      if (dir == 0) sym_panel<SYM_PARTS>(pbuf + bsel * pdb, zp, shift, r0, r1, bi, ws, we, acc0, acc1, racc);
+      else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, bpart, bnp, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
       PROF_ADD(9);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
@@ -878,12 +916,14 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         if (last) {
           // combine: out[k] = sum over the parts; the column-walk sums and the row-walk sums of a warp cover the same
           // rows in two lane orders
-          const int lane = tid & 31;
-          const int k = ws + lane, kr = ws + ((lane & 15) << 1) + (lane >> 4);
-          double* cp = cpart + (tid / SYM_K) * smax;
-          if (k < we) cp[k] = sum;
-          __syncwarp();
-          if (kr < we) cp[kr] += racc;
+          if (dir == 0) {
+            const int lane = tid & 31;
+            const int k = ws + lane, kr = ws + ((lane & 15) << 1) + (lane >> 4);
+            double* cp = cpart + (tid / SYM_K) * smax;
+            if (k < we) cp[k] = sum;
+            __syncwarp();
+            if (kr < we) cp[kr] += racc;
+          } else if (bk >= 0) cpart[bpart * smax + bk] = sum;
         }
       }
       if (last) {
@@ -898,9 +938,16 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         PROF_ADD(10);
         if (tid < s) {
           double o = cpart[tid];
+          if (dir == 0) {
 #pragma unroll
-          for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[w2 * smax + tid];
-          bi[tid] = (dir == 0) ? o : bi[tid] - o;
+            for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[w2 * smax + tid];
+            bi[tid] = o;
+          } else {
+            const int nch = (s + 31) >> 5;
+            const int np = min(CP_SLICES, (nwarps - (tid >> 5) + nch - 1) / nch);
+            for (int w2 = 1; w2 < np; ++w2) o += cpart[w2 * smax + tid];
+            bi[tid] -= o;
+          }
         }
         __syncthreads();
         PROF_ADD(4);
@@ -1132,8 +1179,8 @@ int plm_qp_alloc(plm_handle* h) {
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 8 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
-  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + (1 + SYM_PARTS_MAX) * smax + 32 + 2 + 16) * 8;
-  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + (1 + SYM_PARTS_MAX) * smax + 32 + 2 + 16) * 8;
+  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + 2 * (ADMM_THREADS / SYM_K) * smax + 32 + 2 + 16) * 8;
+  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + 2 * (ADMM_THREADS_LAT / SYM_K) * smax + 32 + 2 + 16) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024 || h->smem_admm_lat > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";

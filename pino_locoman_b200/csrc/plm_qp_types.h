@@ -12,6 +12,7 @@ namespace plm {
 // flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage,
 // bits 3.. warp row-range table),
 // offset of the copy inside the stage block, stage size | x_off << 8}
+// A backward step streams columns [first, end) of B_i instead (all s rows of each); the seventh int is the column stride sp.
 #define PLM_SCHED_INTS 8
 #define PLM_WR_TABLES 5   // warp row-range tables: one per node type + the final stage
 
@@ -45,7 +46,9 @@ struct QpLayout {
   int32_t wr_lat[PLM_WR_TABLES][5];
   int32_t g_doubles;                   // doubles of one stage's compact coupling block (4 per integrator row)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
-  int32_t fac_total;
+  int32_t bk_off[PLM_MAXNODES + 1];    // offset (doubles) of stage i's back-substitution block B_i = S_i^-1 G_i^T, i < N:
+                                       // column major [ndx][sp], sp = s rounded up to even
+  int32_t fac_total;                   // everything the ADMM iterations stream: the S_i^-1 and the B_i
   int32_t smax;                        // largest stage size
   // OSQP settings
   int32_t max_iter, check_termination, scaling;
@@ -71,7 +74,7 @@ struct QpWork {
   double* lh = nullptr;      // [m]     E l
   double* uh = nullptr;      // [m]     E u
   double* rho = nullptr;     // [m]     rho_vec
-  double* Linv = nullptr;    // [fac_total] packed inverse stage blocks S_i^-1
+  double* Linv = nullptr;    // [fac_total] packed inverse stage blocks S_i^-1, then the back-substitution blocks B_i
   double* Gc = nullptr;      // [nodes][ndx][4] compact coupling blocks diag(rho n) A_int (sparse couplings only)
   double* x = nullptr;       // [n]     persistent scaled ADMM iterates
   double* z = nullptr;       // [m]
