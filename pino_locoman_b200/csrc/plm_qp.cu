@@ -596,7 +596,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // Two instantiations: throughput (256 threads, 3 CTAs per SM) and, for batches that leave SMs idle, latency (512
 // threads, one CTA per SM, no register pressure).
 #define ADMM_THREADS 256
-#define ADMM_MIN_CTAS 3
+#define ADMM_MIN_CTAS 4
 #define ADMM_THREADS_LAT 512
 #define NBUF 2        // ring of panel buffers, throughput kernel
 #define NBUF_LAT 3    // latency kernel (whole stages)
@@ -725,17 +725,23 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const int pdb = LAT ? Q.panel_doubles_lat : Q.panel_doubles;
   const int gd = Q.g_doubles;
   const bool sparse = Q.sparse_coupling != 0;
-  // panel buffers and coupling-block buffers first (16-byte aligned), then the mbarriers, then the gathered vectors
+  // panel buffers and coupling-block buffers first (16-byte aligned), then the mbarriers, then the gathered vectors.
+  // Throughput kernel: the row vector w is dead during the sweeps and no panel is resident outside them, so w ALIASES
+  // the panel buffers (the ring is filled at the start of each iteration's sweeps and runs empty at their end); this
+  // is what lets four CTAs share an SM.  The latency kernel has shared memory to spare and prefetches across iterations.
+  constexpr bool ALIAS = !LAT;
+  const int ring = NB * (pdb + gd);
+  const int ring_al = ALIAS ? ((max(ring, m) + 1) & ~1) : ring;
   double* pbuf = sm;                                   // [NB][pdb]
   double* gbuf = sm + NB * pdb;                      // [NB][gd] compact coupling block travelling with a stage's first panel
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(gbuf + NB * gd);  // [NB] "panel landed" barriers
-  int* cnt = reinterpret_cast<int*>(gbuf + NB * gd + NB);                          // [NB] warps done with the panel (running count)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + ring_al);  // [NB] "panel landed" barriers
+  int* cnt = reinterpret_cast<int*>(sm + ring_al + NB);                          // [NB] warps done with the panel (running count)
   int* wrs = cnt + NB;                                                                // [PLM_WR_TABLES][5] warp row ranges
-  double* xt = gbuf + NB * gd + 2 * NB + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
-  double* w = xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
+  double* xt = sm + ring_al + 2 * NB + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
+  double* w = ALIAS ? sm : xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   constexpr int SYM_PARTS = NT / SYM_K;
   constexpr int CP_SLICES = 2 * SYM_PARTS;    // column parts of a backward step (at most)
-  double* cpart = w + m;       // [CP_SLICES][smax] partial sums of a stage product, one slice per part
+  double* cpart = xt + n + (ALIAS ? 0 : m);       // [CP_SLICES][smax] partial sums of a stage product, one slice per part
   double* red = cpart + CP_SLICES * smax;     // [32]
   double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
@@ -787,6 +793,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   }
   // 16-byte loads of sym_panel may read one element past a stage vector: keep every shared vector finite
   for (int j = tid; j < (int)(zp + 2 - xt); j += nth) xt[j] = 0.0;
+  if (ALIAS) for (int j = tid; j < ring_al; j += nth) sm[j] = 0.0;
   __syncthreads();
   unsigned used = 0;
   auto issue_step = [&](int st, int buf) {            // one thread: schedule step st into buffer buf
@@ -803,7 +810,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     bulk_g2s(pbuf + (size_t)buf * pdb, Lf + S0.x, bytes, &bars[buf]);
     if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
   };
-  if (tid == 0)
+  if (!ALIAS && tid == 0)
     for (int k = 0; k < NB; ++k) issue_step(k, k);
   constexpr int nwarps = NT / 32;
   int status = 0, it = 0;
@@ -831,6 +838,10 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     __syncthreads();
     spmv_ell<true>(idx32 + Q.f_cell_base, idx + Q.f_cell_ind, F.cperm, n, Q.n_cslices, AC, w, xt, sigma, x, qh);
     __syncthreads();
+    if (ALIAS && tid == 0) {     // w is dead: the ring takes over its shared memory (generic accesses before async writes)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int k = 0; k < NB; ++k) issue_step(k, (int)((used + k) % NB));
+    }
     PROF_ADD(0);
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
     double acc0 = 0.0, acc1 = 0.0, racc = 0.0;
@@ -864,7 +875,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (pend >= 0) {      // the previous step's buffer: refill it if this warp was the last one out
         if ((pend + 1) % nwarps == 0) {
           const int nx = pend_st + NB;
-          issue_step(nx >= nsched ? nx - nsched : nx, (int)((used - 1) % NB));
+          if (!ALIAS || nx < nsched) issue_step(nx >= nsched ? nx - nsched : nx, (int)((used - 1) % NB));
         }
         pend = -1;
       }
@@ -930,7 +941,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         if (pend >= 0) {
           if ((pend + 1) % nwarps == 0) {
             const int nx = pend_st + NB;
-            issue_step(nx >= nsched ? nx - nsched : nx, bsel);
+            if (!ALIAS || nx < nsched) issue_step(nx >= nsched ? nx - nsched : nx, bsel);
           }
           pend = -1;
         }
@@ -1109,7 +1120,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     PROF_ADD(8);
     if (status != 0) break;
   }
-  for (unsigned k = used; k < used + NB; ++k) mbar_wait(&bars[k % NB], (k / NB) & 1u);   // drain prefetches in flight
+  if (!ALIAS)
+    for (unsigned k = used; k < used + NB; ++k) mbar_wait(&bars[k % NB], (k / NB) & 1u);   // drain prefetches in flight
   if (it > Q.max_iter) it = Q.max_iter;
   if (status == 0) status = -2;   // maximum iterations reached
   // failure detection beyond osqp's own codes: -10 the stage factorisation met a non-positive pivot, -11 NaN iterates
@@ -1179,7 +1191,8 @@ int plm_qp_alloc(plm_handle* h) {
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 8 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
-  h->smem_admm = (size_t)(NBUF * (Q.panel_doubles + Q.g_doubles) + 2 * NBUF + L.n + L.m + 2 * (ADMM_THREADS / SYM_K) * smax + 32 + 2 + 16) * 8;
+  // throughput kernel: w aliases the panel ring
+  h->smem_admm = (size_t)(((std::max(NBUF * (Q.panel_doubles + Q.g_doubles), L.m) + 1) & ~1) + 2 * NBUF + L.n + 2 * (ADMM_THREADS / SYM_K) * smax + 32 + 2 + 16) * 8;
   h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + 2 * (ADMM_THREADS_LAT / SYM_K) * smax + 32 + 2 + 16) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024 || h->smem_admm_lat > 227 * 1024) {
