@@ -61,7 +61,7 @@ __device__ __forceinline__ StageView stage_view(const PlmLayout& L, const QpLayo
 // Scaling.  mode 0: data update (A = J values, q, l, u given).  mode 1: setup-time scaling with the dummy data of
 // optimization/ocp.py:305-310 (A = ones on the pattern, q = 1, l = -1, u = 1); only E is kept (as Eprev).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(QP_THREADS)
+__global__ void __launch_bounds__(QP_THREADS, 4)
 qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, int mode,
                 const double* __restrict__ hess, const double* __restrict__ qin, const double* __restrict__ Jv,
                 const double* __restrict__ lin, const double* __restrict__ uin, QpWork W) {
@@ -912,7 +912,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       }
       if (dir == 0) sym_panel<SYM_PARTS>(pbuf + bsel * pdb, zp, shift, r0, r1, bi, ws, we, acc0, acc1, racc);
       else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, bpart, bnp, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
-      PROF_ADD(9);
+      if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
         // shared-memory read of the panel by this warp has returned; the refill check is deferred past the next wait

@@ -7,7 +7,7 @@
 namespace plm {
 
 // A stage factor (packed lower triangle, row-major) is streamed through shared memory in panels of consecutive rows.
-#define PLM_PANEL_DOUBLES 2048        // 16 KB
+#define PLM_PANEL_DOUBLES 2192        // 17 KB: two panels per B2G stage in either sweep, four CTAs per SM
 // schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage,
 // flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage,
 // bits 3.. warp row-range table),

@@ -21,7 +21,7 @@ out = (ctypes.c_longlong * 16)()
 lib.plm_debug_admm_profile(out, 1)
 x, stats = h.sqp_step(x, p); torch.cuda.synchronize()
 lib.plm_debug_admm_profile(out, 0)
-names = ["rhs(w,spmv_cols,add)", "fwd coupling", "panel wait + sched decode", "release (syncwarp/fence/atomic/refill)", "combine + barrier", "bwd gather", "spmv_rows", "update", "check", "sym_panel loops", "cpart store + barrier", "", "", "", "", "loop"]
+names = ["rhs(w,spmv_cols,add)", "fwd coupling", "panel wait + sched decode", "release (syncwarp/fence/atomic/refill)", "combine + barrier", "rect_panel loops (bwd)", "spmv_rows", "update", "check", "sym_panel loops (fwd)", "cpart store + barrier", "", "", "", "", "loop"]
 tot = sum(out)
 print("phase ms", h.last_phase_ms(), "iters", stats[0, 0].item())
 for n_, v in zip(names, out):
