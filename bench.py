@@ -377,6 +377,12 @@ def main():
     if os.path.exists(tpath):     # per-instance DRAM bytes from the committed ncu captures, scaled to this batch
         with open(tpath) as f:
             traffic = {k: v * B for k, v in json.load(f).get("per_instance_bytes", {}).items()}
+    fp64_peak = ctypes.c_double(0.0)       # DFMA microbenchmark on this GPU
+    h.lib.plm_fp64_peak(ctypes.byref(fp64_peak))
+    ncu_pipe = {}
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            ncu_pipe = json.load(f).get("fp64_pipe_frac_ncu", {})
     line = {
         "metric": "sqp_iters_per_s", "value": value, "unit": "SQP iters/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -394,7 +400,8 @@ def main():
                      "algorithmic_bytes": bytes_admm},
         "roofline_node_eval": {"kernel": "node_eval_kernel", "bound": "hbm", "achieved": ach_eval, "peak": peak, "unit": "GB/s",
                                "frac": ach_eval / peak, "traffic": traffic.get("node_eval_kernel"),
-                               "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval},
+                               "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval,
+                               "fp64_peak_tflops_measured": fp64_peak.value, "fp64_pipe_frac_ncu": ncu_pipe.get("node_eval_kernel")},
         "mpc": {"workload": "closed loop from the nominal state: gait update + warm start + 1 SQP iteration + state advance, device resident",
                 "mpc_steps_per_s": B / (ms_mpc / 1e3), "ms_per_step": ms_mpc, "admm_iters_avg": mpc_iters},
         "e2e": {"value": total_inst / (ms_e2e / 1e3), "unit": "SQP iters/s", "h2d_bytes_per_step": int(B * (n + h.np) * 8),

@@ -184,6 +184,10 @@ int plm_mpc_step(plm_handle* h, double* d_x, double* d_p, const double* d_t0, do
 int plm_last_phase_ms(plm_handle* h, double* ms4);
 /* Number of kernels this library has launched through the handle since creation. */
 int64_t plm_launch_count(const plm_handle* h);
+/* Measurement aid (the FP64 roofline denominator is measured on the box, not assumed): runs a DFMA
+ * microbenchmark (eight independent fused multiply-add chains per thread, all SMs) on the current device and stores the
+ * sustained FP64 rate in TFLOP/s (2 flops per DFMA).  Synchronises the device.  No reference counterpart. */
+int plm_fp64_peak(double* tflops);
 
 #ifdef __cplusplus
 }

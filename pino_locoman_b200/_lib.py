@@ -66,6 +66,7 @@ SIGNATURES = {
     "plm_sqp_step": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, vp, vp, vp]),
     "plm_last_phase_ms": (ctypes.c_int, [vp, c_double_p]),
     "plm_launch_count": (ctypes.c_int64, [vp]),
+    "plm_fp64_peak": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

@@ -23,6 +23,19 @@ using namespace plm;
 
 void plm_sqp_free(plm_handle* h);
 
+// DFMA throughput microbenchmark: eight independent chains per thread (plm_fp64_peak)
+__global__ void fp64_peak_kernel(int iters, double m, double* sink) {
+  double a0 = threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double c = 1e-9;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456) *sink = r;      // never true: keeps the chains alive
+}
+
 extern "C" {
 
 void plm_fill_default_ocp_desc(plm_ocp_desc* d, int32_t dynamics, int32_t nodes) {
@@ -199,5 +212,29 @@ int plm_hess_diag(plm_handle* h, const double* d_p, int32_t batch, double* d_hes
 }
 
 int64_t plm_launch_count(const plm_handle* h) { return h->launches; }
+
+int plm_fp64_peak(double* tflops) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 3;
+  double* sink = nullptr;
+  if (cudaMalloc(&sink, sizeof(double)) != cudaSuccess) return 7;
+  const int blocks = sms * 4, threads = 512, iters = 1 << 15;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {       // first repetition warms up
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(iters, 1.0000001, sink);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(sink); return 5; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads / ((double)best * 1e-3) * 1e-12;
+  return 0;
+}
 
 }  // extern "C"
