@@ -696,21 +696,28 @@ __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const 
 }
 
 // Backward step: out[k] += sum_j B[k][j] in[j] over the resident columns [j0, j1) of B_i (column major, stride sp).  Warp
-// (chunk, part) owns the outputs k = 32 chunk + lane and every np-th resident column starting at j0 + part; the sums
-// live in registers across the panels of the stage.  Lanes read consecutive addresses, `in` is a broadcast.
+// (chunk, part) owns the outputs k = 32 chunk + lane and a contiguous share of the resident columns (ceil(c / np) of
+// them, computed with the reciprocal rcp = ceil(2^16 / np): no integer division on the step path); the sums live in
+// registers across the panels of the stage.  Lanes read consecutive addresses, `in` is a broadcast.
 __device__ __forceinline__ void rect_panel(const double* __restrict__ pan, int sp, int j0, int j1, const double* __restrict__ vin, int k,
-                                           int part, int np, double& acc0, double& acc1) {
-  const double* a = pan + k + (size_t)part * sp;
-  const int st = np * sp;
-  int j = j0 + part;
+                                           int part, int np, int rcp, double& acc0, double& acc1) {
+  const int cw = ((j1 - j0 + np - 1) * rcp) >> 16;
+  int j = j0 + part * cw;
+  const int je = min(j1, j + cw);
+  const double* a = pan + k + (j - j0) * sp;
 #pragma unroll 2
-  for (; j + np < j1; j += 2 * np) {
-    const double a0 = a[0], a1 = a[st];
+  for (; j + 1 < je; j += 2) {
+    const double a0 = a[0], a1 = a[sp];
     acc0 += a0 * vin[j];
-    acc1 += a1 * vin[j + np];
-    a += 2 * st;
+    acc1 += a1 * vin[j + 1];
+    a += 2 * sp;
   }
-  if (j < j1) acc0 += a[0] * vin[j];
+  if (j < je) acc0 += a[0] * vin[j];
+}
+
+// ceil(2^16 / v) for the small divisors of the backward-step bookkeeping: x / v == (x * rcp16(v)) >> 16 for x < 256
+__device__ __forceinline__ int rcp16(int v) {
+  return v == 1 ? 65536 : v == 2 ? 32768 : v == 3 ? 21846 : v == 4 ? 16384 : v == 5 ? 13108 : v == 6 ? 10923 : v == 7 ? 9363 : 8192;
 }
 
 template <int NT, int MINB, int NB, bool LAT>
@@ -846,7 +853,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
     double acc0 = 0.0, acc1 = 0.0, racc = 0.0;
     int ws = 0, we = 0;                       // rows of the current stage owned by this warp
-    int bk = -1, bpart = 0, bnp = 1;          // backward steps: output, column part, parts of this thread's chunk
+    int bk = -1, bpart = 0, bnp = 1, brcp = 65536;   // backward steps: output, column part, parts of this thread's chunk (and reciprocal)
     int pend = -1, pend_st = 0;               // lane 0: deferred refill check of the previous step
     int4 S0 = __ldg(reinterpret_cast<const int4*>(sched));
     int4 S1 = __ldg(reinterpret_cast<const int4*>(sched) + 1);
@@ -858,10 +865,11 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (first) {
         if (dir == 0) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
         else {          // backward: warp -> (chunk of 32 outputs, column part)
-          const int nch = (s + 31) >> 5, wp = tid >> 5;
-          bpart = wp / nch;
+          const int nch = (s + 31) >> 5, wp = tid >> 5, rn = rcp16(nch);      // nch <= 4 (s <= SYM_K)
+          bpart = (wp * rn) >> 16;
           const int chunk = wp - bpart * nch;
-          bnp = min(CP_SLICES, (nwarps - chunk + nch - 1) / nch);
+          bnp = min(CP_SLICES, ((nwarps - chunk + nch - 1) * rn) >> 16);
+          brcp = rcp16(bnp);
           bk = 32 * chunk + (tid & 31);
           if (bpart >= CP_SLICES || bk >= s) bk = -1;
         }
@@ -911,7 +919,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         acc0 = 0.0; acc1 = 0.0; racc = 0.0;
       }
       if (dir == 0) sym_panel<SYM_PARTS>(pbuf + bsel * pdb, zp, shift, r0, r1, bi, ws, we, acc0, acc1, racc);
-      else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, bpart, bnp, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
+      else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, bpart, bnp, brcp, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
       if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
@@ -955,7 +963,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
             bi[tid] = o;
           } else {
             const int nch = (s + 31) >> 5;
-            const int np = min(CP_SLICES, (nwarps - (tid >> 5) + nch - 1) / nch);
+            const int np = min(CP_SLICES, ((nwarps - (tid >> 5) + nch - 1) * rcp16(nch)) >> 16);
             for (int w2 = 1; w2 < np; ++w2) o += cpart[w2 * smax + tid];
             bi[tid] -= o;
           }
