@@ -78,7 +78,7 @@ def synthetic_inputs(robot, ocp, batch, rank):
     B, nj = batch, robot.nj
     q = np.tile(robot.q0, (B, 1))
     q[:, 0:2] = rng.uniform(-1, 1, (B, 2))
-    q[:, 2] = rng.uniform(0.45, 0.65, B)
+    q[:, 2] = rng.uniform(0.28, 0.40, B) if robot.q0[2] < 0.4 else rng.uniform(0.45, 0.65, B)      # Go2 stands lower
     yaw, roll, pitch = rng.uniform(-np.pi, np.pi, B), rng.uniform(-0.3, 0.3, B), rng.uniform(-0.3, 0.3, B)
     cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
     q[:, 3] = sr * cp * cy - cr * sp * sy
@@ -91,14 +91,18 @@ def synthetic_inputs(robot, ocp, batch, rank):
     ocp.set_time_params(0.01, 0.08)
     ocp.set_swing_params(0.07, [0.1, -0.2])
     ocp.set_tracking_targets(np.array([0.2, 0, 0, 0, 0, 0]), rng.uniform(-20, 20, (B, 3)), rng.uniform(-0.2, 0.2, (B, 3)))
-    ocp.update_initial_state(np.concatenate((q, v), 1))
+    if ocp.dynamics == "centroidal_vel":      # state (h, q): normalised centroidal momentum instead of v
+        ocp.update_initial_state(np.concatenate((rng.uniform(-0.5, 0.5, (B, 6)), q), 1))
+    else:
+        ocp.update_initial_state(np.concatenate((q, v), 1))
     ocp.update_gait_sequence(rng.integers(0, 80, B) * 0.01)
-    ocp.update_previous_torques(np.zeros(nj))
+    if hasattr(ocp, "update_previous_torques"):
+        ocp.update_previous_torques(np.zeros(nj))
     x = ocp.initial_guess()
     h = ocp.handle
     contact = ocp._get("contact_schedule").reshape(B, ocp.nodes, 4)
     mg = ocp.mass * 9.81
-    lead = robot.nv
+    lead = ocp._lead()                         # leading input block: a (nv), v (nv) or tau_j (nj)
     for i in range(ocp.nodes + 1):
         o = h.x_off[i]
         if i > 0:
@@ -106,13 +110,19 @@ def synthetic_inputs(robot, ocp, batch, rank):
         if i == ocp.nodes:
             break
         u = x[:, o + ocp.ndx_opt:o + ocp.ndx_opt + ocp.nu_opt[i]]
-        u[:, :lead] = rng.normal(0, 5, (B, lead))
+        if ocp.dynamics == "whole_body_aba":
+            u[:, :lead] = rng.uniform(-0.5, 0.5, (B, lead)) * robot.joint_torque_max
+        elif ocp.dynamics == "centroidal_vel":
+            u[:, :lead] = v
+        else:
+            u[:, :lead] = rng.normal(0, 5, (B, lead))
         for k in range(4):
             fz = rng.uniform(0, mg, B)
             u[:, lead + 3 * k] = 0.7 * fz * rng.uniform(-0.5, 0.5, B) * contact[:, i, k]
             u[:, lead + 3 * k + 1] = 0.7 * fz * rng.uniform(-0.5, 0.5, B) * contact[:, i, k]
             u[:, lead + 3 * k + 2] = fz * contact[:, i, k]
-        u[:, lead + 12:lead + 15] = rng.uniform(-20, 20, (B, 3))
+        if robot.nf > 12:
+            u[:, lead + 12:lead + 15] = rng.uniform(-20, 20, (B, 3))
         if ocp.nu_opt[i] > lead + robot.nf:
             u[:, lead + robot.nf:] = rng.uniform(-0.5, 0.5, (B, nj)) * robot.joint_torque_max
     return x, ocp._p.copy()
@@ -198,6 +208,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="MPC instances per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the extra legs on BASELINE configs[0], [2], [3]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,6 +348,57 @@ def main():
         single_phase = [float(v) for v in o1.handle.last_phase_ms()]
         launches += o1.handle.launch_count()
         del o1
+    # ---- the other BASELINE configs (parity-test cases; measured here as extra keys, rank 0 only):
+    # [0] Go2 centroidal_vel single instance, [2] B2G whole_body_aba x 1024 instances, [3] 4096 B2 centroidal_acc node sweep
+    other = {}
+    if rank == 0 and not args.no_other_configs:
+        from pino_locoman_b200.utils.robot import B2, Go2
+
+        def config_leg(robot_cls, dynamics, batch, sweep_only, bytes_node_eval):
+            nonlocal launches
+            r = robot_cls()
+            r.set_gait_sequence("trot", 0.8)
+            o = make_ocp(dynamics=dynamics, default_args=OCP_ARGS[dynamics], robot=r, nodes=NODES, solver="osqp", batch=batch, device=dev)
+            xh, ph = synthetic_inputs(r, o, batch, 0)
+            o.init_solver()
+            hh = o.handle
+            xd, pd = torch.from_numpy(xh).to(dev), torch.from_numpy(ph).to(dev)
+            gg = torch.empty(batch, hh.m, dtype=torch.float64, device=dev)
+            JJ = torch.empty(batch, hh.nnz, dtype=torch.float64, device=dev)
+            for _ in range(3):
+                hh.lib.plm_sqp_data(hh._h, _ptr(xd), _ptr(pd), batch, None, _ptr(JJ), _ptr(gg), None, None, stream)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(10):
+                hh.lib.plm_sqp_data(hh._h, _ptr(xd), _ptr(pd), batch, None, _ptr(JJ), _ptr(gg), None, None, stream)
+            c1.record()
+            torch.cuda.synchronize()
+            ms_sw = c0.elapsed_time(c1) / 10
+            res = {"instances": batch, "n": hh.n, "m": hh.m, "nnz_J": hh.nnz, "ms_per_sweep": ms_sw,
+                   "node_evals_per_s": batch * NODES / (ms_sw / 1e3), "bytes_per_node_eval": bytes_node_eval,
+                   "roofline_frac_hbm": batch * NODES * bytes_node_eval / (ms_sw / 1e3) / 1e9 / peak_hbm}
+            if not sweep_only:
+                xn, st = torch.empty_like(xd), torch.empty(batch, 8, dtype=torch.float64, device=dev)
+                ts, its = [], []
+                for k in range(5):
+                    c0.record()
+                    hh.sqp_step(xd, pd, xn, st)
+                    c1.record()
+                    torch.cuda.synchronize()
+                    ts.append(c0.elapsed_time(c1))
+                    its.append(float(st[:, 0].mean()))
+                    xd, xn = xn, xd
+                ms_it = float(np.median(ts[1:]))
+                res.update({"ms_per_sqp_iter": ms_it, "sqp_iters_per_s": batch / (ms_it / 1e3), "admm_iters_avg": float(np.mean(its[1:])),
+                            "phase_ms": dict(zip(("eval", "qp_update", "qp_solve", "line_search"), [float(v) for v in hh.last_phase_ms()]))})
+            launches += hh.launch_count()
+            return res
+
+        peak_hbm = load_peaks()[0]
+        other["go2_centroidal_vel_1"] = config_leg(Go2, "centroidal_vel", 1, False, 6144.0)
+        other["b2g_whole_body_aba_1024"] = config_leg(B2G, "whole_body_aba", 1024, False, 20172.0)
+        other["b2_centroidal_acc_4096_sweep"] = config_leg(B2, "centroidal_acc", 4096, True, 7320.0)
     # ---- end to end through the plugin surface: host buffers in, host buffers out
     ocp._x0 = x.cpu().numpy()
     for _ in range(min(W, 1)):
@@ -408,6 +470,7 @@ def main():
                 "d2h_bytes_per_step": int(B * (n + 8) * 8)},
         "single_instance": {"workload": "b2 whole_body_rnea trot N=20, 1 instance (BASELINE configs[1])", "ms_per_sqp_iter": single_ms,
                             "phase_ms": dict(zip(("eval", "qp_update", "qp_solve", "line_search"), single_phase))},
+        "other_configs": other,
         "gpu_launches": int(launches_timed), "gpu_launches_all_legs": int(launches),
         "clocks": sampler.summary(),
     }

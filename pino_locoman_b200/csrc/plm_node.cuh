@@ -73,7 +73,12 @@ struct LaneState {
 };
 
 PLM_HD void emit(const NodeWs& ws, const NodeArgs& A, int src, int idx, double val) {
+#if defined(__CUDA_ARCH__)
+  // read-only path: the lookups of a run of emits can be issued ahead of the stores of the earlier ones
+  int pos = __ldg(A.lut + A.T->src_off[src] + idx);
+#else
   int pos = A.lut[A.T->src_off[src] + idx];
+#endif
   if (pos >= 0) ws.J[pos] = val;
 }
 

@@ -84,13 +84,15 @@ PLM_HD void exp_coeffs(double t2, double* A, double* B, double* C) {
   if (t2 < 0.25) {
     double a = 0, b = 0, c = 0;
     // Horner over 11 terms: sum (-1)^i t2^i / (2i+k)!
+    // (the ratios are compile-time reciprocals once the loop is unrolled: no FP64 divisions on the device)
+#pragma unroll
     for (int i = 11; i >= 0; --i) {
-      double k1 = (2.0 * i + 2.0) * (2.0 * i + 3.0);   // ratio for A terms (k=1)
-      double k2 = (2.0 * i + 3.0) * (2.0 * i + 4.0);   // k=2
-      double k3 = (2.0 * i + 4.0) * (2.0 * i + 5.0);   // k=3
-      a = 1.0 - t2 * a / k1;
-      b = 1.0 - t2 * b / k2;
-      c = 1.0 - t2 * c / k3;
+      const double r1 = 1.0 / ((2.0 * i + 2.0) * (2.0 * i + 3.0));   // ratio for A terms (k=1)
+      const double r2 = 1.0 / ((2.0 * i + 3.0) * (2.0 * i + 4.0));   // k=2
+      const double r3 = 1.0 / ((2.0 * i + 4.0) * (2.0 * i + 5.0));   // k=3
+      a = 1.0 - t2 * a * r1;
+      b = 1.0 - t2 * b * r2;
+      c = 1.0 - t2 * c * r3;
     }
     *A = a; *B = b * 0.5; *C = c / 6.0;
   } else {
