@@ -542,19 +542,21 @@ __device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const
     double add = 0.0;
     if (ADD && o >= 0) add = sigma * x[o] - __ldg(q + o);      // x is rewritten by this kernel: coherent load
     double acc = 0.0;
-    for (int p = b0; p < b1; p += 32 * ELL_B) {
+    // every slot row of a slice is 32 wide (padded), so the row count is warp uniform: full groups of ELL_B rows run
+    // without predicates, the remaining rows one at a time
+    int p = b0;
+    for (; p + 32 * (ELL_B - 1) < b1; p += 32 * ELL_B) {
       double a[ELL_B];
       int c[ELL_B];
 #pragma unroll
       for (int j = 0; j < ELL_B; ++j) {
-        const int pp = p + 32 * j;
-        const bool ok = pp < b1;
-        a[j] = ok ? __ldg(vals + pp) : 0.0;
-        c[j] = ok ? (int)__ldg(ind + pp) : 0;
+        a[j] = __ldg(vals + p + 32 * j);
+        c[j] = (int)__ldg(ind + p + 32 * j);
       }
 #pragma unroll
       for (int j = 0; j < ELL_B; ++j) acc += a[j] * v[c[j]];
     }
+    for (; p < b1; p += 32) acc += __ldg(vals + p) * v[(int)__ldg(ind + p)];
     if (o >= 0) out[o] = acc + add;
   }
 }
@@ -572,17 +574,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+#ifndef PLM_MBAR_SUSPEND_NS
+#define PLM_MBAR_SUSPEND_NS 1000
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra.uni WAIT_DONE;\n"
       "bra.uni WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(PLM_MBAR_SUSPEND_NS)      // suspend-time hint: the warp sleeps instead of spinning on issue slots
       : "memory");
 }
 
