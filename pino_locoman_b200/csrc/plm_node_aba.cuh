@@ -7,18 +7,20 @@
 
 namespace plm {
 
-#define PLM_LD 32   // leading dimension of the nv x nv scratch matrices (bank-conflict-free column access)
 
 template <class Exec>
 PLM_HD void aba_solve_and_derivatives(Exec& ex, NodeWs& ws, const NodeArgs& A) {
   const PlmModel& M = *A.M;
   const PlmLayout& L = *A.L;
   const int nv = M.nv, nf = L.nf, nj = M.nj;
-  double* Ms = ws.aba;                 // M, then its Cholesky factor (lower)
-  double* Mi = ws.aba + PLM_LD * nv;   // M^-1
-  double* GQ = ws.aba + 2 * PLM_LD * nv;
-  double* GV = ws.aba + 3 * PLM_LD * nv;
-  double* GF = ws.aba + 4 * PLM_LD * nv;   // [nv][nf]
+  // nv x nv scratch matrices with an odd leading dimension: row-per-lane and column-per-lane accesses are both free of
+  // bank conflicts.  The Cholesky factor is dead once M^-1 exists, so d rnea / dq reuses its storage.
+  const int PLM_LD = nv | 1;
+  double* Mi = ws.aba;                 // M^-1
+  double* Ms = ws.aba + PLM_LD * nv;   // M, then its Cholesky factor (lower)
+  double* GQ = Ms;                     // d rnea / dq (after step 4)
+  double* GV = ws.aba + 2 * PLM_LD * nv;
+  double* GF = ws.aba + 3 * PLM_LD * nv;   // [nv][nf]
   const double* u = A.xs + L.ndx;
 
   // 1. bias torques (a = 0), J and I^C J per column
@@ -42,13 +44,13 @@ PLM_HD void aba_solve_and_derivatives(Exec& ex, NodeWs& ws, const NodeArgs& A) {
       Ms[lane * PLM_LD + c] = v;
     }
   });
-  // 3. Cholesky M = L L^T (right-looking, lane = row)
+  // 3. Cholesky M = L L^T (right-looking, lane = row; reciprocals on the diagonal)
   for (int k = 0; k < nv; ++k) {
     ex.run([&](int lane, LaneState&) {
-      if (lane == k) Ms[k * PLM_LD + k] = sqrt(Ms[k * PLM_LD + k]);
+      if (lane == k) Ms[k * PLM_LD + k] = 1.0 / sqrt(Ms[k * PLM_LD + k]);      // the diagonal holds 1 / L_kk: no divisions below
     });
     ex.run([&](int lane, LaneState&) {
-      if (lane > k && lane < nv) Ms[lane * PLM_LD + k] /= Ms[k * PLM_LD + k];
+      if (lane > k && lane < nv) Ms[lane * PLM_LD + k] *= Ms[k * PLM_LD + k];
     });
     ex.run([&](int lane, LaneState&) {
       if (lane > k && lane < nv) {
@@ -64,13 +66,13 @@ PLM_HD void aba_solve_and_derivatives(Exec& ex, NodeWs& ws, const NodeArgs& A) {
     for (int i = 0; i < nv; ++i) {
       double s = (i == lane) ? 1.0 : 0.0;
       for (int j = 0; j < i; ++j) s -= Ms[i * PLM_LD + j] * Mi[j * PLM_LD + lane];
-      Mi[i * PLM_LD + lane] = s / Ms[i * PLM_LD + i];
+      Mi[i * PLM_LD + lane] = s * Ms[i * PLM_LD + i];
     }
     // backward: L^T x = y
     for (int i = nv - 1; i >= 0; --i) {
       double s = Mi[i * PLM_LD + lane];
       for (int j = i + 1; j < nv; ++j) s -= Ms[j * PLM_LD + i] * Mi[j * PLM_LD + lane];
-      Mi[i * PLM_LD + lane] = s / Ms[i * PLM_LD + i];
+      Mi[i * PLM_LD + lane] = s * Ms[i * PLM_LD + i];
     }
   });
   ex.run([&](int lane, LaneState& st) {

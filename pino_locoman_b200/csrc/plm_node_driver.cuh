@@ -5,7 +5,7 @@
 
 namespace plm {
 
-PLM_HD size_t aba_ws_doubles(int nv, int nf) { return (size_t)4 * 32 * nv + (size_t)nv * nf; }
+PLM_HD size_t aba_ws_doubles(int nv, int nf) { return (size_t)3 * (nv | 1) * nv + (size_t)nv * nf; }   // M^-1, L | dq block, dv block, df block
 
 #if defined(__CUDACC__)
 struct WarpExec {

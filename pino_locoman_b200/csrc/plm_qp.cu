@@ -908,13 +908,22 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
                 bi[tid] -= acc;
               }
             } else {
+              // dense integrator rows (whole_body_aba, centroidal_vel): eight lanes per row, shuffle reduction
               const double* Ap = Ah + L.nnz_off[i - 1];
               const double* rp = rho + L.row_off[i - 1];
-              for (int c2 = tid; c2 < ndx; c2 += nth) {
-                const int e1 = sp.rptr[c2 + 1] - 1;
+              const int sub = tid & 7;
+              for (int c0 = 0; c0 < ndx; c0 += nth >> 3) {
+                const int c2 = c0 + (tid >> 3);
                 double acc = 0.0;
-                for (int e = sp.rptr[c2]; e < e1; ++e) acc += Ap[e] * tprev[sp.ccol[e]];
-                bi[c2] -= rp[c2] * Ap[e1] * acc;
+                int e1 = 0;
+                if (c2 < ndx) {
+                  e1 = sp.rptr[c2 + 1] - 1;
+                  for (int e = sp.rptr[c2] + sub; e < e1; e += 8) acc += Ap[e] * tprev[sp.ccol[e]];
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (c2 < ndx && sub == 0) bi[c2] -= rp[c2] * Ap[e1] * acc;
               }
             }
             __syncthreads();
