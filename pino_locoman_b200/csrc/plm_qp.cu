@@ -466,17 +466,22 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       __syncthreads();
       continue;
     }
-    for (int o = tid; o < s * ndx; o += nth) {
-      const int t = o / ndx, c2 = o % ndx;
-      const int e0 = sv.rptr[c2], e1 = sv.rptr[c2 + 1] - 1;
-      const double g = rs[c2] * As[e1];
-      double acc = 0.0;
-      const double* Xt = H + tri(t, 0);
-      for (int e = e0; e < e1; ++e) {
-        const int k = sv.ccol[e];
-        if (k <= t) acc += As[e] * Xt[k];
+    {   // lanes of a warp share the integrator row c2 (uniform entry loop: dense and sparse rows do not mix) and take
+        // consecutive rows t of X
+      const int s32 = (s + 31) & ~31;
+      for (int o = tid; o < s32 * ndx; o += nth) {
+        const int c2 = o / s32, t = o - c2 * s32;
+        if (t >= s) continue;
+        const int e0 = sv.rptr[c2], e1 = sv.rptr[c2 + 1] - 1;
+        const double g = rs[c2] * As[e1];
+        double acc = 0.0;
+        const double* Xt = H + tri(t, 0);
+        for (int e = e0; e < e1; ++e) {
+          const int k = sv.ccol[e];
+          if (k <= t) acc += As[e] * Xt[k];
+        }
+        Wm[t * ndx + c2] = g * acc;
       }
-      Wm[o] = g * acc;
     }
     __syncthreads();
     {   // B_i = S_i^-1 G_i^T = X^T W (see the sparse branch)
