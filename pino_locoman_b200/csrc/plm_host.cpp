@@ -444,7 +444,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   Q.fac_total = fo;
   {
     // panel schedules: forward sweep stages 0..N (row panels of the packed S_i^-1), backward sweep stages N-1..0
-    // (column panels of B_i), panels of at most `capacity` doubles.  Two schedules: 16 KB panels for the throughput kernel (three CTAs per SM), whole stages
+    // (column panels of B_i), panels of at most `capacity` doubles.  Two schedules: PLM_PANEL_DOUBLES panels for the throughput kernel (four CTAs per SM), whole stages
     // for the latency kernel (one CTA per SM, shared memory to spare).
     auto build = [&](int capacity, int32_t wr[PLM_WR_TABLES][5], int32_t& f_sched, int32_t& n_sched, int32_t& panel_doubles) {
       std::vector<int> sched;

@@ -5,7 +5,8 @@
 //   qp_scale_kernel   Ruiz equilibration (scale_data), cost scaling, rho_vec classification
 //   qp_factor_kernel  reduced KKT  H = P + sigma I + A^T diag(rho) A  is block tridiagonal over the shooting
 //                     stages (only the integrator rows couple stage i with DX_{i+1}); block Cholesky, the inverse
-//                     of every stage factor is stored packed (Linv_i), so the ADMM sweeps are plain mat-vecs
+//                     S_i^-1 of every Schur-complemented stage block is stored packed together with the
+//                     back-substitution block B_i = S_i^-1 G_i^T, so the ADMM sweeps are plain mat-vecs
 //   qp_admm_kernel    x~ = H^-1 (sigma x - q + A^T(rho z - y)), z~ = A x~, relaxation, projection on [l,u],
 //                     dual update, termination tests every check_termination iterations (unscaled residuals,
 //                     primal / dual infeasibility certificates), persistent warm-started iterates.
@@ -597,13 +598,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 // The inverse stage blocks S_i^-1 (symmetric, packed lower triangles, row-major) are streamed through shared memory in
-// panels of consecutive rows (<= 16 KB) by bulk asynchronous copies, NBUF panels deep, following a host-built schedule
+// panels of consecutive rows (<= PLM_PANEL_DOUBLES) by bulk asynchronous copies, NBUF panels deep, following a host-built schedule
 // of one ADMM iteration.  A sweep step is one symmetric product out = S_i^-1 in; each stored element S[t][k] is read
 // once and used twice (row part out[t] += S[t][k] in[k], column part out[k] += S[t][k] in[t], k < t):
 //   forward  stage i: tv_i = S_i^-1 (b_i - G_{i-1} tv_{i-1})
 //   backward stage i: x_i  = tv_i - B_i x_{i+1}[0:ndx],  B_i = S_i^-1 G_i^T (s x ndx, from the factor kernel; x_N = tv_N):
 //                     a plain product, column panels of B_i, every element read from shared memory once
-// Two instantiations: throughput (256 threads, 3 CTAs per SM) and, for batches that leave SMs idle, latency (512
+// Two instantiations: throughput (256 threads, 4 CTAs per SM) and, for batches that leave SMs idle, latency (512
 // threads, one CTA per SM, no register pressure).
 #define ADMM_THREADS 256
 #define ADMM_MIN_CTAS 4

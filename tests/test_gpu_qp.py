@@ -91,3 +91,12 @@ def test_failure_codes(robots):
     assert status[0] in (1, 2, -2) and torch.isfinite(dx[0]).all()
     assert status[1] == -11
     assert status[2] == -10
+
+
+def test_fp64_peak_microbenchmark():
+    """plm_fp64_peak (the measured FP64 roofline denominator of bench.py) returns a plausible DFMA rate."""
+    import ctypes
+    from pino_locoman_b200 import _lib
+    t = ctypes.c_double(0.0)
+    assert _lib.load().plm_fp64_peak(ctypes.byref(t)) == 0
+    assert 5.0 < t.value < 100.0, t.value          # B200: about 36-40 TFLOP/s
