@@ -238,7 +238,18 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
         for (int e = sv.cptr[j]; e < sv.cptr[j + 1]; ++e) {
           const int r = sv.crow[e];
           const double w = rs[r] * As[sv.cpos[e]];
-          for (int e2 = sv.rptr[r]; e2 < sv.rptr[r + 1]; ++e2) {
+          // the columns of one row are distinct (ascending): four read-modify-writes of H in flight at a time
+          int e2 = sv.rptr[r];
+          const int e2e = sv.rptr[r + 1];
+          for (; e2 + 3 < e2e && sv.ccol[e2 + 3] <= j; e2 += 4) {
+            const int k0 = sv.ccol[e2], k1 = sv.ccol[e2 + 1], k2 = sv.ccol[e2 + 2], k3 = sv.ccol[e2 + 3];
+            const double h0 = Hj[k0], h1 = Hj[k1], h2 = Hj[k2], h3 = Hj[k3];
+            Hj[k0] = h0 + w * As[e2];
+            Hj[k1] = h1 + w * As[e2 + 1];
+            Hj[k2] = h2 + w * As[e2 + 2];
+            Hj[k3] = h3 + w * As[e2 + 3];
+          }
+          for (; e2 < e2e; ++e2) {
             const int k = sv.ccol[e2];
             if (k > j) break;
             Hj[k] += w * As[e2];
