@@ -591,6 +591,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+#ifndef PLM_BWD_SINGLE
+#define PLM_BWD_SINGLE 1
+#endif
 #ifndef PLM_MBAR_SUSPEND_NS
 #define PLM_MBAR_SUSPEND_NS 1000
 #endif
@@ -727,14 +730,18 @@ __device__ __forceinline__ void rect_panel(const double* __restrict__ pan, int s
   int j = j0 + part * cw;
   const int je = min(j1, j + cw);
   const double* a = pan + k + (j - j0) * sp;
-#pragma unroll 2
-  for (; j + 1 < je; j += 2) {
-    const double a0 = a[0], a1 = a[sp];
+  double s2 = 0.0, s3 = 0.0;        // four independent chains: one warp may own all the columns of a stage
+  for (; j + 3 < je; j += 4) {
+    const double a0 = a[0], a1 = a[sp], a2 = a[2 * sp], a3 = a[3 * sp];
     acc0 += a0 * vin[j];
     acc1 += a1 * vin[j + 1];
-    a += 2 * sp;
+    s2 += a2 * vin[j + 2];
+    s3 += a3 * vin[j + 3];
+    a += 4 * sp;
   }
-  if (j < je) acc0 += a[0] * vin[j];
+  for (; j < je; ++j) { acc0 += a[0] * vin[j]; a += sp; }
+  acc0 += s2;
+  acc1 += s3;
 }
 
 // ceil(2^16 / v) for the small divisors of the backward-step bookkeeping: x / v == (x * rcp16(v)) >> 16 for x < 256
@@ -887,6 +894,12 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (first) {
         if (dir == 0) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
         else {          // backward: warp -> (chunk of 32 outputs, column part)
+#if PLM_BWD_SINGLE
+          // one warp per 32 outputs over all the columns: no partial sums, the result goes straight into x_i and the
+          // stage needs one CTA barrier instead of two
+          bk = tid < s ? tid : -1;
+          bpart = 0; bnp = 1; brcp = 65536;
+#else
           const int nch = (s + 31) >> 5, wp = tid >> 5, rn = rcp16(nch);      // nch <= 4 (s <= SYM_K)
           bpart = (wp * rn) >> 16;
           const int chunk = wp - bpart * nch;
@@ -894,6 +907,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           brcp = rcp16(bnp);
           bk = 32 * chunk + (tid & 31);
           if (bpart >= CP_SLICES || bk >= s) bk = -1;
+#endif
         }
       }
       {   // schedule entry of the next step (consumed at the end of this one)
@@ -973,7 +987,12 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
             if (k < we) cp[k] = sum;
             __syncwarp();
             if (kr < we) cp[kr] += racc;
-          } else if (bk >= 0) cpart[bpart * smax + bk] = sum;
+          }
+#if PLM_BWD_SINGLE
+          else if (bk >= 0) bi[bk] -= sum;       // nothing else reads stage i's slice of xt during its backward step
+#else
+          else if (bk >= 0) cpart[bpart * smax + bk] = sum;
+#endif
         }
       }
       if (last) {
@@ -986,6 +1005,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         }
         __syncthreads();
         PROF_ADD(10);
+        if (PLM_BWD_SINGLE && dir == 1) continue;
         if (tid < s) {
           double o = cpart[tid];
           if (dir == 0) {
