@@ -929,13 +929,23 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         if (dir == 0) {
           if (i > 0) {     // b_i -= G_{i-1} tv_{i-1}
             const StageView sp = stage_view(L, Q, idx, i - 1);
-            const double* tprev = xt + L.x_off[i - 1];
+            // tv_{i-1} still sits in the partial sums of the parts (one slice set per stage parity): they are added up
+            // here, on read, which saves the combine pass and its CTA barrier; the sum also goes to stage i-1's slice
+            // of xt, where the backward sweep expects it
+            const double* pp = cpart + ((i - 1) & 1) * SYM_PARTS * smax;
+            auto tprev = [&](int k) {
+              double v = pp[k];
+#pragma unroll
+              for (int w2 = 1; w2 < SYM_PARTS; ++w2) v += pp[w2 * smax + k];
+              return v;
+            };
+            if (tid < L.x_off[i] - L.x_off[i - 1]) xt[L.x_off[i - 1] + tid] = tprev(tid);
             if (sparse) {
               if (tid < ndx) {
                 const int e0 = sp.rptr[tid], ne = sp.rptr[tid + 1] - 1 - e0;
                 double acc = 0.0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc += g[4 * tid + j] * tprev[sp.ccol[e0 + (j < ne ? j : 0)]];
+                for (int j = 0; j < 4; ++j) acc += g[4 * tid + j] * tprev(sp.ccol[e0 + (j < ne ? j : 0)]);
                 bi[tid] -= acc;
               }
             } else {
@@ -949,7 +959,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
                 int e1 = 0;
                 if (c2 < ndx) {
                   e1 = sp.rptr[c2 + 1] - 1;
-                  for (int e = sp.rptr[c2] + sub; e < e1; e += 8) acc += Ap[e] * tprev[sp.ccol[e]];
+                  for (int e = sp.rptr[c2] + sub; e < e1; e += 8) acc += Ap[e] * tprev(sp.ccol[e]);
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 4);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -983,7 +993,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           if (dir == 0) {
             const int lane = tid & 31;
             const int k = ws + lane, kr = ws + ((lane & 15) << 1) + (lane >> 4);
-            double* cp = cpart + (tid / SYM_K) * smax;
+            double* cp = cpart + ((i & 1) * SYM_PARTS + tid / SYM_K) * smax;
             if (k < we) cp[k] = sum;
             __syncwarp();
             if (kr < we) cp[kr] += racc;
@@ -1006,11 +1016,12 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         __syncthreads();
         PROF_ADD(10);
         if (PLM_BWD_SINGLE && dir == 1) continue;
+        if (dir == 0 && i < N) continue;          // forward stages: the next stage adds the partial sums up on read
         if (tid < s) {
-          double o = cpart[tid];
+          double o = cpart[(dir == 0 ? (i & 1) * SYM_PARTS * smax : 0) + tid];
           if (dir == 0) {
 #pragma unroll
-            for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[w2 * smax + tid];
+            for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[((i & 1) * SYM_PARTS + w2) * smax + tid];
             bi[tid] = o;
           } else {
             const int nch = (s + 31) >> 5;
