@@ -850,11 +850,14 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     for (int k = 0; k < NB; ++k) issue_step(k, k);
   constexpr int nwarps = NT / 32;
   int status = 0, it = 0;
+  bool w_ready = false;   // shared w already holds rho z - y of the current iterates
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
   PROF_T0();
   for (it = 1; it <= Q.max_iter; ++it) {
     PROF_ADD(15);
-    // ---- rhs = sigma x - q + A^T (rho z - y)
+    // ---- rhs = sigma x - q + A^T (rho z - y); w = rho z - y is left in shared memory by the update phase of the
+    // previous iteration unless that one ran the termination tests (which need delta_y there)
+    if (!w_ready) {
     for (int r0 = tid; r0 < m; r0 += 4 * nth) {
       double a[4], c[4], d[4];
 #pragma unroll
@@ -872,6 +875,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       }
     }
     __syncthreads();
+    }
     spmv_ell<true>(idx32 + Q.f_cell_base, idx + Q.f_cell_ind, F.cperm, n, Q.n_cslices, AC, w, xt, sigma, x, qh);
     __syncthreads();
     if (ALIAS && tid == 0) {     // w is dead: the ring takes over its shared memory (generic accesses before async writes)
@@ -1035,6 +1039,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       }
     }
     // ---- z~ = A x~ ; relaxation, projection, dual update
+    const bool check = (Q.check_termination > 0 && it % Q.check_termination == 0) || it == Q.max_iter;
     spmv_ell<false>(idx32 + Q.f_rell_base, idx + Q.f_rell_ind, F.rperm, m, Q.n_rslices, AR, xt, w, 0.0, nullptr, nullptr);
     __syncthreads();
     PROF_ADD(6);
@@ -1079,15 +1084,16 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           double zn = zr + yo[q4] / rr[q4];
           zn = fmin(fmax(zn, lo[q4]), up[q4]);
           const double dy = rr[q4] * (zr - zn);
-          y[r] = yo[q4] + dy;
+          const double yn = yo[q4] + dy;
+          y[r] = yn;
           z[r] = zn;
-          w[r] = dy;                // delta_y (kept for the primal infeasibility test)
+          w[r] = check ? dy : rr[q4] * zn - yn;     // delta_y for the primal infeasibility test, else the next rhs term
         }
       }
     }
     __syncthreads();
     PROF_ADD(7);
-    const bool check = (Q.check_termination > 0 && it % Q.check_termination == 0) || it == Q.max_iter;
+    w_ready = !check;
     if (!check) continue;
     const bool approx = !(Q.check_termination > 0 && it % Q.check_termination == 0);
     ndx_max = block_reduce(mdx, red, true);
