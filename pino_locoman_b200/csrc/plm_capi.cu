@@ -141,7 +141,7 @@ int plm_get_dims(const plm_handle* h, plm_dims* d) {
   d->nq = M.nq; d->nv = M.nv; d->nj = M.nj; d->nf = L.nf;
   d->nx = L.nx; d->ndx = L.ndx; d->n = L.n; d->m = L.m; d->np = L.np; d->nnz = L.nnz;
   d->nodes = L.nodes;
-  d->kkt_factor_doubles = h->qp_factor_doubles;
+  d->kkt_factor_doubles = h->host.qp.fac_total;      // host table: also valid for layout-only handles
   return 0;
 }
 
