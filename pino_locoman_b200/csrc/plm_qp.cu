@@ -550,14 +550,14 @@ struct FlatIdx {
 template <bool ADD>
 __device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const int16_t* __restrict__ ind, const int16_t* __restrict__ perm, int nitems,
                                          int nsl, const double* __restrict__ vals, const double* v, double* out, double sigma,
-                                         const double* x, const double* __restrict__ q) {
+                                         const double* x, const double* __restrict__ q, const double* addv = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int sl = warp; sl < nsl; sl += nw) {
     const int b0 = __ldg(base + sl) + lane, b1 = __ldg(base + sl + 1);
     const int item = 32 * sl + lane;
     const int o = item < nitems ? (int)__ldg(perm + item) : -1;
     double add = 0.0;
-    if (ADD && o >= 0) add = sigma * x[o] - __ldg(q + o);      // x is rewritten by this kernel: coherent load
+    if (ADD && o >= 0) add = addv ? addv[o] : sigma * x[o] - __ldg(q + o);      // (x is rewritten by this kernel: coherent load)
     double acc = 0.0;
     // every slot row of a slice is 32 wide (padded), so the row count is warp uniform: full groups of ELL_B rows run
     // without predicates, the remaining rows one at a time
@@ -851,6 +851,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   constexpr int nwarps = NT / 32;
   int status = 0, it = 0;
   bool w_ready = false;   // shared w already holds rho z - y of the current iterates
+  bool xq_ready = false;  // shared xt already holds sigma x - q of the current iterates
   double ndx_max = 0.0;   // ||D dx||_inf of the last iteration (dual infeasibility test)
   PROF_T0();
   for (it = 1; it <= Q.max_iter; ++it) {
@@ -876,7 +877,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     }
     __syncthreads();
     }
-    spmv_ell<true>(idx32 + Q.f_cell_base, idx + Q.f_cell_ind, F.cperm, n, Q.n_cslices, AC, w, xt, sigma, x, qh);
+    // (sigma x - q is left in xt by the update phase of the previous iteration, like w)
+    spmv_ell<true>(idx32 + Q.f_cell_base, idx + Q.f_cell_ind, F.cperm, n, Q.n_cslices, AC, w, xt, sigma, x, qh, xq_ready ? xt : nullptr);
     __syncthreads();
     if (ALIAS && tid == 0) {     // w is dead: the ring takes over its shared memory (generic accesses before async writes)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1045,21 +1047,23 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     PROF_ADD(6);
     double mdx = 0.0;
     for (int j0 = tid; j0 < n; j0 += 4 * nth) {
-      double xo[4], dv[4];
+      double xo[4], dv[4];      // dv: D (iterations that run the termination tests) or q (the others)
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int j = j0 + q4 * nth;
         const bool ok = j < n;
         xo[q4] = ok ? x[j] : 0.0;
-        dv[q4] = ok ? __ldg(Dv + j) : 0.0;
+        dv[q4] = ok ? __ldg((check ? Dv : qh) + j) : 0.0;
       }
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int j = j0 + q4 * nth;
         if (j < n) {
           const double xn = alpha * xt[j] + (1.0 - alpha) * xo[q4];
-          mdx = fmax(mdx, fabs(dv[q4] * (xn - xo[q4])));
-          xt[j] = xn - xo[q4];      // delta_x (kept for the dual infeasibility test)
+          if (check) {
+            mdx = fmax(mdx, fabs(dv[q4] * (xn - xo[q4])));
+            xt[j] = xn - xo[q4];      // delta_x (kept for the dual infeasibility test)
+          } else xt[j] = sigma * xn - dv[q4];      // the x part of the next right-hand side
           x[j] = xn;
         }
       }
@@ -1094,6 +1098,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     __syncthreads();
     PROF_ADD(7);
     w_ready = !check;
+    xq_ready = !check;
     if (!check) continue;
     const bool approx = !(Q.check_termination > 0 && it % Q.check_termination == 0);
     ndx_max = block_reduce(mdx, red, true);
