@@ -591,9 +591,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-#ifndef PLM_BWD_SINGLE
-#define PLM_BWD_SINGLE 1
-#endif
 #ifndef PLM_MBAR_SUSPEND_NS
 #define PLM_MBAR_SUSPEND_NS 1000
 #endif
@@ -720,18 +717,15 @@ __device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const 
   }
 }
 
-// Backward step: out[k] += sum_j B[k][j] in[j] over the resident columns [j0, j1) of B_i (column major, stride sp).  Warp
-// (chunk, part) owns the outputs k = 32 chunk + lane and a contiguous share of the resident columns (ceil(c / np) of
-// them, computed with the reciprocal rcp = ceil(2^16 / np): no integer division on the step path); the sums live in
-// registers across the panels of the stage.  Lanes read consecutive addresses, `in` is a broadcast.
+// Backward step: out[k] += sum_j B[k][j] in[j] over the resident columns [j0, j1) of B_i (column major, stride sp).  One
+// warp per 32 outputs (k = 32 warp + lane) takes all the columns; the sums live in registers across the panels of the
+// stage (four independent chains).  Lanes read consecutive addresses, `in` is a broadcast.
 __device__ __forceinline__ void rect_panel(const double* __restrict__ pan, int sp, int j0, int j1, const double* __restrict__ vin, int k,
-                                           int part, int np, int rcp, double& acc0, double& acc1) {
-  const int cw = ((j1 - j0 + np - 1) * rcp) >> 16;
-  int j = j0 + part * cw;
-  const int je = min(j1, j + cw);
-  const double* a = pan + k + (j - j0) * sp;
-  double s2 = 0.0, s3 = 0.0;        // four independent chains: one warp may own all the columns of a stage
-  for (; j + 3 < je; j += 4) {
+                                           double& acc0, double& acc1) {
+  const double* a = pan + k;
+  double s2 = 0.0, s3 = 0.0;
+  int j = j0;
+  for (; j + 3 < j1; j += 4) {
     const double a0 = a[0], a1 = a[sp], a2 = a[2 * sp], a3 = a[3 * sp];
     acc0 += a0 * vin[j];
     acc1 += a1 * vin[j + 1];
@@ -739,14 +733,9 @@ __device__ __forceinline__ void rect_panel(const double* __restrict__ pan, int s
     s3 += a3 * vin[j + 3];
     a += 4 * sp;
   }
-  for (; j < je; ++j) { acc0 += a[0] * vin[j]; a += sp; }
+  for (; j < j1; ++j) { acc0 += a[0] * vin[j]; a += sp; }
   acc0 += s2;
   acc1 += s3;
-}
-
-// ceil(2^16 / v) for the small divisors of the backward-step bookkeeping: x / v == (x * rcp16(v)) >> 16 for x < 256
-__device__ __forceinline__ int rcp16(int v) {
-  return v == 1 ? 65536 : v == 2 ? 32768 : v == 3 ? 21846 : v == 4 ? 16384 : v == 5 ? 13108 : v == 6 ? 10923 : v == 7 ? 9363 : 8192;
 }
 
 template <int NT, int MINB, int NB, bool LAT>
@@ -776,8 +765,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* xt = sm + ring_al + 2 * NB + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = ALIAS ? sm : xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   constexpr int SYM_PARTS = NT / SYM_K;
-  constexpr int CP_SLICES = 2 * SYM_PARTS;    // column parts of a backward step (at most)
-  double* cpart = xt + n + (ALIAS ? 0 : m);       // [CP_SLICES][smax] partial sums of a stage product, one slice per part
+  constexpr int CP_SLICES = 2 * SYM_PARTS;    // partial sums of the forward product: one slice per part and stage parity
+  double* cpart = xt + n + (ALIAS ? 0 : m);       // [CP_SLICES][smax]
   double* red = cpart + CP_SLICES * smax;     // [32]
   double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
@@ -888,7 +877,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
     double acc0 = 0.0, acc1 = 0.0, racc = 0.0;
     int ws = 0, we = 0;                       // rows of the current stage owned by this warp
-    int bk = -1, bpart = 0, bnp = 1, brcp = 65536;   // backward steps: output, column part, parts of this thread's chunk (and reciprocal)
+    int bk = -1;                              // backward steps: output of this thread (-1: none)
     int pend = -1, pend_st = 0;               // lane 0: deferred refill check of the previous step
     int4 S0 = __ldg(reinterpret_cast<const int4*>(sched));
     int4 S1 = __ldg(reinterpret_cast<const int4*>(sched) + 1);
@@ -899,22 +888,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const int bsel = (int)(used % NB);
       if (first) {
         if (dir == 0) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
-        else {          // backward: warp -> (chunk of 32 outputs, column part)
-#if PLM_BWD_SINGLE
-          // one warp per 32 outputs over all the columns: no partial sums, the result goes straight into x_i and the
-          // stage needs one CTA barrier instead of two
-          bk = tid < s ? tid : -1;
-          bpart = 0; bnp = 1; brcp = 65536;
-#else
-          const int nch = (s + 31) >> 5, wp = tid >> 5, rn = rcp16(nch);      // nch <= 4 (s <= SYM_K)
-          bpart = (wp * rn) >> 16;
-          const int chunk = wp - bpart * nch;
-          bnp = min(CP_SLICES, ((nwarps - chunk + nch - 1) * rn) >> 16);
-          brcp = rcp16(bnp);
-          bk = 32 * chunk + (tid & 31);
-          if (bpart >= CP_SLICES || bk >= s) bk = -1;
-#endif
-        }
+        else bk = tid < s ? tid : -1;     // backward: one warp per 32 outputs over all the columns (no partial sums: the
+                                          // result goes straight into x_i and the stage needs one CTA barrier)
       }
       {   // schedule entry of the next step (consumed at the end of this one)
         const int nst = st + 1 < nsched ? st + 1 : 0;
@@ -980,7 +955,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         acc0 = 0.0; acc1 = 0.0; racc = 0.0;
       }
       if (dir == 0) sym_panel<SYM_PARTS>(pbuf + bsel * pdb, zp, shift, r0, r1, bi, ws, we, acc0, acc1, racc);
-      else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, bpart, bnp, brcp, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
+      else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
       if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
@@ -1004,11 +979,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
             __syncwarp();
             if (kr < we) cp[kr] += racc;
           }
-#if PLM_BWD_SINGLE
           else if (bk >= 0) bi[bk] -= sum;       // nothing else reads stage i's slice of xt during its backward step
-#else
-          else if (bk >= 0) cpart[bpart * smax + bk] = sum;
-#endif
         }
       }
       if (last) {
@@ -1021,20 +992,14 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         }
         __syncthreads();
         PROF_ADD(10);
-        if (PLM_BWD_SINGLE && dir == 1) continue;
-        if (dir == 0 && i < N) continue;          // forward stages: the next stage adds the partial sums up on read
+        // backward stages are complete; forward stages leave the partial sums to the next stage's coupling step, except
+        // the last one (x_N = tv_N is the first input of the backward sweep)
+        if (dir == 1 || i < N) continue;
         if (tid < s) {
-          double o = cpart[(dir == 0 ? (i & 1) * SYM_PARTS * smax : 0) + tid];
-          if (dir == 0) {
+          double o = cpart[(i & 1) * SYM_PARTS * smax + tid];
 #pragma unroll
-            for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[((i & 1) * SYM_PARTS + w2) * smax + tid];
-            bi[tid] = o;
-          } else {
-            const int nch = (s + 31) >> 5;
-            const int np = min(CP_SLICES, ((nwarps - (tid >> 5) + nch - 1) * rcp16(nch)) >> 16);
-            for (int w2 = 1; w2 < np; ++w2) o += cpart[w2 * smax + tid];
-            bi[tid] -= o;
-          }
+          for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[((i & 1) * SYM_PARTS + w2) * smax + tid];
+          bi[tid] = o;
         }
         __syncthreads();
         PROF_ADD(4);
