@@ -99,3 +99,30 @@ def test_stored_qp_factor_size(robots, rn, kind, N):
     assert h.dims.kkt_factor_doubles == packed + back
     if (rn, kind, N) == ("b2g", "whole_body_rnea", 20):
         assert (h.n, h.m) == (1842, 2665) and h.dims.kkt_factor_doubles == 170022
+
+
+@pytest.mark.parametrize("rn,kind", [("go2", "centroidal_vel"), ("b2g", "whole_body_aba"), ("b2", "centroidal_acc"), ("b2g", "whole_body_rnea"),
+                                     ("b2", "whole_body_acc")])
+def test_bench_synthetic_inputs_cover_every_formulation(robots, rn, kind):
+    """bench.py's synthetic states (SURVEY 8d distributions) for the legs on all BASELINE configs: finite, contact-masked forces."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from pino_locoman_b200 import OCP_ARGS
+    from pino_locoman_b200.optimization import make_ocp
+    prod, _ = robots
+    B, N = 3, 20
+    ocp = make_ocp(dynamics=kind, default_args=OCP_ARGS[kind], robot=prod[rn], nodes=N, solver="osqp", batch=B, device="layout")
+    x, p = bench.synthetic_inputs(prod[rn], ocp, B, 0)
+    assert x.shape == (B, ocp.handle.n) and p.shape == (B, ocp.handle.np)
+    assert np.isfinite(x).all() and np.isfinite(p).all()
+    contact = ocp._get("contact_schedule").reshape(B, N, 4)
+    lead = ocp._lead()
+    for i in range(N):
+        o = ocp.handle.x_off[i] + ocp.ndx_opt + lead
+        f = x[:, o:o + 12].reshape(B, 4, 3)
+        assert np.all(f[contact[:, i] == 0] == 0.0)           # swing feet carry no force
+        assert np.all(f[..., 2] >= 0.0)
+    x2, p2 = bench.synthetic_inputs(prod[rn], ocp, B, 0)      # seeded: identical bits on every call (CPU and GPU arms)
+    assert np.array_equal(x, x2) and np.array_equal(p, p2)
