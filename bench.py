@@ -400,7 +400,7 @@ def main():
         other["b2g_whole_body_aba_1024"] = config_leg(B2G, "whole_body_aba", 1024, False, 20172.0)
         other["b2_centroidal_acc_4096_sweep"] = config_leg(B2, "centroidal_acc", 4096, True, 7320.0)
     # ---- end to end through the plugin surface: host buffers in, host buffers out
-    ocp._x0 = x.cpu().numpy()
+    ocp.set_initial(x.cpu().numpy())
     for _ in range(min(W, 1)):
         ocp.solve(retract_all=False)
     barrier()

@@ -169,14 +169,15 @@ int plm_sqp_step(plm_handle* h, const double* d_x, const double* d_p, int32_t ba
 /* ---- One receding-horizon step, device resident: body of the generic loop of run_mpc.py:127-143 ------- */
 /* update_gait_sequence(t) with t = t0[b] + t_add (d_t0 may be NULL: t0 = 0; utils/gait_sequence.py:37-77 and
  * optimization/ocp.py:234-242; gait 0 trot, 1 walk, 2 stand; dts_host = the `nodes` horizon step sizes of
- * optimization/ocp.py:71-74, host memory), then warm_start() when warm_start != 0 (forces in d_x reset to the
- * contact-masked f_des, the rest of the previous solution kept: ocp_whole_body_rnea.py:207-235; mass = robot mass of
- * f_des), one SQP iteration d_x -> d_x_new (plm_sqp_step), and x_init <- integrate(x_init, DX_1 of d_x_new) inside d_p
+ * optimization/ocp.py:71-74, host memory), then the starting point of the solve: x_mode 1 = warm_start() (forces in d_x
+ * reset to the contact-masked f_des, the rest of the previous solution kept: ocp_whole_body_rnea.py:207-235), x_mode 0 =
+ * no warm start (d_x <- opti.initial(): DX = 0, U = u_des, what the reference's solve() starts from when warm_start() is
+ * not called, run_mpc.py:131-132), x_mode 2 = d_x as passed (first step); one SQP iteration d_x -> d_x_new (plm_sqp_step), and x_init <- integrate(x_init, DX_1 of d_x_new) inside d_p
  * (run_mpc.py:141); with update_tau_prev != 0 (whole_body_rnea, tau_nodes > 1) also tau_prev <- tau of node 1, as the
  * compiled-solver branch of the loop does (run_mpc.py:108-111; the generic branch keeps tau_prev).  d_x and d_p are
  * updated in place; the caller swaps d_x / d_x_new between steps. */
 int plm_mpc_step(plm_handle* h, double* d_x, double* d_p, const double* d_t0, double t_add, int32_t gait, double gait_period,
-                 const double* dts_host, double mass, int32_t warm_start, int32_t update_tau_prev, int32_t batch,
+                 const double* dts_host, int32_t x_mode, int32_t update_tau_prev, int32_t batch,
                  double* d_x_new, double* d_stats, void* stream);
 
 /* Per-phase device times (ms) of the last plm_sqp_step on this handle: eval, qp_update, qp_solve, line_search.

@@ -57,7 +57,8 @@ struct plm_handle {
   // lazily created two-node probe problems backing the Dynamics* entry points (one per formulation)
   plm_probe* probes[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   int is_probe = 0;
-  int qp_setup_done = 0;
+  int qp_setup_batch = 0;   // instances [0, qp_setup_batch) have had their osqp setup (zero iterates, setup-time row scaling)
+  int ls_alloc_done = 0;
   int sqp_alloc_done = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double* d_mpc_dts = nullptr;   // [PLM_MAXNODES] horizon step sizes of plm_mpc_step
@@ -79,7 +80,7 @@ int plm_launch_bounds_shift(plm_handle* h, int batch, const double* g, const dou
 int plm_launch_stats(plm_handle* h, int batch, const int* iters, const int* status, double* stats, cudaStream_t s);
 void plm_dyn_free(plm_handle* h);
 int plm_qp_alloc(plm_handle* h);
-int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream_t s);
+int plm_qp_setup_impl(plm_handle* h, int first, int count, const double* d_hess, cudaStream_t s);
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J, const double* d_l, const double* d_u, cudaStream_t s);
 int plm_qp_solve_impl(plm_handle* h, int batch, double* d_dx, int* d_iters, int* d_status, cudaStream_t s);
 void plm_qp_free(plm_handle* h);

@@ -18,11 +18,22 @@ using namespace plm;
 
 namespace {
 
+// Python's float % for a positive period (utils/gait_sequence.py:41-42): C fmod keeps the sign of t, Python floors.
+__device__ __forceinline__ double py_mod(double t, double period) {
+  double r = fmod(t, period);
+  if (r < 0.0) r += period;
+  return r;
+}
+
 // One CTA per instance.  The schedule follows the reference operation order exactly (time accumulated node by node,
-// IEEE remainder for the phases): the flags and phases are bit-identical to the host GaitSequence.
+// floor-mod for the phases): the flags and phases are bit-identical to the host GaitSequence.
+// x_mode: 0 = no warm start: x <- opti.initial() (DX = 0, U_i = u_des[:nu_i]: zero leading block and torques, unmasked
+// f_des; optimization/ocp.py:159-163,193), what every solve() of the reference starts from when warm_start() is not
+// called (run_mpc.py:131-132); 1 = warm_start(): forces <- contact-masked f_des, the rest of the previous solution
+// kept; 2 = leave x alone (first step: the caller's initial point).
 __global__ void mpc_prepare_kernel(const PlmLayout* __restrict__ Lp, int batch, int gait, double gait_period, double swing_period, int n_contacts,
                                    const double* __restrict__ dts, const double* __restrict__ t0, double t_add, double mass,
-                                   int warm_start, double* __restrict__ x, double* __restrict__ p) {
+                                   int x_mode, double* __restrict__ x, double* __restrict__ p) {
   const PlmLayout& L = *Lp;
   const int b = blockIdx.x;
   if (b >= batch) return;
@@ -34,8 +45,8 @@ __global__ void mpc_prepare_kernel(const PlmLayout* __restrict__ Lp, int batch, 
     for (int j = 0; j < i; ++j) t = t + dts[j];
     double contact[4] = {1.0, 1.0, 1.0, 1.0}, swing[4] = {0.0, 0.0, 0.0, 0.0};
     if (gait != 2) {
-      const double gait_phase = fmod(t, gait_period) / gait_period;
-      const double swing_phase = fmod(t, swing_period) / swing_period;
+      const double gait_phase = py_mod(t, gait_period) / gait_period;
+      const double swing_phase = py_mod(t, swing_period) / swing_period;
       int f0, f1 = -1;
       if (gait == 0) {                       // trot: FR + RL, then FL + RR
         if (gait_phase < 0.5) { f0 = 0; f1 = 3; } else { f0 = 1; f1 = 2; }
@@ -49,15 +60,21 @@ __global__ void mpc_prepare_kernel(const PlmLayout* __restrict__ Lp, int batch, 
       pb[L.p_contact + 4 * i + f] = contact[f];
       pb[L.p_swing + 4 * i + f] = swing[f];
     }
-    if (warm_start) {
-      // forces of node i <- f_des masked by the contact flags (z components 0.8 / 1.2 m g / n_contacts front / rear);
-      // the external-force entries of f_des are zero
+    if (x_mode == 0) {
+      double* xs = xb + L.x_off[i];
+      const int len = L.x_off[i + 1] - L.x_off[i];
+      for (int j = 0; j < len; ++j) xs[j] = 0.0;
+      if (i == N - 1) for (int j = 0; j < L.ndx; ++j) xb[L.x_off[N] + j] = 0.0;
+    }
+    if (x_mode != 2) {
+      // forces of node i <- f_des (z components 0.8 / 1.2 m g / n_contacts front / rear), masked by the contact flags
+      // in a warm start; the external-force entries of f_des are zero
       const double fg = 9.81 * mass;
       const double fz_front = 0.8 * fg / (double)n_contacts, fz_rear = 1.2 * fg / (double)n_contacts;
       double* f = xb + L.x_off[i] + L.ndx + L.f_idx;
       for (int j = 0; j < L.nf; ++j) {
         double v = 0.0;
-        if (j < 12 && (j % 3) == 2) v = ((j / 3) < 2 ? fz_front : fz_rear) * (contact[j / 3] != 0.0 ? 1.0 : 0.0);
+        if (j < 12 && (j % 3) == 2) v = ((j / 3) < 2 ? fz_front : fz_rear) * ((x_mode == 0 || contact[j / 3] != 0.0) ? 1.0 : 0.0);
         f[j] = v;
       }
     }
@@ -98,10 +115,11 @@ __global__ void mpc_advance_kernel(const PlmLayout* __restrict__ Lp, int batch, 
 extern "C" {
 
 int plm_mpc_step(plm_handle* h, double* d_x, double* d_p, const double* d_t0, double t_add, int32_t gait, double gait_period,
-                 const double* dts_host, double mass, int32_t warm_start, int32_t update_tau_prev, int32_t batch, double* d_x_new,
+                 const double* dts_host, int32_t x_mode, int32_t update_tau_prev, int32_t batch, double* d_x_new,
                  double* d_stats, void* stream) {
   if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
   if (gait < 0 || gait > 2) { h->error = "plm_mpc_step: gait 0 trot, 1 walk, 2 stand"; return 11; }
+  if (x_mode < 0 || x_mode > 2) { h->error = "plm_mpc_step: x_mode 0 initial guess, 1 warm start, 2 keep"; return 11; }
   const PlmLayout& L = h->host.layout;
   const PlmModel& M = h->host.model;
   cudaStream_t s = (cudaStream_t)stream;
@@ -115,8 +133,8 @@ int plm_mpc_step(plm_handle* h, double* d_x, double* d_p, const double* d_t0, do
   // utils/gait_sequence.py:13-35: contacts and swing period per gait
   const int n_contacts = gait == 0 ? 2 : (gait == 1 ? 3 : 4);
   const double swing_period = gait == 0 ? 0.5 * gait_period : (gait == 1 ? 0.25 * gait_period : gait_period);
-  mpc_prepare_kernel<<<batch, 32, 0, s>>>(h->d_layout, batch, gait, gait_period, swing_period, n_contacts, h->d_mpc_dts, d_t0, t_add, mass,
-                                          warm_start, d_x, d_p);
+  mpc_prepare_kernel<<<batch, 32, 0, s>>>(h->d_layout, batch, gait, gait_period, swing_period, n_contacts, h->d_mpc_dts, d_t0, t_add, M.total_mass,
+                                          x_mode, d_x, d_p);
   PLM_LAUNCH_CHECK(h);
   h->launches++;
   if (int rc = plm_sqp_step(h, d_x, d_p, batch, d_x_new, d_stats, stream)) return rc;

@@ -63,13 +63,13 @@ __device__ __forceinline__ StageView stage_view(const PlmLayout& L, const QpLayo
 // optimization/ocp.py:305-310 (A = ones on the pattern, q = 1, l = -1, u = 1); only E is kept (as Eprev).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(QP_THREADS, 4)
-qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, int mode,
+qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, int mode, int first,
                 const double* __restrict__ hess, const double* __restrict__ qin, const double* __restrict__ Jv,
                 const double* __restrict__ lin, const double* __restrict__ uin, QpWork W) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
   const QpLayout& Q = *Qp;
-  const int b = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int b = first + blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int n = L.n, m = L.m, nnz = L.nnz;
   double* D = sm;            // [n]
   double* E = D + n;         // [m]
@@ -1259,13 +1259,14 @@ void plm_qp_free(plm_handle* h) {
   cudaFree(W.x); cudaFree(W.z); cudaFree(W.y); cudaFree(h->d_qp_fail);
 }
 
-int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream_t s) {
+// osqp setup of instances [first, first + count): d_hess is the base of the [max_batch][n] array
+int plm_qp_setup_impl(plm_handle* h, int first, int count, const double* d_hess, cudaStream_t s) {
   const PlmLayout& L = h->host.layout;
   QpWork& W = h->qp;
-  QP_CUDA(h, cudaMemsetAsync(W.x, 0, (size_t)batch * L.n * sizeof(double), s));
-  QP_CUDA(h, cudaMemsetAsync(W.z, 0, (size_t)batch * L.m * sizeof(double), s));
-  QP_CUDA(h, cudaMemsetAsync(W.y, 0, (size_t)batch * L.m * sizeof(double), s));
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, d_hess, nullptr, nullptr, nullptr, nullptr, W);
+  QP_CUDA(h, cudaMemsetAsync(W.x + (size_t)first * L.n, 0, (size_t)count * L.n * sizeof(double), s));
+  QP_CUDA(h, cudaMemsetAsync(W.z + (size_t)first * L.m, 0, (size_t)count * L.m * sizeof(double), s));
+  QP_CUDA(h, cudaMemsetAsync(W.y + (size_t)first * L.m, 0, (size_t)count * L.m * sizeof(double), s));
+  qp_scale_kernel<<<count, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, first, d_hess, nullptr, nullptr, nullptr, nullptr, W);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1273,7 +1274,7 @@ int plm_qp_setup_impl(plm_handle* h, int batch, const double* d_hess, cudaStream
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J,
                        const double* d_l, const double* d_u, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, d_hess, d_q, d_J, d_l, d_u, W);
+  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, 0, d_hess, d_q, d_J, d_l, d_u, W);
   PLM_LAUNCH_CHECK(h);
   qp_factor_kernel<<<batch, QP_THREADS, h->smem_factor, s>>>(h->tab, W.d_ql, W.d_idx, W, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);
@@ -1298,8 +1299,8 @@ extern "C" {
 
 int plm_qp_setup(plm_handle* h, int32_t batch, const double* d_hess, void* stream) {
   if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
-  h->qp_setup_done = 1;
-  return plm_qp_setup_impl(h, batch, d_hess, (cudaStream_t)stream);
+  h->qp_setup_batch = batch;
+  return plm_qp_setup_impl(h, 0, batch, d_hess, (cudaStream_t)stream);
 }
 
 int plm_qp_update(plm_handle* h, int32_t batch, const double* d_hess, const double* d_q, const double* d_J,
@@ -1314,6 +1315,7 @@ int plm_qp_solve(plm_handle* h, int32_t batch, double* d_dx, int32_t* d_iters, i
 }
 
 int plm_qp_get_iterates(plm_handle* h, int32_t batch, double* d_x, double* d_z, double* d_y, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
   const PlmLayout& L = h->host.layout;
   cudaStream_t s = (cudaStream_t)stream;
   QP_CUDA(h, cudaMemcpyAsync(d_x, h->qp.x, (size_t)batch * L.n * 8, cudaMemcpyDeviceToDevice, s));
@@ -1323,6 +1325,7 @@ int plm_qp_get_iterates(plm_handle* h, int32_t batch, double* d_x, double* d_z, 
 }
 
 int plm_qp_set_iterates(plm_handle* h, int32_t batch, const double* d_x, const double* d_z, const double* d_y, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
   const PlmLayout& L = h->host.layout;
   cudaStream_t s = (cudaStream_t)stream;
   QP_CUDA(h, cudaMemcpyAsync(h->qp.x, d_x, (size_t)batch * L.n * 8, cudaMemcpyDeviceToDevice, s));
@@ -1340,6 +1343,7 @@ int plm_debug_admm_profile(long long* out16, int reset) {
 
 /* Debug / test access to the scaling of the last plm_qp_update: D [batch][n], E [batch][m], c [batch]. */
 int plm_qp_get_scaling(plm_handle* h, int32_t batch, double* d_D, double* d_E, double* d_c, void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
   const PlmLayout& L = h->host.layout;
   cudaStream_t s = (cudaStream_t)stream;
   QP_CUDA(h, cudaMemcpyAsync(d_D, h->qp.D, (size_t)batch * L.n * 8, cudaMemcpyDeviceToDevice, s));

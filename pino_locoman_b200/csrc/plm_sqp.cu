@@ -1,8 +1,21 @@
 // Line search and the fused SQP step: orchestration of the kernels on the caller's stream.
 // Replaces the body of the loop at optimization/ocp.py:383-406 and _armijo_line_search (:430-480).
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: no-ops unless a profiler injects itself (nsys / ncu --nvtx)
+
 #include "plm_handle.cuh"
 
 using namespace plm;
+
+// NVTX range per phase of the SQP iteration (tracing); closes on scope exit
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+struct NvtxPhases {   // consecutive sub-ranges; whatever is open is closed on every exit path
+  bool open = false;
+  void next(const char* name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; }
+  ~NvtxPhases() { if (open) nvtxRangePop(); }
+};
 
 #define SQP_CUDA(h, expr)                                                              \
   do {                                                                                 \
@@ -13,26 +26,31 @@ using namespace plm;
     }                                                                                  \
   } while (0)
 
+// allocate once; a failed call leaves the workspace marked not ready and the next call allocates what is missing
+template <class T>
+static cudaError_t need(T** p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc(p, bytes); }
+
 static int ensure_ls(plm_handle* h) {
   LsWork& W = h->ls;
-  if (W.alphas) return 0;
+  if (h->ls_alloc_done) return 0;
   const PlmLayout& L = h->host.layout;
   const size_t B = (size_t)h->max_batch;
   double al[PLM_LS_TRIALS];
   double a = 1.0;
   for (int t = 0; t < PLM_LS_TRIALS; ++t) { al[t] = a; a *= 0.5; }
-  SQP_CUDA(h, cudaMalloc(&W.alphas, sizeof(al)));
+  SQP_CUDA(h, need(&W.alphas, sizeof(al)));
   SQP_CUDA(h, cudaMemcpy(W.alphas, al, sizeof(al), cudaMemcpyHostToDevice));
-  SQP_CUDA(h, cudaMalloc(&W.ftr, B * PLM_LS_TRIALS * 8));
-  SQP_CUDA(h, cudaMalloc(&W.part, B * PLM_LS_TRIALS * L.nodes * 2 * 8));
-  SQP_CUDA(h, cudaMalloc(&W.state, B * 8 * 8));
-  SQP_CUDA(h, cudaMalloc(&W.viol, B * 2 * 8));
-  SQP_CUDA(h, cudaMalloc(&W.f0, B * 8));
-  SQP_CUDA(h, cudaMalloc(&W.gdot, B * 8));
-  SQP_CUDA(h, cudaMalloc(&W.accepted, B * sizeof(int)));
-  SQP_CUDA(h, cudaMalloc(&W.g, B * L.m * 8));
-  SQP_CUDA(h, cudaMalloc(&W.lbg, B * L.m * 8));
-  SQP_CUDA(h, cudaMalloc(&W.ubg, B * L.m * 8));
+  SQP_CUDA(h, need(&W.ftr, B * PLM_LS_TRIALS * 8));
+  SQP_CUDA(h, need(&W.part, B * PLM_LS_TRIALS * L.nodes * 2 * 8));
+  SQP_CUDA(h, need(&W.state, B * 8 * 8));
+  SQP_CUDA(h, need(&W.viol, B * 2 * 8));
+  SQP_CUDA(h, need(&W.f0, B * 8));
+  SQP_CUDA(h, need(&W.gdot, B * 8));
+  SQP_CUDA(h, need(&W.accepted, B * sizeof(int)));
+  SQP_CUDA(h, need(&W.g, B * L.m * 8));
+  SQP_CUDA(h, need(&W.lbg, B * L.m * 8));
+  SQP_CUDA(h, need(&W.ubg, B * L.m * 8));
+  h->ls_alloc_done = 1;
   return 0;
 }
 
@@ -42,15 +60,16 @@ static int ensure_sqp(plm_handle* h) {
   if (h->sqp_alloc_done) return 0;
   const PlmLayout& L = h->host.layout;
   const size_t B = (size_t)h->max_batch;
-  SQP_CUDA(h, cudaMalloc(&W.grad, B * L.n * 8));
-  SQP_CUDA(h, cudaMalloc(&W.J, B * L.nnz * 8));
-  SQP_CUDA(h, cudaMalloc(&W.l, B * L.m * 8));
-  SQP_CUDA(h, cudaMalloc(&W.u, B * L.m * 8));
-  SQP_CUDA(h, cudaMalloc(&W.hess, B * L.n * 8));
-  SQP_CUDA(h, cudaMalloc(&W.dx, B * L.n * 8));
-  SQP_CUDA(h, cudaMalloc(&W.iters, B * sizeof(int)));
-  SQP_CUDA(h, cudaMalloc(&W.status, B * sizeof(int)));
-  for (int i = 0; i < 5; ++i) SQP_CUDA(h, cudaEventCreate(&h->ev[i]));
+  SQP_CUDA(h, need(&W.grad, B * L.n * 8));
+  SQP_CUDA(h, need(&W.J, B * L.nnz * 8));
+  SQP_CUDA(h, need(&W.l, B * L.m * 8));
+  SQP_CUDA(h, need(&W.u, B * L.m * 8));
+  SQP_CUDA(h, need(&W.hess, B * L.n * 8));
+  SQP_CUDA(h, need(&W.dx, B * L.n * 8));
+  SQP_CUDA(h, need(&W.iters, B * sizeof(int)));
+  SQP_CUDA(h, need(&W.status, B * sizeof(int)));
+  for (int i = 0; i < 5; ++i)
+    if (!h->ev[i]) SQP_CUDA(h, cudaEventCreate(&h->ev[i]));
   h->sqp_alloc_done = 1;
   return 0;
 }
@@ -88,8 +107,11 @@ int plm_sqp_step(plm_handle* h, const double* d_x, const double* d_p, int32_t ba
   if (int rc = ensure_sqp(h)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   LsWork& W = h->ls;
+  NvtxRange r_step("plm_sqp_step");
+  NvtxPhases ph;
   SQP_CUDA(h, cudaEventRecord(h->ev[0], s));
   // ---- sqp_data(x, p)  (optimization/ocp.py:386)
+  ph.next("sqp_data");
   if (int rc = plm_launch_targets(h, d_p, batch, s)) return rc;
   if (int rc = plm_launch_node_eval(h, d_x, d_p, batch, W.g, W.J, 1, s)) return rc;
   if (int rc = plm_launch_bounds(h, d_p, batch, W.lbg, W.ubg, s)) return rc;
@@ -97,17 +119,22 @@ int plm_sqp_step(plm_handle* h, const double* d_x, const double* d_p, int32_t ba
   if (int rc = plm_launch_hess_diag(h, d_p, batch, W.hess, s)) return rc;
   SQP_CUDA(h, cudaEventRecord(h->ev[1], s));
   // ---- osqp update (optimization/ocp.py:391-395)
-  if (!h->qp_setup_done) {
-    if (int rc = plm_qp_setup_impl(h, h->max_batch <= batch ? batch : batch, W.hess, s)) return rc;
-    h->qp_setup_done = 1;
+  ph.next("osqp_update");
+  if (h->qp_setup_batch < batch) {
+    // lazy osqp setup (optimization/ocp.py:305-313) of the instances that have not been set up yet: zero iterates and the
+    // setup-time row scaling the first bound classification uses
+    if (int rc = plm_qp_setup_impl(h, h->qp_setup_batch, batch - h->qp_setup_batch, W.hess, s)) return rc;
+    h->qp_setup_batch = batch;
   }
   if (int rc = plm_launch_bounds_shift(h, batch, W.g, W.lbg, W.ubg, W.l, W.u, s)) return rc;
   if (int rc = plm_qp_update_impl(h, batch, W.hess, W.grad, W.J, W.l, W.u, s)) return rc;
   SQP_CUDA(h, cudaEventRecord(h->ev[2], s));
   // ---- osqp solve (optimization/ocp.py:401)
+  ph.next("osqp_solve");
   if (int rc = plm_qp_solve_impl(h, batch, W.dx, W.iters, W.status, s)) return rc;
   SQP_CUDA(h, cudaEventRecord(h->ev[3], s));
   // ---- Armijo line search (optimization/ocp.py:406)
+  ph.next("armijo_line_search");
   if (int rc = plm_line_search_impl(h, d_x, d_p, W.dx, batch, W.g, W.lbg, W.ubg, d_x_new, s)) return rc;
   if (d_stats)
     if (int rc = plm_launch_stats(h, batch, W.iters, W.status, d_stats, s)) return rc;

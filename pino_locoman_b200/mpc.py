@@ -4,6 +4,8 @@
 keeps the decision vector, the parameter vector and the initial states on the GPU between steps: per step one launch
 sequence ``plm_mpc_step`` = update_gait_sequence(k dt_min) -> warm_start() -> solve() -> x_init = integrate(x_init,
 DX_prev[1]).  As in the reference's generic branch the previous torques ``tau_prev`` stay at their initial value.
+With ``warm_start=False`` every step starts from ``opti.initial()`` (DX = 0, U = u_des), as ``run_mpc.py`` does when
+its ``warm_start`` flag is off.
 
     ocp = make_ocp(..., batch=B, device="cuda:0"); ocp.set_time_params(...); ...; ocp.update_initial_state(x_init)
     mpc = BatchedMPC(ocp, warm_start=True)
@@ -46,7 +48,7 @@ class BatchedMPC:
         """One MPC step for every instance; returns the device tensor of SQP statistics [B, 8]."""
         h = self.h
         rc = h.lib.plm_mpc_step(h._h, _ptr(self.x), _ptr(self.p), _ptr(self._t0), self.k * self._dt_min, self._gait, self._period,
-                                self._dts, float(self.ocp.mass), int(self.warm_start and self.k > 0), int(self.update_tau_prev), self.ocp.batch,
+                                self._dts, 2 if self.k == 0 else int(self.warm_start), int(self.update_tau_prev), self.ocp.batch,
                                 _ptr(self.x_new), _ptr(self.stats), h._stream())
         h._rc(rc)
         self.x, self.x_new = self.x_new, self.x

@@ -222,6 +222,11 @@ class OCP:
                 x[:, o + lead + self.nf:o + self.nu_opt[i]] = u_prev[:, lead + self.nf:]
         self._x0 = x
 
+    def set_initial(self, x):
+        """opti.set_initial(opti.x, x): stacked starting point [batch, n] (or [n]) of the following solve() calls."""
+        x = np.asarray(x, dtype=np.float64)
+        self._x0 = np.broadcast_to(x, (self.batch, self.n)).copy()
+
     # ------------------------------------------------------------------ solver
     def _p_device(self):
         if self._p_dirty or getattr(self, "_p_dev", None) is None:
@@ -254,26 +259,25 @@ class OCP:
         """One SQP iteration for every instance: sqp_data -> OSQP update/solve -> Armijo (optimization/ocp.py:375-422).
 
         Returns the stacked solution [batch, n] (the reference returns nothing): a view of a pinned host buffer that the
-        call after next reuses; ``DX_prev`` / ``U_prev`` are views of the same buffer."""
+        call after next reuses; ``DX_prev`` / ``U_prev`` are views of the same buffer (valid until the call after next),
+        the solution history (``q_sol``, ``a_sol``, ``forces_sol``, ...) holds copies.  The starting point is
+        ``opti.initial()``: only ``warm_start()`` moves it."""
         if self.solver != "osqp":
             raise ValueError(f"Solver {self.solver} not supported")
         h = self.handle
+        # opti.initial(): the point of the last warm_start() call, else DX = 0, U = u_des (optimization/ocp.py:159-163,
+        # 193,379); solve() itself never moves it (the reference's retract_stacked_sol does not call set_initial)
         current_x = self.initial_guess() if self._x0 is None else self._x0
         start_time = time.time()
         if getattr(self, "_pin_x", None) is None:     # pinned staging buffers for the host <-> device copies
             self._pin_x = torch.empty(self.batch, self.n, dtype=torch.float64).pin_memory()
-            # two result buffers, used alternately: the solution returned by one call stays valid (and pinned and
-            # contiguous, so it is the next call's input without a staging copy) while the next call writes the other
+            # two result buffers, used alternately: the solution returned by one call (and the DX_prev / U_prev views
+            # of it) stays valid while the next call writes the other one
             self._pin_out = [torch.empty(self.batch, self.n, dtype=torch.float64).pin_memory() for _ in range(2)]
             self._pin_stats = torch.empty(self.batch, 8, dtype=torch.float64).pin_memory()
             self._pin_sel = 0
-        prev = self._pin_out[self._pin_sel ^ 1]
-        if isinstance(current_x, np.ndarray) and current_x.shape == (self.batch, self.n) and np.shares_memory(current_x, prev.numpy()) \
-                and current_x.ctypes.data == prev.data_ptr():
-            xd = prev.to(h.device, non_blocking=True)       # previous solution: already in pinned memory
-        else:
-            self._pin_x.numpy()[:] = current_x
-            xd = self._pin_x.to(h.device, non_blocking=True)
+        self._pin_x.numpy()[:] = current_x
+        xd = self._pin_x.to(h.device, non_blocking=True)
         pd = self._p_device()
         x_new, stats = h.sqp_step(xd, pd)
         pin_out = self._pin_out[self._pin_sel]
@@ -284,7 +288,6 @@ class OCP:
         sol_x = pin_out.numpy()
         self.stats = self._pin_stats.numpy().copy()
         self.solve_time = time.time() - start_time
-        self._x0 = sol_x
         self.retract_stacked_sol(sol_x, retract_all)
         return sol_x
 
@@ -307,7 +310,7 @@ class OCP:
             o = h.x_off[i]
             dx_sol = sol_x[:, o:o + self.ndx_opt]
             u_sol = sol_x[:, o + self.ndx_opt:o + self.ndx_opt + self.nu_opt[i]]
-            self.DX_prev.append(dx_sol)      # views of the solution (a fresh buffer per solve)
+            self.DX_prev.append(dx_sol)      # views of the solution buffer (reused by the call after next)
             self.U_prev.append(u_sol)
             if i == 0 or retract_all:
                 self._append_solution(self.state_integrate(x_init, dx_sol), u_sol)
@@ -323,8 +326,8 @@ class OCP:
     def _append_solution(self, x_sol, u_sol):
         self._append_state(x_sol)
         lead = self._lead()
-        self.a_sol.append(u_sol[:, :lead])
-        self.forces_sol.append(u_sol[:, lead:lead + self.nf])
+        self.a_sol.append(u_sol[:, :lead].copy())      # copies, as the reference's np.array(...) (history outlives the buffer)
+        self.forces_sol.append(u_sol[:, lead:lead + self.nf].copy())
 
     # violation metrics of optimization/ocp.py:482-496 (host versions, for users of g_data)
     @staticmethod

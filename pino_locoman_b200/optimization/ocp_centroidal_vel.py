@@ -34,5 +34,5 @@ class OCPCentroidalVel(OCP):
 
     def _append_solution(self, x_sol, u_sol):
         self._append_state(x_sol)
-        self.v_sol.append(u_sol[:, :self.nv_opt])
-        self.forces_sol.append(u_sol[:, self.f_idx:])
+        self.v_sol.append(u_sol[:, :self.nv_opt].copy())
+        self.forces_sol.append(u_sol[:, self.f_idx:].copy())

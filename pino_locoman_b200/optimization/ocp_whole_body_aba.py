@@ -22,5 +22,5 @@ class OCPWholeBodyABA(OCP):
 
     def _append_solution(self, x_sol, u_sol):
         self._append_state(x_sol)
-        self.tau_sol.append(u_sol[:, :self.nj])
-        self.forces_sol.append(u_sol[:, self.f_idx:])
+        self.tau_sol.append(u_sol[:, :self.nj].copy())
+        self.forces_sol.append(u_sol[:, self.f_idx:].copy())

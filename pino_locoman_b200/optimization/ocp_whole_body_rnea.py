@@ -38,4 +38,4 @@ class OCPWholeBodyRNEA(OCP):
 
     def _append_solution(self, x_sol, u_sol):
         super()._append_solution(x_sol, u_sol)
-        self.tau_sol.append(u_sol[:, self.tau_idx:])
+        self.tau_sol.append(u_sol[:, self.tau_idx:].copy())

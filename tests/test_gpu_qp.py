@@ -23,7 +23,7 @@ def _nominal_problem(o, rng, k):
 
 @pytest.mark.parametrize("variant", ["throughput", "latency"])
 @pytest.mark.parametrize("rn,kind,N", [("b2", "whole_body_rnea", 6), ("b2g", "whole_body_rnea", 5), ("b2", "centroidal_acc", 6),
-                                       ("go2", "centroidal_vel", 5), ("b2g", "whole_body_aba", 4)])
+                                       ("go2", "centroidal_vel", 5), ("b2g", "whole_body_aba", 4), ("b2", "whole_body_acc", 5)])
 def test_qp_matches_oracle_osqp(robots, rn, kind, N, variant, monkeypatch):
     """Both instantiations of the ADMM kernel: the 256-thread one used for large batches and the 512-thread one that
     small batches get (the library reads PLM_ADMM_LATENCY_MAX_BATCH at every solve)."""

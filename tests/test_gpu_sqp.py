@@ -45,7 +45,7 @@ def test_line_search_matches_oracle(robots, rn, kind, N):
 
 
 @pytest.mark.parametrize("rn,kind,N,iters", [("b2", "whole_body_rnea", 6, 4), ("b2g", "whole_body_rnea", 5, 3), ("b2", "centroidal_acc", 6, 3),
-                                             ("go2", "centroidal_vel", 5, 3), ("b2g", "whole_body_aba", 4, 3)])
+                                             ("go2", "centroidal_vel", 5, 3), ("b2g", "whole_body_aba", 4, 3), ("b2", "whole_body_acc", 5, 3)])
 def test_sqp_iterations_match_oracle(robots, rn, kind, N, iters):
     """Several SQP iterations (sqp_data -> OSQP -> Armijo) with warm-started QP iterates; primal variables and cost
     within the north-star tolerance 1e-6 of the reference path restated by the oracle."""
@@ -108,3 +108,26 @@ def test_full_size_sqp_step_is_deterministic(robots, monkeypatch):
     assert torch.equal(x1, x2) and torch.equal(s1, s2)
     # every instance ran the ADMM loop at least to its first termination check
     assert (s1[:, 0] >= 25).all()
+
+
+def test_lazy_qp_setup_covers_a_growing_batch(robots):
+    """plm_sqp_step sets up the OSQP state (zero iterates, setup-time row scaling) lazily: a later call with a larger
+    batch must set up the additional instances too, without touching the warm-started iterates of the earlier ones."""
+    from pino_locoman_b200.handle import Handle
+    prod, ora = robots
+    rng = np.random.default_rng(5)
+    o = OracleOCP(ora["b2"], "centroidal_acc", 5)
+    probs = [_nominal_problem(o, rng, k) for k in (0, 11, 23, 37)]
+    x = torch.tensor(np.stack([q[0] for q in probs]), device="cuda")
+    p = torch.tensor(np.stack([q[1] for q in probs]), device="cuda")
+    full = Handle(prod["b2"], "centroidal_acc", 5, max_batch=4)
+    xf1, sf1 = full.sqp_step(x, p)
+    xf2, sf2 = full.sqp_step(xf1, p)
+    grow = Handle(prod["b2"], "centroidal_acc", 5, max_batch=4)
+    xg1, sg1 = grow.sqp_step(x[:2].contiguous(), p[:2].contiguous())
+    assert torch.equal(xg1, xf1[:2]) and torch.equal(sg1, sf1[:2])
+    # batch grows to 4: instances 0, 1 continue warm-started (second iteration), instances 2, 3 run their first one
+    xin = torch.cat([xg1, x[2:]])
+    xg2, sg2 = grow.sqp_step(xin, p)
+    assert torch.equal(xg2[:2], xf2[:2]) and torch.equal(sg2[:2], sf2[:2])
+    assert torch.equal(xg2[2:], xf1[2:]) and torch.equal(sg2[2:], sf1[2:])
