@@ -167,36 +167,68 @@ def cpu_oracle_timing(x, p, n_inst, iters, procs):
     return wall, t_eval, t_all
 
 
+def oracle_synthetic_inputs(n_inst, seed):
+    """Synthetic instances of the bench workload built with the oracle only (SURVEY 8(d) distributions): the reference arm
+    must not map the product library."""
+    from emu_util import random_problem
+    from oracle.model import OracleRobot
+    from oracle.ocp import OracleOCP
+    rng = np.random.default_rng(seed)
+    o = OracleOCP(OracleRobot(ROBOT), DYNAMICS, NODES)
+    xs, ps = zip(*[random_problem(o, rng) for _ in range(n_inst)])
+    return np.stack(xs), np.stack(ps)
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port: casadi/pinocchio/OSQP are not installable here)."""
+    """--impl reference: the reference's CPU algorithm on all host cores.  casadi / pinocchio / OSQP are not installable
+    here or on the GPU box (profiles/probe_real_stack_r02.log), so what is timed is the restated algorithm: the compiled
+    C++ port (oracle/cport, -O3 -march=native, one process per core) when it is built, else the numpy oracle."""
     if rank != 0:
         return
-    from pino_locoman_b200 import OCP_ARGS
-    from pino_locoman_b200.optimization import make_ocp
-    from pino_locoman_b200.utils.robot import B2G
-    robot = B2G()
-    robot.set_gait_sequence("trot", 0.8)
     procs = os.cpu_count() or 1
     n_inst = max(procs, 2)
-    ocp = make_ocp(dynamics=DYNAMICS, default_args=OCP_ARGS[DYNAMICS], robot=robot, nodes=NODES, solver="osqp", batch=n_inst, device="layout")
-    x, p = synthetic_inputs(robot, ocp, n_inst, 0)
+    x, p = oracle_synthetic_inputs(n_inst, 1234)
+    cport = _load_cport()
     walls = []
     for step in range(args.warmup + args.steps):
-        _, _, t_all = cpu_oracle_timing(x, p, n_inst, 1, procs)
+        if cport is not None:
+            t_all = cport_timing(x, p, n_inst, procs)[0]
+        else:
+            t_all = cpu_oracle_timing(x, p, n_inst, 1, procs)[2] / procs
         if step >= args.warmup:
-            walls.append(t_all / n_inst)      # seconds per SQP iteration on one core; `procs` cores run concurrently
-    ms = 1e3 * float(np.mean(walls)) * n_inst / procs
+            walls.append(t_all)      # wall seconds for n_inst SQP iterations on `procs` cores
+    ms = 1e3 * float(np.mean(walls))
     value = n_inst / (ms / 1e3)
+    kind = "port (C++)" if cport is not None else "port"
     line = {"impl": "reference", "metric": "sqp_iters_per_s", "value": value, "unit": "SQP iters/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{ROBOT} {DYNAMICS} trot N={NODES}, SQP iteration (sqp_data + OSQP + Armijo)", "robot": ROBOT,
-                       "dynamics": DYNAMICS, "nodes": NODES, "instances_per_step": n_inst},
-            "cpu_baseline": {"value": value, "unit": "SQP iters/s", "cores": procs, "kind": "port",
-                             "sample": f"{n_inst} instances x 1 SQP iteration per step, one process per core, numpy oracle "
-                                       "(restated reference algorithm; casadi/pinocchio/osqp not installable)"},
+                       "dynamics": DYNAMICS, "nodes": NODES, "instances_per_step": n_inst,
+                       "same_config": False,
+                       "note": "bounded sample: one instance per host core per step (the GPU arm runs 8192 per GPU); a restated "
+                               "port, not the real casadi/pinocchio/OSQP stack"},
+            "cpu_baseline": {"value": value, "unit": "SQP iters/s", "cores": procs, "kind": kind,
+                             "sample": f"{n_inst} instances x 1 SQP iteration per step, one process per core, "
+                                       + ("C++ port of the reference algorithm (-O3 -march=native)" if cport is not None else "numpy oracle")
+                                       + " (restated reference algorithm; casadi/pinocchio/osqp not installable)"},
             "e2e": {"value": value, "unit": "SQP iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def _load_cport():
+    """The compiled CPU port (oracle/cport), or None when it has not been built."""
+    try:
+        from oracle.cport import load
+        return load()
+    except Exception:
+        return None
+
+
+def cport_timing(x, p, n_inst, procs):
+    """n_inst SQP iterations (one per instance) with the C++ port on `procs` processes; (wall seconds, node-eval seconds)."""
+    from oracle.cport import time_sqp
+    return time_sqp(ROBOT, DYNAMICS, NODES, x, p, procs)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -297,6 +329,26 @@ def main():
     ms_eval = e0.elapsed_time(e1) / reps
     launches += reps
     del g, J
+    # ---- north-star operating point: 512 instances per GPU (4096 on 8 GPUs), one full SQP iteration, latency
+    Bt = min(512, B)
+    xt, pt = x[:Bt].clone(), p[:Bt].contiguous()
+    xt_new, st_t = torch.empty_like(xt), torch.empty(Bt, 8, dtype=torch.float64, device=dev)
+    t_ms, t_phase, t_iters = [], [], []
+    for k in range(4):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        h.sqp_step(xt, pt, xt_new, st_t)
+        a1.record()
+        torch.cuda.synchronize()
+        t_ms.append(a0.elapsed_time(a1))
+        t_phase.append(h.last_phase_ms())
+        t_iters.append(float(st_t[:, 0].mean()))
+        xt, xt_new = xt_new, xt
+    target_ms = float(np.median(t_ms[1:]))
+    target_phase = [float(v) for v in np.median(np.array(t_phase[1:]), axis=0)]
+    target_iters = float(np.mean(t_iters[1:]))
+    launches += h.launch_count() - launches0 - launches
+    del xt, pt, xt_new, st_t
     # ---- closed loop: device-resident receding-horizon steps of every instance (gait update, warm
     # start, one SQP iteration, state advance), nominal start states, extra key
     from pino_locoman_b200.mpc import BatchedMPC
@@ -433,6 +485,9 @@ def main():
     ms_admm = phase[2] / K
     bytes_admm = B * Kavg * (8.0 * nnzF + 8.0 * (3 * n + 4 * m))       # K (8 nnz(F) + 8 (3n + 4m)) per instance
     ach_admm = bytes_admm / (ms_admm / 1e3) / 1e9
+    # the same with the minimal factor (packed S_i^-1 only; the stored factor also holds the back-substitution blocks B_i)
+    nnzF_min = sum((h.x_off[i + 1] - h.x_off[i]) * (h.x_off[i + 1] - h.x_off[i] + 1) // 2 for i in range(NODES)) + h.ndx * (h.ndx + 1) // 2
+    ach_admm_min = B * Kavg * (8.0 * nnzF_min + 8.0 * (3 * n + 4 * m)) / (ms_admm / 1e3) / 1e9
     ach_eval = B * NODES * BYTES_NODE_EVAL / (ms_eval / 1e3) / 1e9
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -459,7 +514,8 @@ def main():
         "qp": {"admm_iters_avg": Kavg, "line_search_trials_avg": Tavg, "accepted_frac": float(np.mean(accepted)), "nnz_F": nnzF},
         "roofline": {"kernel": "qp_admm_kernel", "bound": "hbm", "achieved": ach_admm, "peak": peak, "unit": "GB/s",
                      "frac": ach_admm / peak, "traffic": traffic.get("qp_admm_kernel"), "peak_source": peak_src,
-                     "algorithmic_bytes": bytes_admm},
+                     "algorithmic_bytes": bytes_admm, "nnz_F_stored": nnzF, "nnz_F_minimal": nnzF_min,
+                     "frac_minimal_factor": ach_admm_min / peak, "ms_per_step_kernel": ms_admm},
         "roofline_node_eval": {"kernel": "node_eval_kernel", "bound": "hbm", "achieved": ach_eval, "peak": peak, "unit": "GB/s",
                                "frac": ach_eval / peak, "traffic": traffic.get("node_eval_kernel"),
                                "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval,
@@ -468,6 +524,13 @@ def main():
                 "mpc_steps_per_s": B / (ms_mpc / 1e3), "ms_per_step": ms_mpc, "admm_iters_avg": mpc_iters},
         "e2e": {"value": total_inst / (ms_e2e / 1e3), "unit": "SQP iters/s", "h2d_bytes_per_step": int(B * (n + h.np) * 8),
                 "d2h_bytes_per_step": int(B * (n + 8) * 8)},
+        "target": {"workload": f"north-star operating point: {Bt} {ROBOT} {DYNAMICS} N={NODES} instances per GPU (4096 on 8 GPUs), one full SQP "
+                               "iteration; the north-star asks for < 1 ms",
+                   "instances_per_gpu": Bt, "ms_per_sqp_iter": target_ms,
+                   "phase_ms": dict(zip(("eval", "qp_update", "qp_solve", "line_search"), target_phase)), "admm_iters_avg": target_iters,
+                   "hbm_floor_ms": Bt * target_iters * (8.0 * nnzF + 8.0 * (3 * n + 4 * m)) / (peak * 1e9) * 1e3,
+                   "hbm_floor_note": "instances x ADMM iterations x (8 nnz(F) + 8 (3n + 4m)) bytes / measured HBM peak: the factor of an "
+                                     "instance (1.36 MB) is re-read every iteration and 512 of them (0.7 GB) do not fit the 126 MB L2"},
         "single_instance": {"workload": "b2 whole_body_rnea trot N=20, 1 instance (BASELINE configs[1])", "ms_per_sqp_iter": single_ms,
                             "phase_ms": dict(zip(("eval", "qp_update", "qp_solve", "line_search"), single_phase))},
         "other_configs": other,

@@ -67,6 +67,12 @@ typedef struct {
   double osqp_rho, osqp_sigma, osqp_alpha;            /* 2e-2, 1e-6, 1.4 */
   double osqp_eps_abs, osqp_eps_rel;                  /* 1e-3, 1e-3 */
   double osqp_eps_prim_inf, osqp_eps_dual_inf;        /* 1e-4, 1e-4 */
+  /* include_base (ocp_args.py:3-11; centroidal_vel / centroidal_acc / whole_body_acc): 1 = base velocity / acceleration
+   * among the inputs + the 6 dynamics-gap rows (the reference's OCP_ARGS default); 0 = inputs without the base part,
+   * v_b = base_vel_dynamics(h, q, v_j) / a_b = base_acc_dynamics(q, v, a_j, forces) substituted and no gap rows
+   * (ocp_centroidal_vel.py:19-23,104-120; ocp_centroidal_acc.py:19-23,108-140; ocp_whole_body_acc.py:20-24,109-141). */
+  int32_t include_base;
+  int32_t reserved;                                   /* 0 */
 } plm_ocp_desc;
 
 typedef struct {

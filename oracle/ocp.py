@@ -31,8 +31,11 @@ class OracleOCP:
             raise ValueError(f"Unknown dynamics type: {dynamics}")  # ocp_factory.py:17-18
         args = dict(OCP_ARGS[dynamics])
         args.update(kwargs)
-        if args.get("include_base") is False or args.get("include_acc") is False:
-            raise NotImplementedError("include_base=False / include_acc=False variants (SURVEY 8f rank 2)")
+        # inputs without the base part (v_b / a_b follow from the dynamics, e.g.
+        # ocp_centroidal_vel.py:19-23,104-120) and whole_body_rnea without accelerations (finite differences,
+        # ocp_whole_body_rnea.py:21-25,156,183-191)
+        self.include_base = bool(args.get("include_base", True))
+        self.include_acc = bool(args.get("include_acc", True))
         self.robot, self.kind, self.nodes = robot, dynamics, nodes
         self.model = robot.model
         self.gait = GaitSequence(gait_type, gait_period)
@@ -47,11 +50,18 @@ class OracleOCP:
         self.dyn = cls(self.model, self.mass, self.foot_frames, robot.base_frame)
         self.tau_nodes = args.get("tau_nodes", 0) if dynamics == "whole_body_rnea" else 0
         # --- setup_variables of each ocp_*.py
+        self.n_lead = nv        # leading input block: v / a (nv), without the base part nj, tau_j (nj), nothing
+        if dynamics in ("centroidal_vel", "centroidal_acc", "whole_body_acc") and not self.include_base:
+            self.n_lead = nj
+        if dynamics == "whole_body_aba":
+            self.n_lead = nj
+        if dynamics == "whole_body_rnea" and not self.include_acc:
+            self.n_lead = 0
         if dynamics == "centroidal_vel":
             self.nx, self.ndx = 6 + nq, 6 + nv
             self.x_nom = np.concatenate((np.zeros(6), robot.q0))
-            self.nu = [nv + nf] * N
-            self.f_idx = nv
+            self.nu = [self.n_lead + nf] * N
+            self.f_idx = self.n_lead
         else:
             self.nx, self.ndx = nq + nv, 2 * nv
             self.x_nom = np.concatenate((robot.q0, np.zeros(nv)))
@@ -59,12 +69,13 @@ class OracleOCP:
                 self.nu = [nj + nf] * N
                 self.f_idx = nj
             elif dynamics == "whole_body_rnea":
-                self.nu = [nv + nf + nj] * self.tau_nodes + [nv + nf] * (N - self.tau_nodes)
-                self.f_idx = nv
-                self.tau_idx = nv + nf
+                na = self.n_lead
+                self.nu = [na + nf + nj] * self.tau_nodes + [na + nf] * (N - self.tau_nodes)
+                self.f_idx = na
+                self.tau_idx = na + nf
             else:
-                self.nu = [nv + nf] * N
-                self.f_idx = nv
+                self.nu = [self.n_lead + nf] * N
+                self.f_idx = self.n_lead
         self.x_off = np.concatenate(([0], np.cumsum([self.ndx + u for u in self.nu])))  # stage offsets
         self.n = int(self.x_off[-1]) + self.ndx
         # --- parameter layout, creation order of ocp.py:54-69 (+ rnea :88-89)
@@ -100,16 +111,16 @@ class OracleOCP:
         Q_vel = np.concatenate(([2000, 2000, 1000, 1000, 1000, 2000], [1] * nj))
         if self.kind == "centroidal_vel":   # ocp_centroidal_vel.py:25-49
             Q = np.concatenate(([1000] * 6, Q_base, Q_joint))
-            R = np.concatenate(([1] * self.nv, [1e-3] * nf))
+            R = np.concatenate(([1] * self.n_lead, [1e-3] * nf))
         else:
             Q = np.concatenate((Q_base, Q_joint, Q_vel))
             if self.kind == "whole_body_aba":   # ocp_whole_body_aba.py:44-47
                 R = np.concatenate(([1e-3] * nj, [1e-3] * nf))
             elif self.kind == "whole_body_rnea":  # ocp_whole_body_rnea.py:50-59
-                R = np.concatenate(([1e-3] * self.nv, [1e-3] * nf, [1e-4] * nj))
+                R = np.concatenate(([1e-3] * self.n_lead, [1e-3] * nf, [1e-4] * nj))
                 self.params["W_diag"][:] = 0
             else:
-                R = np.concatenate(([1e-3] * self.nv, [1e-3] * nf))
+                R = np.concatenate(([1e-3] * self.n_lead, [1e-3] * nf))
         self.params["Q_diag"][:] = Q
         self.params["R_diag"][:] = R
 
@@ -168,8 +179,7 @@ class OracleOCP:
         f_des = np.zeros(self.nf)
         f_des[2] = f_des[5] = 0.8 * fg / nc
         f_des[8] = f_des[11] = 1.2 * fg / nc
-        n_lead = self.nj if self.kind == "whole_body_aba" else self.nv
-        u_des = np.concatenate((np.zeros(n_lead), f_des))
+        u_des = np.concatenate((np.zeros(self.n_lead), f_des))
         if self.kind == "whole_body_rnea":
             u_des = np.concatenate((u_des, np.zeros(self.nj)))
         return dx_des, u_des, f_des
@@ -238,13 +248,13 @@ class OracleOCP:
         nv, nj = self.nv, self.nj
         k = self.kind
         if k == "centroidal_vel":
-            rows = 6 + nv + 6
+            rows = 6 + nv + (6 if self.include_base else 0)
         elif k == "whole_body_aba":
             rows = 2 * nv
         elif k == "whole_body_rnea":
-            rows = 2 * nv + 6 + (2 * nj if i < self.tau_nodes else 0)
+            rows = (2 * nv if self.include_acc else nv) + 6 + (2 * nj if i < self.tau_nodes else 0)
         else:
-            rows = 2 * nv + 6
+            rows = 2 * nv + (6 if self.include_base else 0)
         skip = i == 0 and self.first_node_skip
         rows += 4 * (5 + (0 if skip else 3))
         if self.ext_force_frame:
@@ -271,21 +281,33 @@ class OracleOCP:
         forces = u[..., self.f_idx:self.f_idx + nf]
         if self.kind == "centroidal_vel":   # ocp_centroidal_vel.py:85-107
             h, q = x[..., :6], x[..., 6:]
-            v = u[..., :nv]
+            if self.include_base:
+                v = u[..., :nv]
+            else:   # ocp_centroidal_vel.py:109-120: base velocity from the momentum
+                v_j = u[..., :nj]
+                v = np.concatenate((self.dyn.base_vel_dynamics()(h, q, v_j), v_j), -1)
             h_dot = self.dyn.com_dynamics(self.ext_force_frame)(q, forces)
             eq(dx_next[..., :6] - (dx[..., :6] + h_dot * dt))
             eq(dx_next[..., 6:] - (dx[..., 6:] + v * dt))
-            eq(self.dyn.dynamics_gaps()(h, q, v))
+            if self.include_base:
+                eq(self.dyn.dynamics_gaps()(h, q, v))
         else:
             q, v = x[..., :nq], x[..., nq:]
             dq, dv = dx[..., :nv], dx[..., nv:]
             if self.kind == "whole_body_aba":   # ocp_whole_body_aba.py:86-106
                 tau_j = u[..., :nj]
                 a = self.dyn.aba_dynamics(self.ext_force_frame)(q, v, tau_j, forces)
+            elif self.kind == "whole_body_rnea" and not self.include_acc:   # ocp_whole_body_rnea.py:183-191
+                v_next = self.dyn.state_integrate()(x_init, dx_next)[..., nq:]
+                a = (v_next - v) / dt
+            elif not self.include_base:   # ocp_centroidal_acc.py:129-140, ocp_whole_body_acc.py:130-141
+                a_j = u[..., :nj]
+                a = np.concatenate((self.dyn.base_acc_dynamics(self.ext_force_frame)(q, v, a_j, forces), a_j), -1)
             else:
                 a = u[..., :nv]
             eq(dx_next[..., :nv] - (dq + v * dt))
-            eq(dx_next[..., nv:] - (dv + a * dt))
+            if self.include_acc:
+                eq(dx_next[..., nv:] - (dv + a * dt))
             if self.kind == "whole_body_rnea":   # ocp_whole_body_rnea.py:160-171
                 tau = self.dyn.rnea_dynamics(self.ext_force_frame)(q, v, a, forces)
                 eq(tau[..., :6])
@@ -295,7 +317,7 @@ class OracleOCP:
                     g.append(tau_j)
                     lb.append(-self.robot.joint_torque_max)
                     ub.append(self.robot.joint_torque_max)
-            elif self.kind in ("whole_body_acc", "centroidal_acc"):
+            elif self.kind in ("whole_body_acc", "centroidal_acc") and self.include_base:
                 eq(self.dyn.dynamics_gaps(self.ext_force_frame)(q, v, a, forces))
 
         skip = i == 0 and self.first_node_skip

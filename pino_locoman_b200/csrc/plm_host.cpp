@@ -128,7 +128,10 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   L.nx = cvel ? 6 + nq : nq + nv;
   L.ndx = cvel ? 6 + nv : 2 * nv;
   const int ndx = L.ndx;
-  L.lead = (kind == PLM_WHOLE_BODY_ABA) ? nj : nv;
+  const bool nobase = !ocp.include_base && (kind == PLM_CENTROIDAL_VEL || kind == PLM_CENTROIDAL_ACC || kind == PLM_WHOLE_BODY_ACC);
+  L.nobase = nobase ? 1 : 0;
+  // leading input block: v / a (nv), tau_j (nj), or joint part only when the base part follows from the dynamics
+  L.lead = (kind == PLM_WHOLE_BODY_ABA || nobase) ? nj : nv;
   L.f_idx = L.lead;
   L.tau_idx = L.lead + nf;
   // stage offsets
@@ -150,8 +153,10 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   // local column helpers
   const int dq0 = cvel ? 6 : 0;           // dq block inside dx
   auto col_dq = [&](int c) { return dq0 + c; };
-  auto col_v = [&](int c, int nu_i) { (void)nu_i; return cvel ? ndx + c : nv + c; };   // dv (state) or U velocity
+  // dv (state) or U velocity; without base inputs the U block holds the joint part only (c >= 6)
+  auto col_v = [&](int c, int nu_i) { (void)nu_i; return cvel ? ndx + c - (nobase ? 6 : 0) : nv + c; };
   auto col_lead = [&](int c) { return ndx + c; };
+  auto col_leadj = [&](int c) { return ndx + c - (nobase ? 6 : 0); };   // acceleration column of velocity column c
   auto col_f = [&](int k, int t) { return ndx + L.f_idx + 3 * k + t; };
   auto col_tau = [&](int j) { return ndx + L.tau_idx + j; };
   auto col_next = [&](int c, int nu_i) { return ndx + nu_i + c; };
@@ -177,7 +182,8 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     T.row_int = T.row_dyn = T.row_tauj = T.row_taub = T.row_ext = T.row_arm = T.row_qj = T.row_vj = -1;
     const int nu_i = nu[i];
     // lut source offsets
-    const int sizes[PLM_SRC_COUNT] = {nv * nv, nv * nv, nv * nv, nv * nf, nfeet * 3 * nv, nfeet * 3 * nv, 3 * nv, 3 * nv, 6 * nv, 6 * nf};
+    const int sizes[PLM_SRC_COUNT] = {nv * nv, nv * nv, nv * nv, nv * nf, nfeet * 3 * nv, nfeet * 3 * nv, 3 * nv, 3 * nv, 6 * nv, 6 * nf,
+                                      36, nfeet * 3 * 6, 3 * 6};
     int lo = 0;
     for (int s = 0; s < PLM_SRC_COUNT; ++s) { T.src_off[s] = lo; lo += sizes[s]; }
     T.lut_size = lo;
@@ -197,16 +203,27 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       }
       for (int c = 0; c < nv; ++c) {  // dq_next - (dq + v dt)
         int row = rb.new_row();
-        rb.add(row, col_dq(c), 1, 1, 0);
-        rb.add(row, col_v(c, nu_i), 1, 2, 0);
+        if (nobase && c < 6) {
+          // v_b = A_b^-1 (m h - A_j v_j) (dynamics_centroidal_vel.py:73-89): dense in dh, dq and v_j; the -1 of dq_c is
+          // folded into the computed entry of column dq_c (c >= 3; the translation increments c < 3 have no other term)
+          for (int k = 0; k < 6; ++k) rb.add(row, k, 0, PLM_SRC_IH, c * 6 + k);
+          if (c < 3) rb.add(row, col_dq(c), 1, 1, 0);
+          for (int d = 3; d < nv; ++d) rb.add(row, col_dq(d), 0, PLM_SRC_TQ, c * nv + d);
+          for (int d = 6; d < nv; ++d) rb.add(row, col_v(d, nu_i), 0, PLM_SRC_TV, c * nv + d);
+        } else {
+          rb.add(row, col_dq(c), 1, 1, 0);
+          rb.add(row, col_v(c, nu_i), 1, 2, 0);
+        }
         rb.add(row, col_next(6 + c, nu_i), 1, 0, 0);
       }
-      T.row_dyn = (int)rb.rows.size();
-      for (int r = 0; r < 6; ++r) {   // A v - m h
-        int row = rb.new_row();
-        rb.add(row, r, 1, 3, 0);
-        for (int c = 3; c < nv; ++c) rb.add(row, col_dq(c), 0, PLM_SRC_TQ, r * nv + c);
-        for (int c = 0; c < nv; ++c) rb.add(row, col_v(c, nu_i), 0, PLM_SRC_TV, r * nv + c);
+      if (!nobase) {
+        T.row_dyn = (int)rb.rows.size();
+        for (int r = 0; r < 6; ++r) {   // A v - m h
+          int row = rb.new_row();
+          rb.add(row, r, 1, 3, 0);
+          for (int c = 3; c < nv; ++c) rb.add(row, col_dq(c), 0, PLM_SRC_TQ, r * nv + c);
+          for (int c = 0; c < nv; ++c) rb.add(row, col_v(c, nu_i), 0, PLM_SRC_TV, r * nv + c);
+        }
       }
     } else {
       for (int c = 0; c < nv; ++c) {  // dq_next - (dq + v dt)
@@ -223,13 +240,21 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
           for (int j = 0; j < nj; ++j) rb.add(row, col_lead(j), 0, PLM_SRC_TA, c * nv + j);
           for (int k = 0; k < M.ncontact; ++k)
             for (int tt = 0; tt < 3; ++tt) rb.add(row, col_f(k, tt), 0, PLM_SRC_TF, c * nf + 3 * k + tt);
+        } else if (nobase && c < 6) {
+          // a_b = base_acc_dynamics(q, v, a_j, forces) (dynamics_centroidal_acc.py:43-82, dynamics_whole_body_acc.py:43-83):
+          // dense in dq, dv, a_j and the forces; the -1 of dv_c is folded into the computed entry of column dv_c
+          for (int d = 3; d < nv; ++d) rb.add(row, col_dq(d), 0, PLM_SRC_TQ, c * nv + d);
+          for (int d = 0; d < nv; ++d) rb.add(row, col_v(d, nu_i), 0, PLM_SRC_TV, c * nv + d);
+          for (int d = 6; d < nv; ++d) rb.add(row, col_leadj(d), 0, PLM_SRC_TA, c * nv + d);
+          for (int k = 0; k < M.ncontact; ++k)
+            for (int tt = 0; tt < 3; ++tt) rb.add(row, col_f(k, tt), 0, PLM_SRC_TF, c * nf + 3 * k + tt);
         } else {
           rb.add(row, col_v(c, nu_i), 1, 1, 0);
-          rb.add(row, col_lead(c), 1, 2, 0);
+          rb.add(row, col_leadj(c), 1, 2, 0);
         }
         rb.add(row, col_next(nv + c, nu_i), 1, 0, 0);
       }
-      if (kind == PLM_WHOLE_BODY_RNEA || kind == PLM_WHOLE_BODY_ACC || kind == PLM_CENTROIDAL_ACC) {
+      if (!nobase && (kind == PLM_WHOLE_BODY_RNEA || kind == PLM_WHOLE_BODY_ACC || kind == PLM_CENTROIDAL_ACC)) {
         T.row_dyn = (int)rb.rows.size();
         const bool centroidal = kind == PLM_CENTROIDAL_ACC;
         const int nrow_t = 6 + (jr ? nj : 0);
@@ -267,6 +292,12 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       if (!skip) {
         for (int r = 0; r < 3; ++r) {   // c v_xy = 0 ; c v_z + (1-c)(v_z - v_des) = 0
           row = rb.new_row();
+          if (cvel && nobase) {   // the foot velocity depends on v_b(dh, dq, v_j): every column
+            for (int h6 = 0; h6 < 6; ++h6) rb.add(row, h6, 0, PLM_SRC_FH, (k * 3 + r) * 6 + h6);
+            for (int c = 3; c < nv; ++c) rb.add(row, col_dq(c), 0, PLM_SRC_FQ, (k * 3 + r) * nv + c);
+            for (int c = 6; c < nv; ++c) rb.add(row, col_v(c, nu_i), 0, PLM_SRC_FV, (k * 3 + r) * nv + c);
+            continue;
+          }
           for (int c = 0; c < nv; ++c) {
             if (!((M.col_contacts[c] >> k) & 1u)) continue;
             if (q_cols_ok(c)) rb.add(row, col_dq(c), 0, PLM_SRC_FQ, (k * 3 + r) * nv + c);
@@ -286,6 +317,12 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
         T.row_arm = (int)rb.rows.size();
         for (int r = 0; r < 3; ++r) {
           int row = rb.new_row();
+          if (cvel && nobase && r == 2) {   // world z of the frame velocity: depends on v_b(dh, dq, v_j)
+            for (int h6 = 0; h6 < 6; ++h6) rb.add(row, h6, 0, PLM_SRC_AH, r * 6 + h6);
+            for (int c = 3; c < nv; ++c) rb.add(row, col_dq(c), 0, PLM_SRC_AQ, r * nv + c);
+            for (int c = 6; c < nv; ++c) rb.add(row, col_v(c, nu_i), 0, PLM_SRC_AV, r * nv + c);
+            continue;
+          }
           for (int c = 0; c < nv; ++c) {
             if (!((M.col_arm >> c) & 1u)) continue;
             if (r < 2 && M.col_body[c] == 0) continue;

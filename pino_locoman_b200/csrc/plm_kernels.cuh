@@ -19,7 +19,7 @@ struct TrialArgs {
 };
 
 // One warp per (instance, node).  Shared memory: [PlmModel | PlmLayout | per-warp NodeWs + row/J staging].
-template <int KIND>
+template <int KIND, bool NOBASE>
 __global__ void __launch_bounds__(PLM_NODE_WARPS * 32, 2)
 node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* __restrict__ p, int batch,
                  double* __restrict__ g, double* __restrict__ Jv, int want_jac, int ws_doubles, TrialArgs tr) {
@@ -72,7 +72,7 @@ node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* _
   A.want_jac = want_jac;
   WarpExec ex;
   ex.lane = lane;
-  node_eval_body<KIND>(ex, ws, A);
+  node_eval_body<KIND, NOBASE>(ex, ws, A);
   const PlmNodeType& T = *A.T;
   if (tr.part) {
     // constraint-violation partials of this node: sum of squares and max of [max(0, lbg-g); max(0, g-ubg)]

@@ -5,21 +5,22 @@
 
 using namespace plm;
 
-template <int KIND>
+template <int KIND, bool NOBASE>
 static int setup_one(plm_handle* h) {
-  cudaError_t e = cudaFuncSetAttribute(node_eval_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per function, shared by all handles
+  cudaError_t e = cudaFuncSetAttribute(node_eval_kernel<KIND, NOBASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per function, shared by all handles
   if (e != cudaSuccess) { h->error = std::string("node kernel shared memory: ") + cudaGetErrorString(e); return 6; }
   return 0;
 }
 
 int plm_setup_node_kernels(plm_handle* h) {
   if (h->node_smem > 227 * 1024) { h->error = "node workspace exceeds shared memory"; return 6; }
+  const bool nb = h->host.layout.nobase != 0;
   switch (h->host.layout.dynamics) {
-    case PLM_CENTROIDAL_VEL: return setup_one<PLM_CENTROIDAL_VEL>(h);
-    case PLM_CENTROIDAL_ACC: return setup_one<PLM_CENTROIDAL_ACC>(h);
-    case PLM_WHOLE_BODY_ACC: return setup_one<PLM_WHOLE_BODY_ACC>(h);
-    case PLM_WHOLE_BODY_ABA: return setup_one<PLM_WHOLE_BODY_ABA>(h);
-    default: return setup_one<PLM_WHOLE_BODY_RNEA>(h);
+    case PLM_CENTROIDAL_VEL: return nb ? setup_one<PLM_CENTROIDAL_VEL, true>(h) : setup_one<PLM_CENTROIDAL_VEL, false>(h);
+    case PLM_CENTROIDAL_ACC: return nb ? setup_one<PLM_CENTROIDAL_ACC, true>(h) : setup_one<PLM_CENTROIDAL_ACC, false>(h);
+    case PLM_WHOLE_BODY_ACC: return nb ? setup_one<PLM_WHOLE_BODY_ACC, true>(h) : setup_one<PLM_WHOLE_BODY_ACC, false>(h);
+    case PLM_WHOLE_BODY_ABA: return setup_one<PLM_WHOLE_BODY_ABA, false>(h);
+    default: return setup_one<PLM_WHOLE_BODY_RNEA, false>(h);
   }
 }
 
@@ -36,13 +37,16 @@ int plm_launch_node_trials(plm_handle* h, const double* x, const double* p, int 
   const long long items = (long long)batch * L.nodes * (tr.part ? tr.ntrial : 1);
   const int blocks = (int)((items + h->node_warps - 1) / h->node_warps);
   const dim3 grid(blocks), block(h->node_warps * 32);
+#define PLM_NODE_LAUNCH(KIND, NB) node_eval_kernel<KIND, NB><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles, tr)
+  const bool nb = L.nobase != 0;
   switch (L.dynamics) {
-    case PLM_CENTROIDAL_VEL: node_eval_kernel<PLM_CENTROIDAL_VEL><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles, tr); break;
-    case PLM_CENTROIDAL_ACC: node_eval_kernel<PLM_CENTROIDAL_ACC><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles, tr); break;
-    case PLM_WHOLE_BODY_ACC: node_eval_kernel<PLM_WHOLE_BODY_ACC><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles, tr); break;
-    case PLM_WHOLE_BODY_ABA: node_eval_kernel<PLM_WHOLE_BODY_ABA><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles, tr); break;
-    default: node_eval_kernel<PLM_WHOLE_BODY_RNEA><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles, tr); break;
+    case PLM_CENTROIDAL_VEL: if (nb) PLM_NODE_LAUNCH(PLM_CENTROIDAL_VEL, true); else PLM_NODE_LAUNCH(PLM_CENTROIDAL_VEL, false); break;
+    case PLM_CENTROIDAL_ACC: if (nb) PLM_NODE_LAUNCH(PLM_CENTROIDAL_ACC, true); else PLM_NODE_LAUNCH(PLM_CENTROIDAL_ACC, false); break;
+    case PLM_WHOLE_BODY_ACC: if (nb) PLM_NODE_LAUNCH(PLM_WHOLE_BODY_ACC, true); else PLM_NODE_LAUNCH(PLM_WHOLE_BODY_ACC, false); break;
+    case PLM_WHOLE_BODY_ABA: PLM_NODE_LAUNCH(PLM_WHOLE_BODY_ABA, false); break;
+    default: PLM_NODE_LAUNCH(PLM_WHOLE_BODY_RNEA, false); break;
   }
+#undef PLM_NODE_LAUNCH
   PLM_LAUNCH_CHECK(h);
   return 0;
 }

@@ -50,7 +50,14 @@ struct NodeWs {
   double* J;     // node block of the Jacobian values: the instance's block in HBM (kernel) or a staging array (host emulation)
   double* aba;   // ABA scratch: M/L, Minv, GQ, GV (nv x 32 each), GF (nv x nf)
   double* xbuf;  // [2 ndx + nu] staged x + alpha dx of this node (line-search trials)
+  double* vb;    // formulations without base inputs (PLM_VB_DOUBLES): A_b^-1 (36) | gaps at zero base part -> base part (6) |
+                 // d(foot / arm velocity rows)/d v_b (15 x 6) | force columns of the base rows (18 x 6)
 };
+#define PLM_VB_AINV 0
+#define PLM_VB_W 36
+#define PLM_VB_FB 42
+#define PLM_VB_GF 132
+#define PLM_VB_DOUBLES 240
 
 struct NodeArgs {
   const PlmModel* M;
@@ -70,6 +77,7 @@ struct LaneState {
   double Jq[6];
   double w[6], y[6], dFv[6], dFq[6], dFqn[6];
   double tau;
+  double Tq[6], Tv[6];   // centroidal_vel without base inputs: d v_b / d dq_lane, d v_b / d v_lane
 };
 
 PLM_HD void emit(const NodeWs& ws, const NodeArgs& A, int src, int idx, double val) {
@@ -106,12 +114,15 @@ PLM_HD void node_phase_a(NodeWs& ws, const NodeArgs& A, int lane) {
   const double* u = A.xs + L.ndx;
   if (lane < nv) {
     ws.cq[lane] = dx[dqoff + lane];
+    // without base inputs the leading block of U holds the joint part only; the base part starts at zero and is
+    // solved for after the first pass (node_phase_base_solve)
+    const double ulead = L.nobase ? (lane >= 6 ? u[lane - 6] : 0.0) : ((KIND == PLM_WHOLE_BODY_ABA) ? 0.0 : u[lane]);
     if (KIND == PLM_CENTROIDAL_VEL) {
-      ws.cv[lane] = u[lane];
+      ws.cv[lane] = ulead;
       ws.ca[lane] = 0.0;
     } else {
       ws.cv[lane] = x_init[M.nq + lane] + dx[nv + lane];
-      ws.ca[lane] = (KIND == PLM_WHOLE_BODY_ABA) ? 0.0 : u[lane];
+      ws.ca[lane] = ulead;
     }
   }
   int b = lane + 1;
@@ -413,9 +424,98 @@ PLM_HD void shift_to(const double* F, const double* c, double* o) {   // wrench 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase E: dynamics rows (values and Jacobian entries).
+// Formulations without base inputs (include_base = False).  The base part w of the velocity (centroidal_vel) or of the
+// acceleration (centroidal_acc, whole_body_acc) follows from the six dynamics-gap rows, which are affine in it:
+//   gaps(w) = A_b w + gaps(0),   w = -A_b^-1 gaps(0),   d w / d theta = -A_b^-1 d gaps / d theta
+// (dynamics_centroidal_vel.py:73-89 base_vel; dynamics_centroidal_acc.py:43-82, dynamics_whole_body_acc.py:43-83 base_acc).
+// Pass 1 (phases A-C with w = 0) gives gaps(0) and A_b = d gaps / d w (lanes 0..5 own one column each); pass 2 repeats
+// phases B, C with w in place.  The gap rows themselves are not part of these formulations.
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
+PLM_HD void node_phase_base_cols(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane) {
+  if (lane >= 6) return;
+  const PlmLayout& L = *A.L;
+  const double* root = ws.rec[0];
+  const double mC = root[PLM_REC_M];
+  const double* mcC = root + PLM_REC_MC;
+  double w[6];
+  inertia_mul(mC, mcC, root + PLM_REC_IB, st.J, w);      // I^C_0 J_lane
+  double* Ab = ws.vb + PLM_VB_AINV;
+  double* g0 = ws.vb + PLM_VB_W;
+  if (KIND == PLM_WHOLE_BODY_ACC) {
+    // M_bb[c][lane] = J_c . I^C_0 J_lane ;  gaps(0)[lane] = J_lane . F^C_0
+    for (int c = 0; c < 6; ++c) {
+      const int k = c % 3;
+      const double e[3] = {ws.Rb[k], ws.Rb[3 + k], ws.Rb[6 + k]};
+      Ab[6 * c + lane] = (c < 3) ? dot3(e, w) : dot3(e, w + 3);
+    }
+    g0[lane] = dot6(st.J, root + PLM_REC_F);
+  } else {
+    const double com[3] = {mcC[0] / mC, mcC[1] / mC, mcC[2] / mC};
+    double o[6];
+    shift_to(w, com, o);
+    for (int r = 0; r < 6; ++r) Ab[6 * r + lane] = o[r];
+    if (lane == 0) {
+      shift_to(KIND == PLM_CENTROIDAL_ACC ? root + PLM_REC_F : root + PLM_REC_H, com, o);
+      if (KIND == PLM_CENTROIDAL_VEL) {
+        const double* x_init = A.p + L.p_x_init;
+        for (int r = 0; r < 6; ++r) o[r] -= mC * (x_init[r] + A.xs[r]);
+      }
+      for (int r = 0; r < 6; ++r) g0[r] = o[r];
+    }
+  }
+}
+
+// Lane 0: A_b^-1 by Gauss-Jordan elimination with partial pivoting (A_b of the centroidal forms is not symmetric: rows
+// in world axes about the centre of mass, columns in base axes), then w = -A_b^-1 gaps(0) into the coordinate arrays.
+template <int KIND>
+PLM_HD void node_phase_base_solve(NodeWs& ws, int lane) {
+  if (lane != 0) return;
+  double* Ab = ws.vb + PLM_VB_AINV;
+  double* g0 = ws.vb + PLM_VB_W;
+  double* aug = ws.vb + PLM_VB_GF;      // [6][12] scratch (the force columns are filled later)
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) { aug[12 * r + c] = Ab[6 * r + c]; aug[12 * r + 6 + c] = (r == c) ? 1.0 : 0.0; }
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double best = fabs(aug[12 * k + k]);
+    for (int r = k + 1; r < 6; ++r) {
+      const double v = fabs(aug[12 * r + k]);
+      if (v > best) { best = v; piv = r; }
+    }
+    if (piv != k)
+      for (int c = 0; c < 12; ++c) { const double t = aug[12 * k + c]; aug[12 * k + c] = aug[12 * piv + c]; aug[12 * piv + c] = t; }
+    const double inv = 1.0 / aug[12 * k + k];
+    for (int c = 0; c < 12; ++c) aug[12 * k + c] *= inv;
+    for (int r = 0; r < 6; ++r) {
+      if (r == k) continue;
+      const double f = aug[12 * r + k];
+      for (int c = 0; c < 12; ++c) aug[12 * r + c] -= f * aug[12 * k + c];
+    }
+  }
+  double* dst = (KIND == PLM_CENTROIDAL_VEL) ? ws.cv : ws.ca;
+  for (int r = 0; r < 6; ++r) {
+    double acc = 0.0;
+    for (int c = 0; c < 6; ++c) { Ab[6 * r + c] = aug[12 * r + 6 + c]; acc += aug[12 * r + 6 + c] * g0[c]; }
+    dst[r] = -acc;
+  }
+}
+
+// Base-integrator rows of a formulation without base inputs: row c (c < 6) gets dt (A_b^-1 o)[c] in the column owned by
+// this lane, where o = d gaps / d (that column); `diag`: the column is the row's own state entry (-1 folded in).
+PLM_HD void emit_base_rows(const NodeWs& ws, const NodeArgs& A, int src, int stride, int col, const double* o, bool diag) {
+  const double* Ainv = ws.vb + PLM_VB_AINV;
+  for (int c = 0; c < 6; ++c) {
+    double t = A.dt * dot6(Ainv + 6 * c, o);
+    if (diag && c == col) t -= 1.0;
+    emit(ws, A, src, c * stride + col, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase E: dynamics rows (values and Jacobian entries).
+// ---------------------------------------------------------------------------------------------
+template <int KIND, bool NOBASE>
 PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane) {
   const PlmModel& M = *A.M;
   const PlmLayout& L = *A.L;
@@ -428,13 +528,16 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
 
   if (KIND == PLM_WHOLE_BODY_RNEA || KIND == PLM_WHOLE_BODY_ACC) {
     // ---- values: tau_rnea rows
-    if (lane < 6) ws.g[T.row_dyn + lane] = st.tau;
-    else if (T.joint_rows) ws.g[T.row_tauj + lane - 6] = st.tau - u[L.tau_idx + lane - 6];
+    if (!NOBASE) {
+      if (lane < 6) ws.g[T.row_dyn + lane] = st.tau;
+      else if (T.joint_rows) ws.g[T.row_tauj + lane - 6] = st.tau - u[L.tau_idx + lane - 6];
+    }
     if (!A.want_jac) return;
     const bool jr = T.joint_rows != 0;
     // ancestors-or-self columns: base 0..5, then chain
     const int len = M.chain_len[lane];
     const int nanc = 6 + (jr ? len : 0);
+    double oa[6], ov[6], oq[6];      // without base inputs: d(base rows)/d(this lane's columns)
     for (int a = 0; a < nanc; ++a) {
       const int c = (a < 6) ? a : (M.chain[lane][a - 6] + 5);
       const double* cr = ws.col[c];
@@ -443,6 +546,7 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
       double va = dot6(cr, st.w);
       double vv = dot6(cr, st.dFv);
       double vq = dot6(cr, same ? st.dFqn : st.dFq);
+      if (NOBASE) { oa[a] = va; ov[a] = vv; oq[a] = vq; continue; }
       emit(ws, A, PLM_SRC_TA, c * nv + lane, va);
       emit(ws, A, PLM_SRC_TV, c * nv + lane, vv);
       emit(ws, A, PLM_SRC_TQ, c * nv + lane, vq);
@@ -462,13 +566,22 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
         emit(ws, A, PLM_SRC_TQ, lane * nv + c, tq);
       }
     }
+    if (NOBASE) {
+      // base dv-integrator rows dv_next - dv - dt a_b(dq, dv, a_j, f)
+      emit_base_rows(ws, A, PLM_SRC_TA, nv, lane, oa, false);
+      emit_base_rows(ws, A, PLM_SRC_TV, nv, lane, ov, true);
+      emit_base_rows(ws, A, PLM_SRC_TQ, nv, lane, oq, false);
+    }
     // forces: d tau_lane / d f_k = -(J_lin + J_ang x p_k)
     if (lane < 6 || jr) {
       for (int k = 0; k < M.ncontact; ++k) {
         if (!((mask >> k) & 1u)) continue;
         double jk[3];
         cross3(st.J + 3, ws.con[k], jk);
-        for (int t = 0; t < 3; ++t) emit(ws, A, PLM_SRC_TF, lane * nf + 3 * k + t, -(st.J[t] + jk[t]));
+        for (int t = 0; t < 3; ++t) {
+          if (NOBASE) ws.vb[PLM_VB_GF + 6 * (3 * k + t) + lane] = -(st.J[t] + jk[t]);      // row lane of force column (k, t)
+          else emit(ws, A, PLM_SRC_TF, lane * nf + 3 * k + t, -(st.J[t] + jk[t]));
+        }
       }
     }
   }
@@ -486,7 +599,7 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
         // gaps = A v - m h,  h = h_init + dh
         for (int r = 0; r < 6; ++r) gsh[r] -= Mtot * (x_init[r] + A.xs[r]);
       }
-      for (int r = 0; r < 6; ++r) ws.g[T.row_dyn + r] = gsh[r];
+      if (!NOBASE) for (int r = 0; r < 6; ++r) ws.g[T.row_dyn + r] = gsh[r];
     }
     if (KIND == PLM_CENTROIDAL_VEL) {
       // h_dot = [sum f + m g; sum (p_k - c) x f_k] / m ; rows dh_next - (dh + h_dot dt)
@@ -515,11 +628,14 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
       shift_to(st.dFq, com, o);
       cross3(dc, tot, t3);
       for (int r = 0; r < 3; ++r) o[3 + r] -= t3[r];
-      for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TQ, r * nv + lane, o[r]);
+      if (NOBASE) emit_base_rows(ws, A, PLM_SRC_TQ, nv, lane, o, false);
+      else for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TQ, r * nv + lane, o[r]);
       shift_to(st.dFv, com, o);
-      for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TV, r * nv + lane, o[r]);
+      if (NOBASE) emit_base_rows(ws, A, PLM_SRC_TV, nv, lane, o, true);
+      else for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TV, r * nv + lane, o[r]);
       shift_to(st.w, com, o);
-      for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TA, r * nv + lane, o[r]);
+      if (NOBASE) emit_base_rows(ws, A, PLM_SRC_TA, nv, lane, o, false);
+      else for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TA, r * nv + lane, o[r]);
     } else {
       // d(shift_c H)/dq = shift(Jq x* H^C + I^C phi_q) - (0, dc x H_lin);  d/dv = shift(I^C J)
       double dH[6], t6[6];
@@ -529,9 +645,22 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
       shift_to(dH, com, o);
       cross3(dc, tot, t3);
       for (int r = 0; r < 3; ++r) o[3 + r] -= t3[r];
-      for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TQ, r * nv + lane, o[r]);
-      shift_to(st.w, com, o);
-      for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TV, r * nv + lane, o[r]);
+      if (NOBASE) {
+        // base dq-integrator rows dq_next - dq - dt v_b(dh, dq, v_j); the directions d v_b / d(column) are kept for the
+        // foot / arm velocity rows (node_phase_fjac)
+        const double* Ainv = ws.vb + PLM_VB_AINV;
+        emit_base_rows(ws, A, PLM_SRC_TQ, nv, lane, o, true);
+        for (int c = 0; c < 6; ++c) st.Tq[c] = -dot6(Ainv + 6 * c, o);
+        shift_to(st.w, com, o);
+        emit_base_rows(ws, A, PLM_SRC_TV, nv, lane, o, false);
+        for (int c = 0; c < 6; ++c) st.Tv[c] = -dot6(Ainv + 6 * c, o);
+        if (lane < 6)      // d gaps / d dh_lane = -m e_lane
+          for (int c = 0; c < 6; ++c) emit(ws, A, PLM_SRC_IH, c * 6 + lane, -A.dt * Mtot * Ainv[6 * c + lane]);
+      } else {
+        for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TQ, r * nv + lane, o[r]);
+        shift_to(st.w, com, o);
+        for (int r = 0; r < 6; ++r) emit(ws, A, PLM_SRC_TV, r * nv + lane, o[r]);
+      }
       // d(h_dot)/dq: angular rows sum_k (dp_k - dc) x f_k / m, times -dt for the integrator row
       double acc[3] = {0, 0, 0};
       for (int k = 0; k < M.ncontact; ++k) {
@@ -553,7 +682,10 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
         e[t] = 1.0;
         double n[3];
         cross3(r3, e, n);
-        if (KIND == PLM_CENTROIDAL_ACC) {
+        if (KIND == PLM_CENTROIDAL_ACC && NOBASE) {
+          const double of[6] = {t == 0 ? -1.0 : 0.0, t == 1 ? -1.0 : 0.0, t == 2 ? -1.0 : 0.0, -n[0], -n[1], -n[2]};
+          emit_base_rows(ws, A, PLM_SRC_TF, nf, 3 * k + t, of, false);
+        } else if (KIND == PLM_CENTROIDAL_ACC) {
           emit(ws, A, PLM_SRC_TF, t * nf + 3 * k + t, -1.0);
           for (int r = 0; r < 3; ++r) emit(ws, A, PLM_SRC_TF, (3 + r) * nf + 3 * k + t, -n[r]);
         } else {
@@ -583,7 +715,104 @@ PLM_HD double spline_vel_z(double phase, double T, double h, double v_lo, double
   return (3.0 * c3 * tn * tn + 2.0 * c2 * tn + c1) / dt;
 }
 
-template <int KIND>
+// Foot-velocity and arm-velocity Jacobian entries, lane = column.
+// MODE 0: the rows depend on the lane's own columns only (kinematic-tree pattern).
+// MODE 1 / 2 (centroidal_vel without base inputs): the frame velocities also depend on every column through
+// v_b(dh, dq, v_j).  MODE 1 (lanes 0..5, before phase E): record d(row)/d v_b[lane]; MODE 2 (after phase E): emit
+// d(row)/d(column) = direct part + sum_j d(row)/d v_b[j] * d v_b[j]/d(column) for every row and column.
+template <int KIND, int MODE>
+PLM_HD void node_phase_fjac(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane) {
+  const PlmModel& M = *A.M;
+  const PlmLayout& L = *A.L;
+  const PlmNodeType& T = *A.T;
+  const int nv = M.nv;
+  if (!A.want_jac || lane >= nv || !T.state_rows) return;
+  const double* contact = A.p + L.p_contact + 4 * A.node;
+  double* fb = (MODE != 0) ? ws.vb + PLM_VB_FB : nullptr;
+  const double* Ainv = (MODE == 2) ? ws.vb + PLM_VB_AINV : nullptr;
+  const double Mtot = (MODE == 2) ? ws.rec[0][PLM_REC_M] : 0.0;
+  if (MODE == 1 && lane >= 6) return;
+  // MODE 2: `row` indexes the source block (foot rows 3 k + r, arm rows r), `frow` the recorded coefficients
+  auto chain = [&](int frow, int row, int srcq, int srcv, int srch, double dq_direct, double dv_direct) {
+    const double* f6 = fb + 6 * frow;
+    emit(ws, A, srcq, row * nv + lane, dq_direct + dot6(f6, st.Tq));
+    emit(ws, A, srcv, row * nv + lane, dv_direct + dot6(f6, st.Tv));
+    if (lane < 6) {      // column dh_lane: d v_b / d dh_lane = m A_b^-1[:, lane]
+      double acc = 0.0;
+      for (int j = 0; j < 6; ++j) acc += f6[j] * Ainv[6 * j + lane];
+      emit(ws, A, srch, row * 6 + lane, Mtot * acc);
+    }
+  };
+  const unsigned mask = M.col_contacts[lane];
+  for (int k = 0; k < M.nfeet; ++k) {
+    const bool in = ((mask >> k) & 1u) != 0;
+    if (MODE != 2 && !in) continue;
+    const double* ck = ws.con[k];
+    const double c = contact[k];
+    const double sc3[3] = {c, c, 1.0};
+    double jk[3] = {0, 0, 0}, o[3] = {0, 0, 0};
+    if (in) {
+      double jq[3], D[6], x6[6], t3[3];
+      cross3(st.J + 3, ck, jk);
+      cross3(st.Jq + 3, ck, jq);
+      for (int i = 0; i < 3; ++i) { jk[i] += st.J[i]; jq[i] += st.Jq[i]; }
+      for (int i = 0; i < 6; ++i) D[i] = ck[3 + i] - st.Vp[i];
+      mxm(st.Jq, D, x6);
+      cross3(x6 + 3, ck, o);
+      cross3(ck + 6, jq, t3);
+      for (int i = 0; i < 3; ++i) o[i] += x6[i] + t3[i];
+    }
+    for (int r = 0; r < 3; ++r) {
+      if (MODE == 0) {
+        emit(ws, A, PLM_SRC_FV, (k * 3 + r) * nv + lane, sc3[r] * jk[r]);
+        emit(ws, A, PLM_SRC_FQ, (k * 3 + r) * nv + lane, sc3[r] * o[r]);
+      } else if (MODE == 1) fb[6 * (k * 3 + r) + lane] = sc3[r] * jk[r];
+      else chain(k * 3 + r, k * 3 + r, PLM_SRC_FQ, PLM_SRC_FV, PLM_SRC_FH, sc3[r] * o[r], sc3[r] * jk[r]);
+    }
+  }
+  if (T.row_arm >= 0) {
+    const bool in = ((M.col_arm >> lane) & 1u) != 0;
+    if (MODE != 2 && !in) return;
+    const double* ak = ws.arm;
+    double jk[3] = {0, 0, 0}, o[3] = {0, 0, 0}, jq[3] = {0, 0, 0}, t3[3] = {0, 0, 0};
+    if (in) {
+      double D[6], x6[6];
+      cross3(st.J + 3, ak, jk);
+      cross3(st.Jq + 3, ak, jq);
+      for (int i = 0; i < 3; ++i) { jk[i] += st.J[i]; jq[i] += st.Jq[i]; }
+      for (int i = 0; i < 6; ++i) D[i] = ak[3 + i] - st.Vp[i];
+      mxm(st.Jq, D, x6);
+      cross3(x6 + 3, ak, o);
+      for (int i = 0; i < 3; ++i) o[i] += x6[i];
+      cross3(ak + 6, jq, t3);
+    }
+    // row 2: world z of the full frame velocity
+    if (MODE == 0) {
+      emit(ws, A, PLM_SRC_AV, 2 * nv + lane, jk[2]);
+      emit(ws, A, PLM_SRC_AQ, 2 * nv + lane, o[2] + t3[2]);
+    } else if (MODE == 1) {
+      fb[6 * (3 * M.nfeet + 0) + lane] = 0.0;      // rows 0, 1: velocity relative to the base, independent of v_b
+      fb[6 * (3 * M.nfeet + 1) + lane] = 0.0;
+      fb[6 * (3 * M.nfeet + 2) + lane] = jk[2];
+    } else chain(3 * M.nfeet + 2, 2, PLM_SRC_AQ, PLM_SRC_AV, PLM_SRC_AH, o[2] + t3[2], jk[2]);
+    if (MODE != 1 && in && M.col_body[lane] != 0) {
+      // rows 0,1: velocity relative to the base, in base axes (only arm-chain columns contribute)
+      double Wb[3], wrel[3], orel[3], ob[3], jb[3];
+      matvec3(ws.Rb, ws.cv + 3, Wb);
+      for (int i = 0; i < 3; ++i) wrel[i] = ak[6 + i] - Wb[i];
+      cross3(wrel, jq, t3);
+      for (int i = 0; i < 3; ++i) orel[i] = o[i] + t3[i];
+      matTvec3(ws.Rb, orel, ob);
+      matTvec3(ws.Rb, jk, jb);
+      for (int r = 0; r < 2; ++r) {
+        emit(ws, A, PLM_SRC_AV, r * nv + lane, jb[r]);
+        emit(ws, A, PLM_SRC_AQ, r * nv + lane, ob[r]);
+      }
+    }
+  }
+}
+
+template <int KIND, bool NOBASE>
 PLM_HD void node_phase_f(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane) {
   const PlmModel& M = *A.M;
   const PlmLayout& L = *A.L;
@@ -672,58 +901,10 @@ PLM_HD void node_phase_f(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
     ws.g[T.row_arm + 2] = full[2] + ak[5] - des[2];
   }
   if (!A.want_jac || lane >= nv) return;
-  // ---- foot velocity Jacobians: lane = column
-  if (T.state_rows) {
-    const unsigned mask = M.col_contacts[lane];
-    for (int k = 0; k < M.nfeet; ++k) {
-      if (!((mask >> k) & 1u)) continue;
-      const double* ck = ws.con[k];
-      const double c = contact[k];
-      double jk[3], jq[3], D[6], x6[6], o[3], t3[3];
-      cross3(st.J + 3, ck, jk);
-      cross3(st.Jq + 3, ck, jq);
-      for (int i = 0; i < 3; ++i) { jk[i] += st.J[i]; jq[i] += st.Jq[i]; }
-      for (int i = 0; i < 6; ++i) D[i] = ck[3 + i] - st.Vp[i];
-      mxm(st.Jq, D, x6);
-      cross3(x6 + 3, ck, o);
-      cross3(ck + 6, jq, t3);
-      for (int i = 0; i < 3; ++i) o[i] += x6[i] + t3[i];
-      const double sc3[3] = {c, c, 1.0};
-      for (int r = 0; r < 3; ++r) {
-        emit(ws, A, PLM_SRC_FV, (k * 3 + r) * nv + lane, sc3[r] * jk[r]);
-        emit(ws, A, PLM_SRC_FQ, (k * 3 + r) * nv + lane, sc3[r] * o[r]);
-      }
-    }
-    if (T.row_arm >= 0 && ((M.col_arm >> lane) & 1u)) {
-      const double* ak = ws.arm;
-      double jk[3], jq[3], D[6], x6[6], o[3], t3[3];
-      cross3(st.J + 3, ak, jk);
-      cross3(st.Jq + 3, ak, jq);
-      for (int i = 0; i < 3; ++i) { jk[i] += st.J[i]; jq[i] += st.Jq[i]; }
-      for (int i = 0; i < 6; ++i) D[i] = ak[3 + i] - st.Vp[i];
-      mxm(st.Jq, D, x6);
-      cross3(x6 + 3, ak, o);
-      for (int i = 0; i < 3; ++i) o[i] += x6[i];
-      cross3(ak + 6, jq, t3);
-      // row 2: world z of the full frame velocity
-      emit(ws, A, PLM_SRC_AV, 2 * nv + lane, jk[2]);
-      emit(ws, A, PLM_SRC_AQ, 2 * nv + lane, o[2] + t3[2]);
-      if (M.col_body[lane] != 0) {
-        // rows 0,1: velocity relative to the base, in base axes (only arm-chain columns contribute)
-        double Wb[3], wrel[3], orel[3], ob[3], jb[3];
-        matvec3(ws.Rb, ws.cv + 3, Wb);
-        for (int i = 0; i < 3; ++i) wrel[i] = ak[6 + i] - Wb[i];
-        cross3(wrel, jq, t3);
-        for (int i = 0; i < 3; ++i) orel[i] = o[i] + t3[i];
-        matTvec3(ws.Rb, orel, ob);
-        matTvec3(ws.Rb, jk, jb);
-        for (int r = 0; r < 2; ++r) {
-          emit(ws, A, PLM_SRC_AV, r * nv + lane, jb[r]);
-          emit(ws, A, PLM_SRC_AQ, r * nv + lane, ob[r]);
-        }
-      }
-    }
-  }
+  // foot / arm velocity Jacobians (lane = column); centroidal_vel without base inputs emits them after phase E, when
+  // the directions d v_b / d(column) are known, and only records the rows' coefficients on v_b here
+  if (KIND == PLM_CENTROIDAL_VEL && NOBASE) node_phase_fjac<KIND, 1>(ws, A, st, lane);
+  else node_phase_fjac<KIND, 0>(ws, A, st, lane);
 }
 
 // Constant Jacobian entries; lanes stride over the list.

@@ -35,6 +35,7 @@ PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf, int nbody, boo
   size_t extra = (size_t)nbody * PLM_REC + (size_t)nv * PLM_COLREC + (size_t)L.max_rows + (stage_J ? (size_t)L.max_nnz : 0) +
                  (size_t)(2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
   if (L.dynamics == PLM_WHOLE_BODY_ABA) extra += aba_ws_doubles(nv, nf);
+  if (L.nobase) extra += PLM_VB_DOUBLES;
   return base + extra + 2;
 }
 
@@ -50,13 +51,14 @@ PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, int nv, int nbody, doub
   else { ws.J = tail; tail += L.max_nnz; }
   ws.xbuf = tail;
   ws.aba = ws.xbuf + (2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
+  ws.vb = ws.aba;      // (the ABA formulation has no variant without base inputs: the two scratch areas never coexist)
 }
 
 }  // namespace plm
 #include "plm_node_aba.cuh"
 namespace plm {
 
-template <int KIND, class Exec>
+template <int KIND, bool NOBASE, class Exec>
 PLM_HD void node_eval_body(Exec& ex, NodeWs& ws, const NodeArgs& A) {
   const PlmModel& M = *A.M;
   const PlmNodeType& T = *A.T;
@@ -64,21 +66,37 @@ PLM_HD void node_eval_body(Exec& ex, NodeWs& ws, const NodeArgs& A) {
   ex.run([&](int lane, LaneState&) { node_phase_a<KIND>(ws, A, lane); });
   ex.run([&](int lane, LaneState& st) { node_phase_b<KIND>(ws, A, st, lane); });
   for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
+  if (NOBASE) {
+    // inputs without the base part: solve the six gap rows for it (first pass ran with a zero base part), then
+    // repeat the chain walk and the composites with it in place
+    ex.run([&](int lane, LaneState& st) { node_phase_base_cols<KIND>(ws, A, st, lane); });
+    ex.run([&](int lane, LaneState&) { node_phase_base_solve<KIND>(ws, lane); });
+    ex.run([&](int lane, LaneState& st) { node_phase_b<KIND>(ws, A, st, lane); });
+    for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
+  }
   if (KIND == PLM_WHOLE_BODY_ABA) {
     aba_solve_and_derivatives<Exec>(ex, ws, A);
     ex.run([&](int lane, LaneState& st) {
-      node_phase_f<KIND>(ws, A, st, lane);
+      node_phase_f<KIND, false>(ws, A, st, lane);
       if (A.want_jac) node_phase_consts(ws, A, lane, 32);
     });
   } else {
     // contact / arm / shared rows first: they only need the chain state of phase B, which keeps the register
     // footprint of the derivative phases (D, E) down
     ex.run([&](int lane, LaneState& st) {
-      node_phase_f<KIND>(ws, A, st, lane);
+      node_phase_f<KIND, NOBASE>(ws, A, st, lane);
       if (A.want_jac) node_phase_consts(ws, A, lane, 32);
       node_phase_d<KIND>(ws, A, st, lane);
     });
-    ex.run([&](int lane, LaneState& st) { node_phase_e<KIND>(ws, A, st, lane); });
+    ex.run([&](int lane, LaneState& st) { node_phase_e<KIND, NOBASE>(ws, A, st, lane); });
+    if (NOBASE && A.want_jac) {
+      if (KIND == PLM_WHOLE_BODY_ACC)      // force columns of the base rows: written row-wise by lanes 0..5 in phase E
+        ex.run([&](int lane, LaneState&) {
+          if (lane < A.L->nf) emit_base_rows(ws, A, PLM_SRC_TF, A.L->nf, lane, ws.vb + PLM_VB_GF + 6 * lane, false);
+        });
+      if (KIND == PLM_CENTROIDAL_VEL)
+        ex.run([&](int lane, LaneState& st) { node_phase_fjac<KIND, 2>(ws, A, st, lane); });
+    }
   }
 }
 

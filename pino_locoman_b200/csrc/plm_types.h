@@ -63,6 +63,9 @@ enum PlmSrc {
   PLM_SRC_AV,       // [3][nv]
   PLM_SRC_XQ,       // [6][nv] centroidal_vel: d(h_dot)/d dq
   PLM_SRC_XF,       // [6][nf] centroidal_vel: d(h_dot)/d forces
+  PLM_SRC_IH,       // [6][6]  centroidal_vel without base inputs: d(base dq-integrator rows)/d dh
+  PLM_SRC_FH,       // [nfeet][3][6]  "  : d(foot velocity rows)/d dh
+  PLM_SRC_AH,       // [3][6]         "  : d(arm rows)/d dh
   PLM_SRC_COUNT
 };
 
@@ -101,6 +104,7 @@ struct PlmNodeType {
 // Whole-problem layout (per OCP formulation), shared by every instance of the batch.
 struct PlmLayout {
   int32_t dynamics, nodes, tau_nodes;
+  int32_t nobase;                      // include_base = False: inputs without the base part, no dynamics-gap rows
   int32_t nx, ndx, n, m, np, nnz;
   int32_t nf;
   int32_t f_idx, tau_idx, lead;    // offsets inside U_i: forces, torques; size of the leading block (a / v / tau_j)

@@ -10,10 +10,10 @@ class OCPWholeBodyAcc(OCP):
 
     def __init__(self, robot, solver, nodes, include_base=False, batch=1, device=None):
         super().__init__(robot, solver, nodes, batch=batch, device=device)
-        if not include_base:
-            raise NotImplementedError("include_base=False (base acceleration from the dynamics) is not available yet")
-        self.include_base = include_base
-        self.na_opt = self.nv
+        # include_base=False: inputs (a_j, f); a_b = base_acc_dynamics(q, v, a_j, f) is substituted inside the node kernel and
+        # the six gap rows are dropped (ocp_whole_body_acc.py:20-24,109-141)
+        self.include_base = bool(include_base)
+        self.na_opt = self.nv if self.include_base else self.nj
         self.x_nom = np.concatenate((robot.q0, np.zeros(self.nv)))
         self.f_idx = self.na_opt
 

@@ -15,11 +15,12 @@ class OcpDesc(ctypes.Structure):
                 ("mu", ctypes.c_double), ("osqp_max_iter", ctypes.c_int32), ("osqp_check_termination", ctypes.c_int32),
                 ("osqp_scaling", ctypes.c_int32), ("osqp_rho", ctypes.c_double), ("osqp_sigma", ctypes.c_double),
                 ("osqp_alpha", ctypes.c_double), ("osqp_eps_abs", ctypes.c_double), ("osqp_eps_rel", ctypes.c_double),
-                ("osqp_eps_prim_inf", ctypes.c_double), ("osqp_eps_dual_inf", ctypes.c_double)]
+                ("osqp_eps_prim_inf", ctypes.c_double), ("osqp_eps_dual_inf", ctypes.c_double),
+                ("include_base", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
-def default_ocp_desc(dynamics, nodes, tau_nodes=3):
-    return OcpDesc(DYN_ID[dynamics], nodes, tau_nodes, 0.7, 100, 25, 10, 2e-2, 1e-6, 1.4, 1e-3, 1e-3, 1e-4, 1e-4)
+def default_ocp_desc(dynamics, nodes, tau_nodes=3, include_base=True):
+    return OcpDesc(DYN_ID[dynamics], nodes, tau_nodes, 0.7, 100, 25, 10, 2e-2, 1e-6, 1.4, 1e-3, 1e-3, 1e-4, 1e-4, int(include_base), 0)
 
 
 def build_emu():
@@ -35,11 +36,11 @@ def build_emu():
 
 
 class Emu:
-    def __init__(self, robot, dynamics, nodes, tau_nodes=3):
+    def __init__(self, robot, dynamics, nodes, tau_nodes=3, include_base=True):
         from pino_locoman_b200.utils.robot import robot_desc
         self.lib = build_emu()
         self.rd = robot_desc(robot)
-        self.od = default_ocp_desc(dynamics, nodes, tau_nodes)
+        self.od = default_ocp_desc(dynamics, nodes, tau_nodes, include_base)
         err = ctypes.create_string_buffer(256)
         self.h = self.lib.emu_create(ctypes.byref(self.rd), ctypes.byref(self.od), err, 256)
         if not self.h:
@@ -121,8 +122,8 @@ def random_problem(oocp, rng, t_current=None, ext=True):
         if o.kind == "whole_body_aba":
             u[:lead] = rng.uniform(-0.5, 0.5, r.nj) * r.joint_torque_max
         elif o.kind == "centroidal_vel":
-            u[:lead] = np.concatenate((rng.uniform(-1, 1, 6), rng.uniform(-0.25, 0.25, r.nj) * r.joint_vel_max))
-        else:
+            u[:lead] = np.concatenate((rng.uniform(-1, 1, 6), rng.uniform(-0.25, 0.25, r.nj) * r.joint_vel_max))[-lead:]
+        elif lead:
             u[:lead] = rng.normal(0, 5, lead)
         for kf in range(4):
             fz = rng.uniform(0, mg)

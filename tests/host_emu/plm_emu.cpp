@@ -37,7 +37,9 @@ static void run_node(const HostTables& t, const double* x, const double* p, int 
   A.want_jac = want_jac;
   HostExec ex;
   memset(&ex, 0, sizeof(ex));
-  node_eval_body<KIND>(ex, ws, A);
+  constexpr bool has_variant = KIND == PLM_CENTROIDAL_VEL || KIND == PLM_CENTROIDAL_ACC || KIND == PLM_WHOLE_BODY_ACC;
+  if (has_variant && t.layout.nobase) node_eval_body<KIND, has_variant>(ex, ws, A);      // include_base = False
+  else node_eval_body<KIND, false>(ex, ws, A);
   const PlmNodeType& T = *A.T;
   for (int r = 0; r < T.nrows; ++r) g[(size_t)b * L.m + L.row_off[node] + r] = ws.g[r];
   if (node == 0) for (int r = 0; r < L.ndx; ++r) g[(size_t)b * L.m + r] = A.xs[r];

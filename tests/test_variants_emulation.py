@@ -63,3 +63,28 @@ def test_reference_initial_guess_point(robots):
     rng = np.random.default_rng(6)
     for rn, kind in (("b2", "whole_body_rnea"), ("b2g", "whole_body_aba"), ("go2", "centroidal_vel"), ("b2", "whole_body_acc")):
         _check(prod[rn], ora[rn], kind, 3, rng, exact_guess=True)
+
+
+@pytest.mark.parametrize("rn,kind", [("b2", "centroidal_acc"), ("b2g", "whole_body_acc"), ("go2", "centroidal_vel"), ("b2g", "centroidal_vel"),
+                                     ("b2g", "centroidal_acc"), ("go2", "whole_body_acc")])
+def test_formulations_without_base_inputs(robots, rn, kind):
+    """include_base=False (ocp_centroidal_vel.py:104-120, ocp_centroidal_acc.py:129-140, ocp_whole_body_acc.py:130-141): the base
+    velocity / acceleration is solved for from the six gap rows inside the node evaluation; rows and the chain-rule
+    Jacobian (dense base-integrator, foot- and arm-velocity rows) against the oracle's complex-step differentiation."""
+    prod, ora = robots
+    rng = np.random.default_rng(12)
+    for exact in (False, True):
+        o = OracleOCP(ora[rn], kind, 3, include_base=False)
+        e = Emu(prod[rn], kind, 3, include_base=False)
+        assert (e.n, e.m, e.np_) == (o.n, o.m, o.np_)
+        x, p = random_problem(o, rng)
+        if exact:
+            x = o.initial_guess()
+        g_ref, _, _ = o.g_data(x, p)
+        J_ref = o.jac_g(x, p)
+        g, Jv = e.eval(x, p)
+        assert not np.isnan(Jv).any()                      # every pattern entry is written
+        assert np.abs(g[0] - g_ref).max() <= TOL * max(1.0, np.abs(g_ref).max())
+        assert np.abs(e.dense(Jv[0]) - J_ref).max() <= TOL * np.abs(J_ref).max()
+        g2, _ = e.eval(x, p, want_jac=False)               # residual-only mode (line-search trials)
+        assert np.array_equal(g2, g)
