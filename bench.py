@@ -11,7 +11,8 @@ consecutive steps continue the SQP sequence (x <- x_new, warm-started ADMM itera
 Prints ONE JSON line on rank 0.  `value` = SQP iterations/s with inputs resident in HBM; `e2e` = the same through
 the plugin surface (OCP.solve with host buffers, H2D + D2H inside the timed region); `node_evals_per_s` and the two
 roofline objects report the dyn+Jacobian kernel and the dominant (ADMM) kernel against the measured HBM peak;
-`cpu_baseline` is the numpy oracle on one host core (a port, for context only).
+`cpu_baseline` is the compiled C++ port of the reference algorithm (oracle/cport) on one host core, with the numpy oracle
+beside it (ports, for context only: the real casadi / pinocchio / OSQP stack is not installable here).
 """
 import argparse
 import ctypes
@@ -210,7 +211,7 @@ def run_reference(args, rank):
                                "port, not the real casadi/pinocchio/OSQP stack"},
             "cpu_baseline": {"value": value, "unit": "SQP iters/s", "cores": procs, "kind": kind,
                              "sample": f"{n_inst} instances x 1 SQP iteration per step, one process per core, "
-                                       + ("C++ port of the reference algorithm (-O3 -march=native)" if cport is not None else "numpy oracle")
+                                       + ("C++ port of the reference algorithm (-O3 -march=x86-64-v3)" if cport is not None else "numpy oracle")
                                        + " (restated reference algorithm; casadi/pinocchio/osqp not installable)"},
             "e2e": {"value": value, "unit": "SQP iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -538,12 +539,23 @@ def main():
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline:
-        n_cpu = 8          # ~10 s of CPU work on one core
-        wall, t_eval, t_all = cpu_oracle_timing(x_host, p_host, n_cpu, 1, 1)
-        line["cpu_baseline"] = {"value": n_cpu / t_all, "unit": "SQP iters/s", "cores": 1, "kind": "port",
-                                "node_evals_per_s": n_cpu * NODES / t_eval,
-                                "sample": f"{n_cpu} instances x 1 SQP iteration of the same workload, numpy oracle on one core "
-                                          "(restated reference algorithm, not casadi/pinocchio/OSQP)"}
+        # CPU baseline on ONE host core, bounded sample of the same workload (same synthetic instances as the GPU arm):
+        # the compiled C++ port of the reference algorithm (oracle/cport) when it is built, plus the numpy oracle
+        n_np = 4
+        wall, t_eval, t_all = cpu_oracle_timing(x_host, p_host, n_np, 1, 1)
+        numpy_port = {"value": n_np / t_all, "unit": "SQP iters/s", "cores": 1, "node_evals_per_s": n_np * NODES / t_eval,
+                      "sample": f"{n_np} instances x 1 SQP iteration, numpy oracle"}
+        if _load_cport() is not None:
+            n_cpu = 256        # ~10 s of CPU work on one core
+            t_sqp, t_ev = cport_timing(x_host[:n_cpu], p_host[:n_cpu], n_cpu, 1)
+            line["cpu_baseline"] = {"value": n_cpu / t_sqp, "unit": "SQP iters/s", "cores": 1, "kind": "port (C++)",
+                                    "node_eval_share": t_ev / t_sqp,
+                                    "sample": f"{n_cpu} instances x 1 SQP iteration of the same workload, C++ port of the reference algorithm "
+                                              "(-O3, one core; restated, not casadi/pinocchio/OSQP: those are not installable on this box, "
+                                              "profiles/probe_real_stack_r02.log)",
+                                    "numpy_port": numpy_port}
+        else:
+            line["cpu_baseline"] = dict(numpy_port, kind="port")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

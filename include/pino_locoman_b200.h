@@ -72,7 +72,10 @@ typedef struct {
    * v_b = base_vel_dynamics(h, q, v_j) / a_b = base_acc_dynamics(q, v, a_j, forces) substituted and no gap rows
    * (ocp_centroidal_vel.py:19-23,104-120; ocp_centroidal_acc.py:19-23,108-140; ocp_whole_body_acc.py:20-24,109-141). */
   int32_t include_base;
-  int32_t reserved;                                   /* 0 */
+  /* include_acc (ocp_args.py:17; whole_body_rnea): 1 = accelerations among the inputs + the dv integrator rows (the
+   * reference's OCP_ARGS default); 0 = no acceleration inputs, a_i = (v_{i+1} - v_i) / dt_i substituted and the dv
+   * integrator rows dropped (ocp_whole_body_rnea.py:21-25,156,183-191): the RNEA rows then touch dv_{i+1}. */
+  int32_t include_acc;
 } plm_ocp_desc;
 
 typedef struct {

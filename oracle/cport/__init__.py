@@ -32,7 +32,7 @@ class OcpDesc(ctypes.Structure):        # plm_ocp_desc
                 ("osqp_scaling", ctypes.c_int32), ("osqp_rho", ctypes.c_double), ("osqp_sigma", ctypes.c_double),
                 ("osqp_alpha", ctypes.c_double), ("osqp_eps_abs", ctypes.c_double), ("osqp_eps_rel", ctypes.c_double),
                 ("osqp_eps_prim_inf", ctypes.c_double), ("osqp_eps_dual_inf", ctypes.c_double),
-                ("include_base", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("include_base", ctypes.c_int32), ("include_acc", ctypes.c_int32)]
 
 
 def build(portable=False):
@@ -117,7 +117,7 @@ class CPortSQP:
         self.lib = load()
         self._rd = robot_desc_from_oracle(oocp.robot)
         od = OcpDesc(DYN_ID[oocp.kind], oocp.nodes, max(oocp.tau_nodes, 1), 0.7, 100, 25, 10, 2e-2, 1e-6, 1.4, 1e-3, 1e-3, 1e-4, 1e-4,
-                     int(getattr(oocp, "include_base", True)), 0)
+                     int(getattr(oocp, "include_base", True)), int(getattr(oocp, "include_acc", True)))
         for k, v in osqp_opts.items():
             setattr(od, "osqp_" + k, v)
         err = ctypes.create_string_buffer(256)

@@ -23,7 +23,7 @@ class OcpDesc(ctypes.Structure):
                 ("osqp_scaling", ctypes.c_int32), ("osqp_rho", ctypes.c_double), ("osqp_sigma", ctypes.c_double),
                 ("osqp_alpha", ctypes.c_double), ("osqp_eps_abs", ctypes.c_double), ("osqp_eps_rel", ctypes.c_double),
                 ("osqp_eps_prim_inf", ctypes.c_double), ("osqp_eps_dual_inf", ctypes.c_double),
-                ("include_base", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("include_base", ctypes.c_int32), ("include_acc", ctypes.c_int32)]
 
 
 class Dims(ctypes.Structure):

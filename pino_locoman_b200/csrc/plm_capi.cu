@@ -55,6 +55,7 @@ void plm_fill_default_ocp_desc(plm_ocp_desc* d, int32_t dynamics, int32_t nodes)
   d->osqp_eps_prim_inf = 1e-4;
   d->osqp_eps_dual_inf = 1e-4;
   d->include_base = 1;         // ocp_args.py:3-11
+  d->include_acc = 1;          // ocp_args.py:17
 }
 
 void plm_abi_struct_sizes(int32_t out[3]) {

@@ -134,6 +134,7 @@ static int get_probe(plm_handle* h, int dynamics, plm_probe** out) {
   rd.joint_torque_max = M.joint_torque_max; rd.q0 = M.q0;
   plm_ocp_desc od = h->ocp;
   od.dynamics = dynamics; od.nodes = 2; od.tau_nodes = 2;
+  od.include_base = 1; od.include_acc = 1;      // the Dynamics* functions are those of the full formulations
   plm_probe* pr = new plm_probe();
   int rc = plm_create(&rd, &od, h->max_batch, &pr->h);
   if (rc) { h->error = std::string("probe: ") + (pr->h ? pr->h->error : "alloc"); probe_free(pr); return rc; }

@@ -130,8 +130,11 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   const int ndx = L.ndx;
   const bool nobase = !ocp.include_base && (kind == PLM_CENTROIDAL_VEL || kind == PLM_CENTROIDAL_ACC || kind == PLM_WHOLE_BODY_ACC);
   L.nobase = nobase ? 1 : 0;
-  // leading input block: v / a (nv), tau_j (nj), or joint part only when the base part follows from the dynamics
-  L.lead = (kind == PLM_WHOLE_BODY_ABA || nobase) ? nj : nv;
+  const bool noacc = !ocp.include_acc && kind == PLM_WHOLE_BODY_RNEA;
+  L.noacc = noacc ? 1 : 0;
+  // leading input block: v / a (nv), tau_j (nj), the joint part only when the base part follows from the dynamics, or
+  // nothing (whole_body_rnea with finite-difference accelerations)
+  L.lead = noacc ? 0 : ((kind == PLM_WHOLE_BODY_ABA || nobase) ? nj : nv);
   L.f_idx = L.lead;
   L.tau_idx = L.lead + nf;
   // stage offsets
@@ -183,7 +186,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     const int nu_i = nu[i];
     // lut source offsets
     const int sizes[PLM_SRC_COUNT] = {nv * nv, nv * nv, nv * nv, nv * nf, nfeet * 3 * nv, nfeet * 3 * nv, 3 * nv, 3 * nv, 6 * nv, 6 * nf,
-                                      36, nfeet * 3 * 6, 3 * 6};
+                                      36, nfeet * 3 * 6, 3 * 6, nv * nv};
     int lo = 0;
     for (int s = 0; s < PLM_SRC_COUNT; ++s) { T.src_off[s] = lo; lo += sizes[s]; }
     T.lut_size = lo;
@@ -232,7 +235,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
         rb.add(row, col_v(c, nu_i), 1, 2, 0);
         rb.add(row, col_next(c, nu_i), 1, 0, 0);
       }
-      for (int c = 0; c < nv; ++c) {  // dv_next - (dv + a dt)
+      for (int c = 0; c < nv && !noacc; ++c) {  // dv_next - (dv + a dt)
         int row = rb.new_row();
         if (kind == PLM_WHOLE_BODY_ABA) {
           for (int d = 3; d < nv; ++d) rb.add(row, col_dq(d), 0, PLM_SRC_TQ, c * nv + d);
@@ -268,7 +271,8 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
             if (!rel) continue;
             if (q_cols_ok(c)) rb.add(row, col_dq(c), 0, PLM_SRC_TQ, r * nv + c);
             rb.add(row, col_v(c, nu_i), 0, PLM_SRC_TV, r * nv + c);
-            rb.add(row, col_lead(c), 0, PLM_SRC_TA, r * nv + c);
+            if (noacc) rb.add(row, col_next(nv + c, nu_i), 0, PLM_SRC_TN, r * nv + c);      // a = (dv_next - dv) / dt
+            else rb.add(row, col_lead(c), 0, PLM_SRC_TA, r * nv + c);
           }
           for (int k = 0; k < M.ncontact; ++k) {
             if (!is_anc_or_self(M, rbody, M.contact_body[k])) continue;
@@ -408,14 +412,21 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     QpTypeIdx& I = Q.type[t];
     I.rptr = push(rptr); I.ccol = push(ccol); I.cptr = push(cptr); I.cpos = push(cpos); I.crow = push(crow);
     I.ncols = ncols; I.s = s;
-    // structural assumptions of the stage solver: the first ndx rows are the integrator rows, each with
-    // exactly one entry in DX_{i+1} (its last entry, at next-column r); no other row touches DX_{i+1}
+    // structure the stage solver exploits: the first ndx rows are the integrator rows, each with exactly one entry in
+    // DX_{i+1} (its last entry, at next-column r), and no other row touches DX_{i+1}; anything else takes the
+    // general-coupling path (tables of the coupling rows below)
+    std::vector<int> gc_rows, gc_rowq(rows.size(), -1);
     for (size_t r = 0; r < rows.size(); ++r) {
       int nnext = 0;
       for (int c : rows[r]) if (c >= s) nnext++;
       const bool integ = (int)r < ndx;
-      if (integ ? (nnext != 1 || rows[r].back() != s + (int)r) : nnext != 0) { out.error = "unexpected stage coupling pattern"; return false; }
+      if (integ ? (nnext != 1 || rows[r].back() != s + (int)r) : nnext != 0) Q.general_coupling = 1;
+      if (nnext > 0) { gc_rowq[r] = (int)gc_rows.size(); gc_rows.push_back((int)r); }
     }
+    I.ncoup = (int)gc_rows.size();
+    I.gc_rows = push(gc_rows);
+    I.gc_rowq = push(gc_rowq);
+    Q.ncoup_max = std::max(Q.ncoup_max, I.ncoup);
   }
   {
     // flat CSR / CSC of the whole pattern (value order = CSR order)
@@ -460,8 +471,8 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     build_ell(rperm, rptr, nullptr, rcol, Q.f_rell_base, Q.f_rell_src, Q.f_rell_ind, Q.n_rslices, Q.rell_total);
     build_ell(cperm, tptr, &tsrc, trow, Q.f_cell_base, Q.f_cell_src, Q.f_cell_ind, Q.n_cslices, Q.cell_total);
   }
-  Q.sparse_coupling = 1;
-  for (int t = 0; t < L.ntypes; ++t)
+  Q.sparse_coupling = Q.general_coupling ? 0 : 1;
+  for (int t = 0; t < L.ntypes && !Q.general_coupling; ++t)
     for (int r = 0; r < ndx; ++r)
       if ((int)out.type_rowcols[t][r].size() - 1 > 4) Q.sparse_coupling = 0;
   Q.smax = 0;

@@ -116,7 +116,12 @@ PLM_HD void node_phase_a(NodeWs& ws, const NodeArgs& A, int lane) {
     ws.cq[lane] = dx[dqoff + lane];
     // without base inputs the leading block of U holds the joint part only; the base part starts at zero and is
     // solved for after the first pass (node_phase_base_solve)
-    const double ulead = L.nobase ? (lane >= 6 ? u[lane - 6] : 0.0) : ((KIND == PLM_WHOLE_BODY_ABA) ? 0.0 : u[lane]);
+    double ulead = L.nobase ? (lane >= 6 ? u[lane - 6] : 0.0) : ((KIND == PLM_WHOLE_BODY_ABA) ? 0.0 : u[lane]);
+    if (KIND == PLM_WHOLE_BODY_RNEA && L.noacc) {
+      // no acceleration inputs: a = (v_{i+1} - v_i) / dt_i = (dv_{i+1} - dv_i) / dt_i   (ocp_whole_body_rnea.py:183-191)
+      const double* dxn = A.xs + L.ndx + A.T->nu;
+      ulead = (dxn[nv + lane] - dx[nv + lane]) / A.dt;
+    }
     if (KIND == PLM_CENTROIDAL_VEL) {
       ws.cv[lane] = ulead;
       ws.ca[lane] = 0.0;
@@ -547,8 +552,14 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
       double vv = dot6(cr, st.dFv);
       double vq = dot6(cr, same ? st.dFqn : st.dFq);
       if (NOBASE) { oa[a] = va; ov[a] = vv; oq[a] = vq; continue; }
-      emit(ws, A, PLM_SRC_TA, c * nv + lane, va);
-      emit(ws, A, PLM_SRC_TV, c * nv + lane, vv);
+      if (KIND == PLM_WHOLE_BODY_RNEA && L.noacc) {      // a = (dv_next - dv) / dt: the a-column moves to dv (-1/dt) and dv_next (+1/dt)
+        const double vn = va / A.dt;
+        emit(ws, A, PLM_SRC_TN, c * nv + lane, vn);
+        emit(ws, A, PLM_SRC_TV, c * nv + lane, vv - vn);
+      } else {
+        emit(ws, A, PLM_SRC_TA, c * nv + lane, va);
+        emit(ws, A, PLM_SRC_TV, c * nv + lane, vv);
+      }
       emit(ws, A, PLM_SRC_TQ, c * nv + lane, vq);
       if (!same && jr) {
         // row = this lane's column (descendant), column = ancestor c
@@ -561,8 +572,14 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
           point_wrench(ws.con[k], g, wr);
           tq += dot6(st.J, wr);
         }
-        emit(ws, A, PLM_SRC_TA, lane * nv + c, va);
-        emit(ws, A, PLM_SRC_TV, lane * nv + c, tv);
+        if (KIND == PLM_WHOLE_BODY_RNEA && L.noacc) {
+          const double vn = va / A.dt;
+          emit(ws, A, PLM_SRC_TN, lane * nv + c, vn);
+          emit(ws, A, PLM_SRC_TV, lane * nv + c, tv - vn);
+        } else {
+          emit(ws, A, PLM_SRC_TA, lane * nv + c, va);
+          emit(ws, A, PLM_SRC_TV, lane * nv + c, tv);
+        }
         emit(ws, A, PLM_SRC_TQ, lane * nv + c, tq);
       }
     }
@@ -833,7 +850,7 @@ PLM_HD void node_phase_f(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
       ws.g[T.row_int + 6 + lane] = dxn[6 + lane] - (dx[6 + lane] + ws.cv[lane] * dt);
     } else {
       ws.g[T.row_int + lane] = dxn[lane] - (dx[lane] + ws.cv[lane] * dt);
-      ws.g[T.row_int + nv + lane] = dxn[nv + lane] - (dx[nv + lane] + ws.ca[lane] * dt);
+      if (!L.noacc) ws.g[T.row_int + nv + lane] = dxn[nv + lane] - (dx[nv + lane] + ws.ca[lane] * dt);
     }
   }
   // ---- joint rows: torque bounds, joint position / velocity bounds

@@ -86,7 +86,10 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   const double* q = qin ? qin + (size_t)b * n : nullptr;
   double* Dg = W.D + (size_t)b * n;      // also the exchange buffers of the Jacobi-style update
   double* Eg = W.E + (size_t)b * m;
-  const double* A = Ag;     // read from L2 in every pass: staging 160 KB of values would leave one CTA per SM
+  // A is read from L2 in every pass.  Keeping the values in shared memory instead (one 1024-thread CTA per SM, measured in
+  // round 2) gives the same time (17.7 vs 18 ms at 8192 instances): the passes are bound by the index-table loads and the
+  // divergent row / column walks, not by the traffic of the values.
+  const double* A = Ag;
   for (int j = tid; j < n; j += nth) D[j] = 1.0;
   for (int r = tid; r < m; r += nth) E[r] = 1.0;
   double c = 1.0;
@@ -172,7 +175,7 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
 // ------------------------------------------------------------------------------------------------------------
 // Factorisation.  Packed lower-triangular storage: element (i, j <= i) at i(i+1)/2 + j.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+__device__ __forceinline__ int tri(int i, int j) { return ((i * (i + 1)) >> 1) + j; }      // (i (i+1) is even and >= 0: shift, not signed division)
 
 // D = A B + C on the FP64 tensor cores (DMMA m8n8k4).  Lane l holds A[l/4][l%4] (8x4, row major), B[l%4][l/4] (4x8,
 // column major) and C / D [l/4][2 (l%4) + {0, 1}] (8x8).
@@ -313,7 +316,8 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       }
       __syncthreads();
       {
-        const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int nw = QP_THREADS >> 5;      // compile-time warp count: the round-robin arithmetic below must not divide
         const int R0 = k + 4, ntr = (s - R0 + 7) >> 3;
         const int fr = lane >> 2, fk = lane & 3;
         // tiles of the lower triangle, dealt round robin to the warps (running tile count, no division)
@@ -401,7 +405,8 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     // ---- S_i^-1 = X^T X (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit).
     // 8x8 output tiles on the FP64 tensor cores: S[r][c] = sum_{t >= r} X[t][r] X[t][c], four rows t of X per DMMA.
     {
-      const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+      const int warp = tid >> 5, lane = tid & 31;
+      constexpr int nw = QP_THREADS >> 5;
       const int nt8 = (s + 7) >> 3;
       const int fr = lane >> 2, fk = lane & 3;
       double* So = Lout + Q.fac_off[i];
@@ -431,7 +436,7 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     }
     if (last) break;
     // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = X G^T ; K = W^T W
-    for (int c2 = tid; c2 < ndx; c2 += nth) {
+    for (int c2 = tid; c2 < ndx && !Q.general_coupling; c2 += nth) {
       const int elast = sv.rptr[c2 + 1] - 1;              // next entry of integrator row c2
       const double nn = As[elast];
       gsc[c2] = rs[c2] * nn * nn;
@@ -478,6 +483,45 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       __syncthreads();
       continue;
     }
+    if (Q.general_coupling) {
+      // Any row of the node may touch DX_{i+1} (whole_body_rnea without acceleration inputs: RNEA rows depend on dv_{i+1}).
+      // With a_q / n_q the own-stage / DX_{i+1} part of coupling row q:  G = sum_q rho_q n_q a_q^T,  W = X G^T, i.e.
+      // W[t][c] = sum_q n_q[c] Y[t][q],  Y[t][q] = rho_q (X a_q)[t];  the carry sum_q rho_q n_q n_q^T replaces the diagonal gsc.
+      const QpTypeIdx& I = Q.type[L.node_type[i]];
+      const int16_t* crows = idx + I.gc_rows;
+      const int nc = I.ncoup, ncm = Q.ncoup_max;
+      double* Y = rs + L.max_rows;          // [smax][ncm]
+      double* Nn = Y + smax * ncm;          // [ncm][ndx]
+      for (int o = tid; o < nc * ndx; o += nth) Nn[o] = 0.0;
+      for (int c2 = tid; c2 < ndx; c2 += nth) gsc[c2] = 0.0;
+      __syncthreads();
+      for (int q = tid; q < nc; q += nth) {
+        const int r = crows[q];
+        for (int e = sv.rptr[r]; e < sv.rptr[r + 1]; ++e)
+          if (sv.ccol[e] >= s) Nn[q * ndx + sv.ccol[e] - s] = As[e];
+      }
+      const int s32 = (s + 31) & ~31;
+      for (int o = tid; o < s32 * nc; o += nth) {
+        const int q = o / s32, t = o - q * s32;
+        if (t >= s) continue;
+        const int r = crows[q];
+        const double* Xt = H + tri(t, 0);
+        double acc = 0.0;
+        for (int e = sv.rptr[r]; e < sv.rptr[r + 1]; ++e) {
+          const int k = sv.ccol[e];
+          if (k > t) break;                 // (columns ascending: the rest is above the diagonal of X or in DX_{i+1})
+          acc += As[e] * Xt[k];
+        }
+        Y[t * ncm + q] = rs[r] * acc;
+      }
+      __syncthreads();
+      for (int o = tid; o < s * ndx; o += nth) {
+        const int t = o / ndx, c2 = o - t * ndx;
+        double acc = 0.0;
+        for (int q = 0; q < nc; ++q) acc += Nn[q * ndx + c2] * Y[t * ncm + q];
+        Wm[t * ndx + c2] = acc;
+      }
+    } else
     {   // lanes of a warp share the integrator row c2 (uniform entry loop: dense and sparse rows do not mix) and take
         // consecutive rows t of X
       const int s32 = (s + 31) & ~31;
@@ -519,7 +563,14 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       int t = 0;
       for (; t + 1 < s; t += 2) { a0 += Wm[t * ndx + r] * Wm[t * ndx + c2]; a1 += Wm[(t + 1) * ndx + r] * Wm[(t + 1) * ndx + c2]; }
       if (t < s) a0 += Wm[t * ndx + r] * Wm[t * ndx + c2];
-      K[o] = a0 + a1;
+      double carry = 0.0;                   // general coupling: H_{i+1,i+1} += sum_q rho_q n_q n_q^T (K is subtracted from H)
+      if (Q.general_coupling) {
+        const QpTypeIdx& I = Q.type[L.node_type[i]];
+        const int16_t* crows = idx + I.gc_rows;
+        const double* Nn = rs + L.max_rows + smax * Q.ncoup_max;
+        for (int q = 0; q < I.ncoup; ++q) carry += rs[crows[q]] * Nn[q * ndx + r] * Nn[q * ndx + c2];
+      }
+      K[o] = a0 + a1 - carry;
     }
     __syncthreads();
   }
@@ -591,6 +642,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Experiment switch: L2 prefetch of the panel PLM_ADMM_PREFETCH_STEPS schedule steps ahead of the shared-memory ring (no
+// shared memory needed), so that the ring's own bulk copies hit L2.  It does not pay: the kernel is bound by the
+// instruction / barrier chain of a CTA, not by the latency of its panel loads.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+#ifndef PLM_ADMM_PREFETCH_STEPS
+#define PLM_ADMM_PREFETCH_STEPS 0   // measured (round 2, tools/admm_quick.sh): 4 steps ahead 592 instances 24.2 -> 25.6 ms, 148 instances (latency kernel) 10.2 -> 10.4 ms: no gain, off
+#endif
 #ifndef PLM_MBAR_SUSPEND_NS
 #define PLM_MBAR_SUSPEND_NS 1000
 #endif
@@ -769,6 +829,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* cpart = xt + n + (ALIAS ? 0 : m);       // [CP_SLICES][smax]
   double* red = cpart + CP_SLICES * smax;     // [32]
   double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
+  double* gcs = zp + 2;        // [ncoup_max] general coupling only: rho_q (a_q . tv_{i-1}) of the coupling rows
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
   const double* AR = W.AhatR + (size_t)b * Q.rell_total;
@@ -834,6 +895,12 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     mbar_expect_tx(&bars[buf], bytes + (with_g ? (unsigned)gd * 8u : 0u));
     bulk_g2s(pbuf + (size_t)buf * pdb, Lf + S0.x, bytes, &bars[buf]);
     if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
+    if (PLM_ADMM_PREFETCH_STEPS > 0) {      // the panel PLM_ADMM_PREFETCH_STEPS steps further on (wraps into the next iteration)
+      int pf = st + PLM_ADMM_PREFETCH_STEPS;
+      if (pf >= nsched) pf -= nsched;
+      const int4 P0 = __ldg(reinterpret_cast<const int4*>(sched + pf * PLM_SCHED_INTS));
+      bulk_prefetch_l2(Lf + P0.x, (unsigned)P0.y * 8u);
+    }
   };
   if (!ALIAS && tid == 0)
     for (int k = 0; k < NB; ++k) issue_step(k, k);
@@ -921,7 +988,37 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
               return v;
             };
             if (tid < L.x_off[i] - L.x_off[i - 1]) xt[L.x_off[i - 1] + tid] = tprev(tid);
-            if (sparse) {
+            if (Q.general_coupling) {
+              // b_i -= sum_q n_q rho_q (a_q . tv_{i-1}) over the coupling rows q of node i-1 (see the factor kernel)
+              const QpTypeIdx& I = Q.type[L.node_type[i - 1]];
+              const int16_t* crows = idx + I.gc_rows;
+              const int16_t* rowq = idx + I.gc_rowq;
+              const double* Ap = Ah + L.nnz_off[i - 1];
+              const double* rp = rho + L.row_off[i - 1];
+              const int sub = tid & 7, sprev = sp.s;
+              for (int q0 = 0; q0 < I.ncoup; q0 += nth >> 3) {
+                const int q = q0 + (tid >> 3);
+                double acc = 0.0;
+                int r = 0;
+                if (q < I.ncoup) {
+                  r = crows[q];
+                  for (int e = sp.rptr[r] + sub; e < sp.rptr[r + 1]; e += 8) {
+                    const int k = sp.ccol[e];
+                    if (k < sprev) acc += Ap[e] * tprev(k);
+                  }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (q < I.ncoup && sub == 0) gcs[q] = rp[r] * acc;
+              }
+              __syncthreads();
+              if (tid < ndx) {
+                double acc = 0.0;
+                for (int e = sp.cptr[sprev + tid]; e < sp.cptr[sprev + tid + 1]; ++e) acc += Ap[sp.cpos[e]] * gcs[rowq[sp.crow[e]]];
+                bi[tid] -= acc;
+              }
+            } else if (sparse) {
               if (tid < ndx) {
                 const int e0 = sp.rptr[tid], ne = sp.rptr[tid + 1] - 1 - e0;
                 double acc = 0.0;
@@ -1237,9 +1334,11 @@ int plm_qp_alloc(plm_handle* h) {
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
   h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 8 * smax + L.max_nnz + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
+  if (Q.general_coupling) h->smem_factor += (size_t)(smax * Q.ncoup_max + Q.ncoup_max * ndx) * 8;     // Y, Nn
   // throughput kernel: w aliases the panel ring
-  h->smem_admm = (size_t)(((std::max(NBUF * (Q.panel_doubles + Q.g_doubles), L.m) + 1) & ~1) + 2 * NBUF + L.n + 2 * (ADMM_THREADS / SYM_K) * smax + 32 + 2 + 16) * 8;
-  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + 2 * (ADMM_THREADS_LAT / SYM_K) * smax + 32 + 2 + 16) * 8;
+  const int gcn = Q.general_coupling ? Q.ncoup_max : 0;
+  h->smem_admm = (size_t)(((std::max(NBUF * (Q.panel_doubles + Q.g_doubles), L.m) + 1) & ~1) + 2 * NBUF + L.n + 2 * (ADMM_THREADS / SYM_K) * smax + 32 + 2 + 16 + gcn) * 8;
+  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + 2 * (ADMM_THREADS_LAT / SYM_K) * smax + 32 + 2 + 16 + gcn) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024 || h->smem_admm_lat > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";

@@ -26,6 +26,10 @@ struct QpTypeIdx {
   int32_t crow;   // [nnz]      local row of each CSC entry
   int32_t ncols;  // s + ndx
   int32_t s;      // stage size ndx + nu
+  // general coupling (QpLayout::general_coupling): the rows with entries in DX_{i+1}
+  int32_t gc_rows;   // [ncoup]  local row of coupling row q
+  int32_t gc_rowq;   // [nrows]  q of a local row, -1 if the row does not touch DX_{i+1}
+  int32_t ncoup;
 };
 
 struct QpLayout {
@@ -35,6 +39,12 @@ struct QpLayout {
   int32_t f_rptr, f_tptr, f_tsrc, f_rcol, f_trow;
   int32_t f_rperm, f_cperm;            // int16 pool: rows / columns sorted by descending length (balanced warps)
   int32_t sparse_coupling;             // every integrator row has at most 4 entries in its own stage (all but whole_body_aba / centroidal_vel)
+  // general_coupling = 0: the first ndx rows of every node are the integrator rows, each with exactly one entry in
+  // DX_{i+1} (its last one, at next-column r), and no other row touches DX_{i+1}.  1: any row may touch DX_{i+1}
+  // (whole_body_rnea without acceleration inputs: the RNEA rows depend on dv_{i+1}); the coupling block
+  // H_{i+1,i} = sum_q rho_q n_q a_q^T and the carry sum_q rho_q n_q n_q^T are formed from the coupling rows q
+  // (a_q: own-stage part, n_q: DX_{i+1} part of row q)
+  int32_t general_coupling, ncoup_max;
   // sliced-ELL copies of A^ for the ADMM products (see plm_host.cpp): slice bases / source positions (int32 pool), indices (int16 pool)
   int32_t f_rell_base, f_rell_src, f_rell_ind, n_rslices, rell_total;
   int32_t f_cell_base, f_cell_src, f_cell_ind, n_cslices, cell_total;

@@ -66,6 +66,7 @@ enum PlmSrc {
   PLM_SRC_IH,       // [6][6]  centroidal_vel without base inputs: d(base dq-integrator rows)/d dh
   PLM_SRC_FH,       // [nfeet][3][6]  "  : d(foot velocity rows)/d dh
   PLM_SRC_AH,       // [3][6]         "  : d(arm rows)/d dh
+  PLM_SRC_TN,       // [nv][nv] whole_body_rnea without acceleration inputs: d(dynamics rows)/d dv_{i+1}
   PLM_SRC_COUNT
 };
 
@@ -105,6 +106,7 @@ struct PlmNodeType {
 struct PlmLayout {
   int32_t dynamics, nodes, tau_nodes;
   int32_t nobase;                      // include_base = False: inputs without the base part, no dynamics-gap rows
+  int32_t noacc;                       // include_acc = False (whole_body_rnea): a = (v_{i+1} - v_i) / dt, no dv integrator rows
   int32_t nx, ndx, n, m, np, nnz;
   int32_t nf;
   int32_t f_idx, tau_idx, lead;    // offsets inside U_i: forces, torques; size of the leading block (a / v / tau_j)

@@ -27,7 +27,7 @@ def _check_in(t, shape_tail, name):
 class Handle:
     """One problem formulation (robot x dynamics x horizon) on one GPU."""
 
-    def __init__(self, robot, dynamics, nodes, max_batch, tau_nodes=3, device=None, include_base=True, **osqp_opts):
+    def __init__(self, robot, dynamics, nodes, max_batch, tau_nodes=3, device=None, include_base=True, include_acc=True, **osqp_opts):
         if dynamics not in _lib.DYNAMICS_ID:
             raise ValueError(f"Unknown dynamics type: {dynamics}")
         self.layout_only = int(max_batch) == 0     # layout queries only (host-logic tests); no compute
@@ -44,6 +44,7 @@ class Handle:
         self.lib.plm_fill_default_ocp_desc(ctypes.byref(od), _lib.DYNAMICS_ID[dynamics], nodes)
         od.tau_nodes = tau_nodes
         od.include_base = int(bool(include_base))
+        od.include_acc = int(bool(include_acc))
         for k, v in osqp_opts.items():
             setattr(od, "osqp_" + k, v)
         self.ocp_desc = od

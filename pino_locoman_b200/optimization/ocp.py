@@ -108,7 +108,7 @@ class OCP:
         """Create the library handle: fixes the x layout [DX_0, U_0, ..., DX_N] and the row layout of g."""
         self.handle = Handle(self.robot, self.dynamics, self.nodes, 0 if self.device == "layout" else self.batch,
                              tau_nodes=max(self.tau_nodes, 1), device=None if self.device == "layout" else self.device,
-                             include_base=getattr(self, "include_base", True))
+                             include_base=getattr(self, "include_base", True), include_acc=getattr(self, "include_acc", True))
         h = self.handle
         self.nx, self.ndx_opt, self.nu_opt = h.nx, h.ndx, list(h.nu)
         self.n, self.m = h.n, h.m

@@ -11,13 +11,13 @@ class OCPWholeBodyRNEA(OCP):
 
     def __init__(self, robot, solver, nodes, tau_nodes, include_acc=True, batch=1, device=None):
         super().__init__(robot, solver, nodes, batch=batch, device=device)
-        if not include_acc:
-            raise NotImplementedError("include_acc=False (finite-difference accelerations) is not available yet")
         if not 1 <= tau_nodes <= nodes:
             raise ValueError("tau_nodes must be in [1, nodes]")
         self.tau_nodes = tau_nodes
-        self.include_acc = include_acc
-        self.na_opt = self.nv
+        # include_acc=False: no acceleration inputs, a_i = (v_{i+1} - v_i) / dt_i inside the node kernel and no dv
+        # integrator rows (ocp_whole_body_rnea.py:21-25,156,183-191); the RNEA rows then couple stage i with dv_{i+1}
+        self.include_acc = bool(include_acc)
+        self.na_opt = self.nv if self.include_acc else 0
         self.x_nom = np.concatenate((robot.q0, np.zeros(self.nv)))
         self.tau_sol = []
         self.f_idx = self.na_opt

@@ -16,11 +16,11 @@ class OcpDesc(ctypes.Structure):
                 ("osqp_scaling", ctypes.c_int32), ("osqp_rho", ctypes.c_double), ("osqp_sigma", ctypes.c_double),
                 ("osqp_alpha", ctypes.c_double), ("osqp_eps_abs", ctypes.c_double), ("osqp_eps_rel", ctypes.c_double),
                 ("osqp_eps_prim_inf", ctypes.c_double), ("osqp_eps_dual_inf", ctypes.c_double),
-                ("include_base", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("include_base", ctypes.c_int32), ("include_acc", ctypes.c_int32)]
 
 
-def default_ocp_desc(dynamics, nodes, tau_nodes=3, include_base=True):
-    return OcpDesc(DYN_ID[dynamics], nodes, tau_nodes, 0.7, 100, 25, 10, 2e-2, 1e-6, 1.4, 1e-3, 1e-3, 1e-4, 1e-4, int(include_base), 0)
+def default_ocp_desc(dynamics, nodes, tau_nodes=3, include_base=True, include_acc=True):
+    return OcpDesc(DYN_ID[dynamics], nodes, tau_nodes, 0.7, 100, 25, 10, 2e-2, 1e-6, 1.4, 1e-3, 1e-3, 1e-4, 1e-4, int(include_base), int(include_acc))
 
 
 def build_emu():
@@ -36,11 +36,11 @@ def build_emu():
 
 
 class Emu:
-    def __init__(self, robot, dynamics, nodes, tau_nodes=3, include_base=True):
+    def __init__(self, robot, dynamics, nodes, tau_nodes=3, include_base=True, include_acc=True):
         from pino_locoman_b200.utils.robot import robot_desc
         self.lib = build_emu()
         self.rd = robot_desc(robot)
-        self.od = default_ocp_desc(dynamics, nodes, tau_nodes, include_base)
+        self.od = default_ocp_desc(dynamics, nodes, tau_nodes, include_base, include_acc)
         err = ctypes.create_string_buffer(256)
         self.h = self.lib.emu_create(ctypes.byref(self.rd), ctypes.byref(self.od), err, 256)
         if not self.h:

@@ -46,7 +46,8 @@ def test_cport_rows_and_jacobian(cport, rn, kind, N):
 
 
 @pytest.mark.parametrize("rn,kind,N,iters,kw", [("b2g", "whole_body_rnea", 5, 3, {}), ("b2", "centroidal_acc", 5, 2, {}), ("go2", "centroidal_vel", 4, 2, {}),
-                                                ("b2", "centroidal_acc", 4, 2, {"include_base": False})])
+                                                ("b2", "centroidal_acc", 4, 2, {"include_base": False}),
+                                                ("b2", "whole_body_rnea", 5, 3, {"include_acc": False})])
 def test_cport_sqp_iterations_match_numpy_oracle(cport, rn, kind, N, iters, kw):
     rng = np.random.default_rng(8)
     o = OracleOCP(OracleRobot(rn), kind, N, **kw)

@@ -122,3 +122,49 @@ def test_plugin_surface_mpc_loop(robots, rn, kind):
         hq = np.concatenate((ocp.h_sol[-1], ocp.q_sol[-1]), 1)
         vb = oracles[0].dyn.base_vel_dynamics()(hq[0, :6], hq[0, 6:], ocp.v_sol[-1][0, 6:])
         assert np.abs(vb - ocp.v_sol[-1][0, :6]).max() <= 1e-9 * max(1.0, np.abs(vb).max())
+
+
+def test_rnea_without_acceleration_inputs(robots, monkeypatch):
+    """include_acc=False (ocp_whole_body_rnea.py:21-25,156,183-191): a_i = (v_{i+1} - v_i) / dt_i, no dv integrator rows; the
+    RNEA rows touch dv_{i+1}, which the QP kernels handle on their general-coupling path.  Rows / Jacobian on random
+    states, then warm-started SQP iterations on both instantiations of the ADMM kernel."""
+    from pino_locoman_b200.handle import Handle
+    prod, ora = robots
+    rng = np.random.default_rng(42)
+    for rn, N in (("b2", 6), ("b2g", 5)):
+        o = OracleOCP(ora[rn], "whole_body_rnea", N, include_acc=False)
+        h = Handle(prod[rn], "whole_body_rnea", N, max_batch=2, include_acc=False)
+        assert (h.n, h.m, h.np) == (o.n, o.m, o.np_)
+        probs = [random_problem(o, rng) for _ in range(2)]
+        x = torch.tensor(np.stack([q[0] for q in probs]), device="cuda")
+        p = torch.tensor(np.stack([q[1] for q in probs]), device="cuda")
+        grad, J, g, lbg, ubg = h.sqp_data(x, p)
+        Jd = h.jac_dense(J).cpu().numpy()
+        for b, (xb, pb) in enumerate(probs):
+            g_ref, lb_ref, ub_ref = o.g_data(xb, pb)
+            J_ref = o.jac_g(xb, pb)
+            assert np.abs(g[b].cpu().numpy() - g_ref).max() <= 1e-9 * max(1.0, np.abs(g_ref).max())
+            assert np.abs(Jd[b] - J_ref).max() <= 1e-9 * np.abs(J_ref).max()
+            assert np.array_equal(lbg[b].cpu().numpy(), lb_ref) and np.array_equal(ubg[b].cpu().numpy(), ub_ref)
+    for variant in ("throughput", "latency"):
+        monkeypatch.setenv("PLM_ADMM_LATENCY_MAX_BATCH", "0" if variant == "throughput" else "1000000")
+        for rn, N in (("b2", 6), ("b2g", 20)):
+            B, iters = 2, 3
+            ocps = [OracleOCP(ora[rn], "whole_body_rnea", N, include_acc=False) for _ in range(B)]
+            xs, ps = zip(*[nominal_problem(o, rng, k) for o, k in zip(ocps, (0, 37))])
+            sqps = [OracleSQP(o) for o in ocps]
+            for s in sqps:
+                s.init_solver()
+            h = Handle(prod[rn], "whole_body_rnea", N, max_batch=B, include_acc=False)
+            x = torch.tensor(np.stack(xs), device="cuda")
+            p = torch.tensor(np.stack(ps), device="cuda")
+            xr = [np.array(v) for v in xs]
+            for it in range(iters):
+                x, stats = h.sqp_step(x, p)
+                stats = stats.cpu().numpy()
+                for b in range(B):
+                    xr[b], info = sqps[b].solve(xr[b], ps[b])
+                    assert int(stats[b, 0]) == info["qp_iters"], (variant, rn, it, b, stats[b], info["qp_iters"])
+                    assert bool(stats[b, 2]) == info["accepted"] and int(stats[b, 4]) == info["trials"], (variant, rn, it, b)
+                    assert np.abs(x[b].cpu().numpy() - xr[b]).max() <= 1e-6 * max(1.0, np.abs(xr[b]).max()), (variant, rn, it, b)
+                    assert abs(stats[b, 5] - info["f"]) <= 1e-6 * max(1.0, abs(info["f"]))

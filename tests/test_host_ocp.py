@@ -61,21 +61,21 @@ def test_factory_errors(robots):
                    device="layout")
     with pytest.raises(ValueError, match="not supported"):
         ocp.init_solver()
-    with pytest.raises(NotImplementedError):     # finite-difference accelerations: RNEA rows would couple stage i with dv_{i+1}
-        make_ocp(dynamics="whole_body_rnea", default_args={"tau_nodes": 3, "include_acc": False}, robot=prod["b2"], nodes=10, solver="osqp",
-                 device="layout")
 
 
-@pytest.mark.parametrize("rn,kind", [("b2", "centroidal_acc"), ("b2g", "whole_body_acc"), ("go2", "centroidal_vel"), ("b2g", "centroidal_vel")])
-def test_layout_without_base_inputs(robots, rn, kind):
-    """include_base=False: inputs (v_j | a_j, f), no gap rows; sizes and initial guess equal the oracle's."""
+@pytest.mark.parametrize("rn,kind,kw", [("b2", "centroidal_acc", {"include_base": False}), ("b2g", "whole_body_acc", {"include_base": False}),
+                                        ("go2", "centroidal_vel", {"include_base": False}), ("b2g", "centroidal_vel", {"include_base": False}),
+                                        ("b2g", "whole_body_rnea", {"tau_nodes": 3, "include_acc": False})])
+def test_layout_of_the_reduced_input_variants(robots, rn, kind, kw):
+    """include_base=False / include_acc=False: inputs (v_j | a_j, f) / (f, tau_j), no gap rows / no dv
+    integrator rows; sizes and initial guess equal the oracle's."""
     from oracle.ocp import OracleOCP
     prod, ora = robots
-    ocp = make_ocp(dynamics=kind, default_args={"include_base": False}, robot=prod[rn], nodes=8, solver="osqp", device="layout")
-    o = OracleOCP(ora[rn], kind, 8, include_base=False)
+    ocp = make_ocp(dynamics=kind, default_args=kw, robot=prod[rn], nodes=8, solver="osqp", device="layout")
+    o = OracleOCP(ora[rn], kind, 8, **kw)
     assert (ocp.n, ocp.m, ocp.handle.np) == (o.n, o.m, o.np_)
     assert list(ocp.handle.x_off[:9]) == [int(v) for v in o.x_off]
-    assert ocp.nu_opt[0] == prod[rn].nj + prod[rn].nf == o.nu[0]
+    assert ocp.nu_opt[0] == o.nu[0] and ocp.nu_opt[-1] == o.nu[-1]
     assert np.allclose(ocp.initial_guess()[0], o.initial_guess(), rtol=1e-12, atol=0)      # (two independent URDF loaders: masses agree to 1e-12)
     assert np.array_equal(ocp._get("R_diag")[0], o.params["R_diag"])
 

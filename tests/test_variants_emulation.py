@@ -65,17 +65,20 @@ def test_reference_initial_guess_point(robots):
         _check(prod[rn], ora[rn], kind, 3, rng, exact_guess=True)
 
 
-@pytest.mark.parametrize("rn,kind", [("b2", "centroidal_acc"), ("b2g", "whole_body_acc"), ("go2", "centroidal_vel"), ("b2g", "centroidal_vel"),
-                                     ("b2g", "centroidal_acc"), ("go2", "whole_body_acc")])
-def test_formulations_without_base_inputs(robots, rn, kind):
+@pytest.mark.parametrize("rn,kind,kw", [("b2", "centroidal_acc", {"include_base": False}), ("b2g", "whole_body_acc", {"include_base": False}),
+                                        ("go2", "centroidal_vel", {"include_base": False}), ("b2g", "centroidal_vel", {"include_base": False}),
+                                        ("b2g", "centroidal_acc", {"include_base": False}), ("go2", "whole_body_acc", {"include_base": False}),
+                                        ("b2g", "whole_body_rnea", {"include_acc": False}), ("b2", "whole_body_rnea", {"include_acc": False})])
+def test_formulations_without_base_inputs(robots, rn, kind, kw):
     """include_base=False (ocp_centroidal_vel.py:104-120, ocp_centroidal_acc.py:129-140, ocp_whole_body_acc.py:130-141): the base
-    velocity / acceleration is solved for from the six gap rows inside the node evaluation; rows and the chain-rule
-    Jacobian (dense base-integrator, foot- and arm-velocity rows) against the oracle's complex-step differentiation."""
+    velocity / acceleration is solved for from the six gap rows inside the node evaluation; include_acc=False
+    (ocp_whole_body_rnea.py:183-191): finite-difference accelerations.  Rows and the chain-rule Jacobian (dense base-integrator,
+    foot- and arm-velocity rows; RNEA rows reaching into dv_{i+1}) against the oracle's complex-step differentiation."""
     prod, ora = robots
     rng = np.random.default_rng(12)
     for exact in (False, True):
-        o = OracleOCP(ora[rn], kind, 3, include_base=False)
-        e = Emu(prod[rn], kind, 3, include_base=False)
+        o = OracleOCP(ora[rn], kind, 4, **kw)      # (N = 4 with tau_nodes = 3: both RNEA node types)
+        e = Emu(prod[rn], kind, 4, **kw)
         assert (e.n, e.m, e.np_) == (o.n, o.m, o.np_)
         x, p = random_problem(o, rng)
         if exact:
