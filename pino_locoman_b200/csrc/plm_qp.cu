@@ -86,9 +86,11 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   const double* q = qin ? qin + (size_t)b * n : nullptr;
   double* Dg = W.D + (size_t)b * n;      // also the exchange buffers of the Jacobi-style update
   double* Eg = W.E + (size_t)b * m;
-  // A is read from L2 in every pass.  Keeping the values in shared memory instead (one 1024-thread CTA per SM, measured in
-  // round 2) gives the same time (17.7 vs 18 ms at 8192 instances): the passes are bound by the index-table loads and the
-  // divergent row / column walks, not by the traffic of the values.
+  // A is read from L2 / HBM in every pass (27 GB at 8192 instances: the values do not survive in L2 between passes).
+  // Measured alternatives of round 2, none faster than this form (16.6 ms at 8192 instances; profiles/ncu_r02_summary.md):
+  // values resident in shared memory with one 1024-thread CTA per SM, thread per row (17.7 ms) or warp per sliced-ELL
+  // slice with packed index words (19 ms: barrier stalls of the 32-warp CTA take over); a whole warp per row / column of
+  // more than 32 entries with a shuffle reduction (16.4 ms).  55 % of the instructions are the two pass loops below.
   const double* A = Ag;
   for (int j = tid; j < n; j += nth) D[j] = 1.0;
   for (int r = tid; r < m; r += nth) E[r] = 1.0;
