@@ -514,7 +514,10 @@ def main():
         "phase_ms": {"eval": phase[0] / K, "qp_update": phase[1] / K, "qp_solve": phase[2] / K, "line_search": phase[3] / K},
         "qp": {"admm_iters_avg": Kavg, "line_search_trials_avg": Tavg, "accepted_frac": float(np.mean(accepted)), "nnz_F": nnzF},
         "roofline": {"kernel": "qp_admm_kernel", "bound": "hbm", "achieved": ach_admm, "peak": peak, "unit": "GB/s",
-                     "frac": ach_admm / peak, "traffic": traffic.get("qp_admm_kernel"), "peak_source": peak_src,
+                     "frac": ach_admm / peak, "traffic": traffic.get("qp_admm_kernel"),
+                     "traffic_source": "profiles/traffic.json: dram__bytes per instance of this round's kernels (ncu --set full, one wave of "
+                                       "592 instances; the counters overflow at 8192) x the batch: not measured in this run",
+                     "peak_source": peak_src,
                      "algorithmic_bytes": bytes_admm, "nnz_F_stored": nnzF, "nnz_F_minimal": nnzF_min,
                      "frac_minimal_factor": ach_admm_min / peak, "ms_per_step_kernel": ms_admm},
         "roofline_node_eval": {"kernel": "node_eval_kernel", "bound": "hbm", "achieved": ach_eval, "peak": peak, "unit": "GB/s",
