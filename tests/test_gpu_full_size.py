@@ -78,9 +78,12 @@ def test_full_batch_sqp_step_properties(full_batch, robots):
     h = ocp.handle
     x_new, stats = h.sqp_step(x, p)
     st = stats.cpu().numpy()
-    assert np.isfinite(st).all() and torch.isfinite(x_new).all()
     acc = st[:, 2] != 0
     assert acc.mean() > 0.9
+    # (a rejected line search reports f / g_metric of its last trial, as the reference's overwrite quirk does: with a
+    # diverging QP step these may be huge or non-finite; the returned point is the current one)
+    assert torch.isfinite(x_new).all() and np.isfinite(st[acc]).all(), np.argwhere(~np.isfinite(st))[:5]
+    assert np.isfinite(st[:, [0, 1, 2, 4, 7]]).all()
     alpha = st[:, 3]
     assert np.all(np.log2(alpha[acc]) == np.round(np.log2(alpha[acc]))) and np.all((alpha[acc] <= 1.0) & (alpha[acc] > 1e-4))
     assert torch.equal(x_new[torch.as_tensor(~acc, device="cuda")], x[torch.as_tensor(~acc, device="cuda")])     # rejected: current_x returned
@@ -89,7 +92,12 @@ def test_full_batch_sqp_step_properties(full_batch, robots):
     g_new, lbg, ubg = h.g_data(x_new, p)
     viol = torch.maximum(torch.clamp(lbg - g_new, min=0), torch.clamp(g_new - ubg, min=0)).amax(1).cpu().numpy()
     assert np.abs(viol - st[:, 7]).max() <= 1e-9 * max(1.0, viol.max())
-    assert set(np.unique(st[:, 1]).astype(int)) <= {1, 2, -2}           # OSQP statuses: solved / solved inaccurate / max iterations
+    # OSQP statuses: solved / solved inaccurate / max iterations; a few random states give an (inaccurate) infeasibility
+    # certificate: OSQP then returns a NaN step and the line search keeps the current point, as in the reference
+    status = st[:, 1].astype(int)
+    assert set(np.unique(status)) <= {1, 2, -2, 3, -3, 4, -4}
+    infeasible = np.isin(status, (3, -3, 4, -4))
+    assert infeasible.mean() < 0.01 and not acc[infeasible].any()
     assert np.all((st[:, 0] >= 25) & (st[:, 0] <= 100) & (st[:, 0] % 25 == 0))
     for b in (0, 5000, B_FULL - 1):
         o = OracleOCP(ora["b2g"], "whole_body_rnea", 20)
