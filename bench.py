@@ -389,16 +389,18 @@ def main():
         o1.init_solver()
         x1 = torch.from_numpy(o1.initial_guess()).to(dev)
         p1 = o1._p_device()
-        ts = []
-        for k in range(6):
+        ts, phs, its1 = [], [], []
+        for k in range(7):
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
-            x1, _ = o1.handle.sqp_step(x1, p1)
+            x1, st1 = o1.handle.sqp_step(x1, p1)
             a1.record()
             torch.cuda.synchronize()
             ts.append(a0.elapsed_time(a1))
-        single_ms = float(np.median(ts[1:]))
-        single_phase = [float(v) for v in o1.handle.last_phase_ms()]
+            phs.append([float(v) for v in o1.handle.last_phase_ms()])
+            its1.append(float(st1[0, 0]))
+        kmed = 1 + int(np.argsort(ts[1:])[len(ts[1:]) // 2])       # the call with the median time (ADMM iterations vary: 25 .. 100)
+        single_ms, single_phase, single_iters = float(ts[kmed]), phs[kmed], its1[kmed]
         launches += o1.handle.launch_count()
         del o1
     # ---- the other BASELINE configs (parity-test cases; measured here as extra keys, rank 0 only):
@@ -536,7 +538,7 @@ def main():
                    "hbm_floor_note": "instances x ADMM iterations x (8 nnz(F) + 8 (3n + 4m)) bytes / measured HBM peak: the factor of an "
                                      "instance (1.36 MB) is re-read every iteration and 512 of them (0.7 GB) do not fit the 126 MB L2"},
         "single_instance": {"workload": "b2 whole_body_rnea trot N=20, 1 instance (BASELINE configs[1])", "ms_per_sqp_iter": single_ms,
-                            "phase_ms": dict(zip(("eval", "qp_update", "qp_solve", "line_search"), single_phase))},
+                            "phase_ms": dict(zip(("eval", "qp_update", "qp_solve", "line_search"), single_phase)), "admm_iters": single_iters},
         "other_configs": other,
         "gpu_launches": int(launches_timed), "gpu_launches_all_legs": int(launches),
         "clocks": sampler.summary(),
