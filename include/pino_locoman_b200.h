@@ -145,6 +145,15 @@ int plm_base_solve(plm_handle* h, int32_t dynamics, const double* d_h, const dou
  * d_vel is [batch][3]. */
 int plm_frame_vel(plm_handle* h, int32_t contact, int32_t relative_to_base, const double* d_q, const double* d_v,
                   int32_t batch, double* d_vel, void* stream);
+/* frame_pos(q) -> pos [batch][3] and frame_vel(q, v) -> vel [batch][6] of ANY frame (dynamics/dynamics.py:67-118): the
+ * frame is given by its parent body (0 = free-flyer root, b > 0 = revolute joint b) and its placement in that body's
+ * joint frame (placement12 = R row-major (9) | p (3), host memory).  vel = getFrameVelocity(LOCAL_WORLD_ALIGNED) =
+ * [linear; angular]; with relative_to_base != 0 the reference's base-relative variant (dynamics.py:86-113, z components
+ * kept in the world frame), the base frame given the same way (base_placement12 NULL = identity).  d_pos or d_vel may
+ * be NULL; d_v may be NULL when d_vel is. */
+int plm_frame_kinematics(plm_handle* h, int32_t body, const double* placement12, int32_t base_body, const double* base_placement12,
+                         int32_t relative_to_base, const double* d_q, const double* d_v, int32_t batch, double* d_pos, double* d_vel,
+                         void* stream);
 
 /* ---- OSQP equivalents (optimization/ocp.py:312-313,395,401) -------------------------------------- */
 /* setup(P, q=1, A=ones(pattern), l=-1, u=1) of optimization/ocp.py:305-313: zero the persistent ADMM iterates

@@ -57,6 +57,8 @@ SIGNATURES = {
     "plm_base_solve": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.c_int32, vp, vp]),
     "plm_mpc_step": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_double, ctypes.c_int32, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]),
     "plm_frame_vel": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp]),
+    "plm_frame_kinematics": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp]),
     "plm_qp_setup": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp]),
     "plm_qp_update": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp, vp, vp]),
     "plm_qp_solve": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp]),

@@ -105,6 +105,7 @@ static void probe_free(plm_probe* pr) {
 }
 
 void plm_dyn_free(plm_handle* h) {
+  cudaFree(h->d_frame_plc);
   for (int k = 0; k < 5; ++k) { probe_free(h->probes[k]); h->probes[k] = nullptr; }
 }
 
@@ -355,6 +356,104 @@ int plm_frame_vel(plm_handle* h, int32_t contact, int32_t relative_to_base, cons
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = run_probe(h, pr, batch, d_q, M.nq, d_v, M.nv, nullptr, M.nv, nullptr, L.nf, 0, s)) return rc;
   return emit_rows(h, pr, batch, 1, row0, 3, 1.0, d_vel, s);
+}
+
+__global__ void frame_kin_kernel(const PlmModel* __restrict__ Mp, int batch, int body, const double* __restrict__ plc12, int base_body,
+                                 const double* __restrict__ base_plc12, int relative_to_base, const double* __restrict__ q,
+                                 const double* __restrict__ v, double* __restrict__ pos, double* __restrict__ vel);
+
+int plm_frame_kinematics(plm_handle* h, int32_t body, const double* placement12, int32_t base_body, const double* base_placement12,
+                         int32_t relative_to_base, const double* d_q, const double* d_v, int32_t batch, double* d_pos, double* d_vel,
+                         void* stream) {
+  if (batch < 1 || batch > h->max_batch) { h->error = "batch exceeds max_batch of the handle"; return 4; }
+  const PlmModel& M = h->host.model;
+  if (body < 0 || body >= M.nbody || base_body < 0 || base_body >= M.nbody) { h->error = "plm_frame_kinematics: body out of range"; return 11; }
+  if (d_vel && !d_v) { h->error = "plm_frame_kinematics: velocities need d_v"; return 11; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->d_frame_plc) DYN_CUDA(h, cudaMalloc(&h->d_frame_plc, 24 * sizeof(double)));
+  double plc[24];
+  for (int i = 0; i < 12; ++i) { plc[i] = placement12[i]; plc[12 + i] = base_placement12 ? base_placement12[i] : (i % 4 == 0 && i < 9 ? 1.0 : 0.0); }
+  DYN_CUDA(h, cudaMemcpyAsync(h->d_frame_plc, plc, sizeof(plc), cudaMemcpyHostToDevice, s));
+  frame_kin_kernel<<<(batch + 63) / 64, 64, 0, s>>>(h->d_model, batch, body, h->d_frame_plc, base_body, h->d_frame_plc + 12, relative_to_base,
+                                                    d_q, d_v, d_pos, d_vel);
+  PLM_LAUNCH_CHECK(h);
+  return 0;
+}
+
+// frame_pos(q) / frame_vel(q, v) of an arbitrary frame (dynamics/dynamics.py:67-118), one thread per instance: forward
+// kinematics and the velocity recursion along the chain of the frame's parent body, in world coordinates.
+//   pos  = oMf.translation
+//   vel  = getFrameVelocity(LOCAL_WORLD_ALIGNED) = [v of the frame origin; omega], world axes; with relative_to_base the
+//          reference's variant (dynamics.py:86-113): [R_b^T(v_f - v_b - w_b x (p_f - p_b))_xy, v_f.z, R_b^T(w_f - w_b)_xy, w_f.z]
+// Frames are given by their parent body and placement (R row-major | p) in that body's joint frame.
+__device__ void frame_state(const PlmModel& M, const double* q, const double* v, int body, const double* plc, double* Rf, double* pf,
+                            double* vf, double* wf) {
+  double R[9], p[3] = {q[0], q[1], q[2]}, vo[3] = {0, 0, 0}, w[3] = {0, 0, 0};
+  quat_to_R(q + 3, R);
+  if (v) { matvec3(R, v, vo); matvec3(R, v + 3, w); }      // free-flyer velocity is expressed in the base frame
+  if (body > 0) {
+    const int col = body + 5, len = M.chain_len[col];
+    for (int l = 0; l < len; ++l) {
+      const int jb = M.chain[col][l];
+      double t[3], t2[3];
+      matvec3(R, M.place_p[jb], t);                          // joint origin in world axes, relative to the parent origin
+      if (v) { cross3(w, t, t2); for (int i = 0; i < 3; ++i) vo[i] += t2[i]; }
+      for (int i = 0; i < 3; ++i) p[i] += t[i];
+      if (M.has_rot[jb]) matmul3(R, M.place_R[jb], R);
+      double sn, cs;
+      sincos(q[7 + jb - 1], &sn, &cs);
+      double Rot[9];
+      const double x = M.axis[jb][0], y = M.axis[jb][1], z = M.axis[jb][2], tt = 1.0 - cs;
+      Rot[0] = cs + tt * x * x;     Rot[1] = tt * x * y - sn * z; Rot[2] = tt * x * z + sn * y;
+      Rot[3] = tt * x * y + sn * z; Rot[4] = cs + tt * y * y;     Rot[5] = tt * y * z - sn * x;
+      Rot[6] = tt * x * z - sn * y; Rot[7] = tt * y * z + sn * x; Rot[8] = cs + tt * z * z;
+      matmul3(R, Rot, R);
+      if (v) {
+        double ax[3];
+        matvec3(R, M.axis[jb], ax);
+        const double qd = v[6 + jb - 1];
+        for (int i = 0; i < 3; ++i) w[i] += ax[i] * qd;
+      }
+    }
+  }
+  double t[3], t2[3];
+  matvec3(R, plc + 9, t);
+  matmul3(R, plc, Rf);
+  for (int i = 0; i < 3; ++i) pf[i] = p[i] + t[i];
+  if (v) {
+    cross3(w, t, t2);
+    for (int i = 0; i < 3; ++i) { vf[i] = vo[i] + t2[i]; wf[i] = w[i]; }
+  }
+}
+
+__global__ void frame_kin_kernel(const PlmModel* __restrict__ Mp, int batch, int body, const double* __restrict__ plc12, int base_body,
+                                 const double* __restrict__ base_plc12, int relative_to_base, const double* __restrict__ q,
+                                 const double* __restrict__ v, double* __restrict__ pos, double* __restrict__ vel) {
+  const PlmModel& M = *Mp;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const double* qb = q + (size_t)b * M.nq;
+  const double* vb = v ? v + (size_t)b * M.nv : nullptr;
+  double plc[12], Rf[9], pf[3], vf[3], wf[3];
+  for (int i = 0; i < 12; ++i) plc[i] = plc12[i];
+  frame_state(M, qb, vb, body, plc, Rf, pf, vf, wf);
+  if (pos) for (int i = 0; i < 3; ++i) pos[(size_t)b * 3 + i] = pf[i];
+  if (!vel) return;
+  double* o = vel + (size_t)b * 6;
+  if (!relative_to_base) {
+    for (int i = 0; i < 3; ++i) { o[i] = vf[i]; o[3 + i] = wf[i]; }
+    return;
+  }
+  double Rb[9], pb[3], vbf[3], wbf[3], d[3], t[3], lin[3], ang[3], linb[3], angb[3];
+  for (int i = 0; i < 12; ++i) plc[i] = base_plc12[i];
+  frame_state(M, qb, vb, base_body, plc, Rb, pb, vbf, wbf);
+  for (int i = 0; i < 3; ++i) d[i] = pf[i] - pb[i];
+  cross3(wbf, d, t);
+  for (int i = 0; i < 3; ++i) { lin[i] = vf[i] - vbf[i] - t[i]; ang[i] = wf[i] - wbf[i]; }
+  matTvec3(Rb, lin, linb);
+  matTvec3(Rb, ang, angb);
+  o[0] = linb[0]; o[1] = linb[1]; o[2] = vf[2];      // z components stay in the world frame (dynamics.py:108-113)
+  o[3] = angb[0]; o[4] = angb[1]; o[5] = wf[2];
 }
 
 __global__ void state_integrate_kernel(int batch, int nq, int nv, int cvel, const double* __restrict__ x, const double* __restrict__ dx,

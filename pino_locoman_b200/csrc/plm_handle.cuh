@@ -62,6 +62,7 @@ struct plm_handle {
   int sqp_alloc_done = 0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double* d_mpc_dts = nullptr;   // [PLM_MAXNODES] horizon step sizes of plm_mpc_step
+  double* d_frame_plc = nullptr; // [24] frame / base-frame placements of plm_frame_kinematics
   int num_sms = 148;             // multiprocessors of the device (kernel variant selection)
 };
 

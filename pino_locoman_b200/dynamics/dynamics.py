@@ -96,15 +96,52 @@ class Dynamics:
             return (tau, jac) if want_jac else tau
         return _Fn("rnea_dyn", lambda q, v, a, forces: run(q, v, a, forces, False), lambda q, v, a, forces: run(q, v, a, forces, True))
 
-    # -- dynamics.py:77-118 ----------------------------------------------------------------------------------
+    # -- dynamics.py:67-118 ----------------------------------------------------------------------------------
+    def _frame_args(self, frame_id):
+        """(parent body, placement R|p as 12 doubles) of a frame name of the robot's kinematic tree."""
+        import numpy as np
+        body, T, _ = self.model.frame(frame_id)
+        plc = np.concatenate((np.asarray(T[:3, :3], dtype=np.float64).reshape(9), np.asarray(T[:3, 3], dtype=np.float64)))
+        return int(body), (ctypes.c_double * 12)(*plc)
+
     def get_frame_velocity(self, frame_id, relative_to_base=False):
+        """frame_vel(q, v) -> [linear; angular] (6) in LOCAL_WORLD_ALIGNED axes, or the base-relative variant of
+        dynamics.py:86-113, for any frame of the model."""
+        h = self.handle
+        body, plc = self._frame_args(frame_id)
+        base_body, base_plc = self._frame_args("base_link") if "base_link" in self.model.frames else (0, None)
+
+        def frame_vel(q, v):
+            B = _check_in(q, (self.nq,), "q").shape[0]
+            _check_in(v, (self.nv,), "v")
+            out = torch.empty(B, 6, dtype=torch.float64, device=q.device)
+            h._rc(h.lib.plm_frame_kinematics(h._h, body, plc, base_body, base_plc, int(relative_to_base), _ptr(q), _ptr(v), B, None, _ptr(out),
+                                             h._stream()))
+            return out
+        return _Fn("frame_vel", frame_vel)
+
+    def get_frame_position(self, frame_id):
+        """frame_pos(q) -> oMf.translation (3) for any frame of the model (dynamics.py:67-75)."""
+        h = self.handle
+        body, plc = self._frame_args(frame_id)
+
+        def frame_pos(q):
+            B = _check_in(q, (self.nq,), "q").shape[0]
+            out = torch.empty(B, 3, dtype=torch.float64, device=q.device)
+            h._rc(h.lib.plm_frame_kinematics(h._h, body, plc, 0, None, 0, _ptr(q), None, B, _ptr(out), None, h._stream()))
+            return out
+        return _Fn("frame_pos", frame_pos)
+
+    def frame_velocity_rows(self, frame_id, relative_to_base=False):
+        """The three velocity components the OCP rows use (optimization/ocp.py:143,177), read off the node kernel's own rows:
+        foot frames (world aligned) and the arm frame (base relative)."""
         h = self.handle
         if not relative_to_base and frame_id in self.foot_frames:
             contact = self.foot_frames.index(frame_id)
         elif relative_to_base and frame_id == self.robot.arm_ee_frame:
             contact = -1
         else:
-            raise NotImplementedError("frame_vel: foot frames (world aligned) and the arm frame (base relative) are on the path")
+            raise ValueError("frame_velocity_rows: foot frames (world aligned) and the arm frame (base relative) only")
 
         def frame_vel(q, v):
             B = _check_in(q, (self.nq,), "q").shape[0]
@@ -113,9 +150,6 @@ class Dynamics:
             h._rc(h.lib.plm_frame_vel(h._h, contact, int(relative_to_base), _ptr(q), _ptr(v), B, _ptr(out), h._stream()))
             return out
         return _Fn("frame_vel", frame_vel)
-
-    def get_frame_position(self, frame_id):
-        raise NotImplementedError("frame_pos is not used by any OCP row (dynamics/dynamics.py:67-75)")
 
     def _gaps(self, dyn_id, ext_force_frame):
         h = self.handle

@@ -69,17 +69,35 @@ def test_rnea_aba_gaps_match_oracle(robots, rn):
     assert np.abs(back.cpu().numpy() - dx).max() < 1e-12
     for b in range(B):
         assert np.abs(x1[b].cpu().numpy() - od.state_integrate()(x0[b], dx[b])).max() < 1e-12
-    # frame velocities
-    for k, fname in enumerate(r.foot_frames):
-        vel = d.get_frame_velocity(fname)(_t(q), _t(v)).cpu().numpy()
-        for b in range(B):
-            ref = od.get_frame_velocity(o.foot_frames[k])(q[b], v[b])[:3]
-            assert np.abs(vel[b] - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+    # frame velocities: all six components (LOCAL_WORLD_ALIGNED / the base-relative variant) and positions, any frame;
+    # the three components the OCP rows use also through the node kernel's own rows
+    has_base = "base_link" in r.model.frames           # (Go2's root link is called "base": the reference's base_frame id is invalid there)
+    frames = list(zip(r.foot_frames, o.foot_frames)) + [("FR_thigh", o.model.getFrameId("FR_thigh"))]
+    if has_base:
+        frames.append(("base_link", o.model.getFrameId("base_link")))
     if r.arm_ee_frame:
-        vel = d.get_frame_velocity(r.arm_ee_frame, relative_to_base=True)(_t(q), _t(v)).cpu().numpy()
+        frames.append((r.arm_ee_frame, o.arm_ee_frame))
+    for fname, fid in frames:
+        for rel in ((False, True) if has_base else (False,)):
+            vel = d.get_frame_velocity(fname, relative_to_base=rel)(_t(q), _t(v)).cpu().numpy()
+            assert vel.shape == (B, 6)
+            for b in range(B):
+                ref = od.get_frame_velocity(fid, relative_to_base=rel)(q[b], v[b])
+                assert np.abs(vel[b] - ref).max() <= TOL * max(1.0, np.abs(ref).max()), (fname, rel)
+        pos = d.get_frame_position(fname)(_t(q)).cpu().numpy()
         for b in range(B):
-            ref = od.get_frame_velocity(o.arm_ee_frame, relative_to_base=True)(q[b], v[b])[:3]
-            assert np.abs(vel[b] - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+            ref = od.get_frame_position(fid)(q[b])
+            assert np.abs(pos[b] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), fname
+    for k, fname in enumerate(r.foot_frames):
+        vel3 = d.frame_velocity_rows(fname)(_t(q), _t(v)).cpu().numpy()
+        vel6 = d.get_frame_velocity(fname)(_t(q), _t(v)).cpu().numpy()
+        assert np.abs(vel3 - vel6[:, :3]).max() <= 1e-12 * max(1.0, np.abs(vel6).max())
+    if r.arm_ee_frame:
+        vel3 = d.frame_velocity_rows(r.arm_ee_frame, relative_to_base=True)(_t(q), _t(v)).cpu().numpy()
+        vel6 = d.get_frame_velocity(r.arm_ee_frame, relative_to_base=True)(_t(q), _t(v)).cpu().numpy()
+        assert np.abs(vel3 - vel6[:, :3]).max() <= 1e-12 * max(1.0, np.abs(vel6).max())
+    with pytest.raises(KeyError):
+        d.get_frame_position("no_such_frame")
 
 
 def test_centroidal_functions_match_oracle(robots):
