@@ -204,7 +204,6 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   double* col1 = rowk + smax;          // [smax] second column / row of a rank-2 step
   double* row1 = col1 + smax;
   double* La = row1 + smax;            // [4][smax] rank-4 step: minus the four new columns of L (rows below the block)
-  double* Wv = colk;                   // [4][smax] rank-4 step: right factors (X rows | inverse block | L columns), aliases the vectors above
   double* As = La + 4 * smax;          // [max_nnz] scaled A values of the node block
   double* rs = As + L.max_nnz;         // [max_rows] rho of the node rows
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
@@ -263,146 +262,154 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       }
     }
     __syncthreads();
-    // ---- right-looking Cholesky fused with the inversion of the factor, in place: after the step of column k the
-    // columns <= k of the buffer hold X = L^-1 (rows > k partially applied: Y[r][c] = -sum_{j<=k} L[r][j] X[j][c]), the
-    // columns > k the trailing matrix.  Two columns per step (rank-2 updates: half the barriers, two thirds of the
-    // shared-memory traffic of rank-1 steps); a single column is left over when s is odd.
-    const int lane8 = tid & 7, slot = tid >> 3, nslot = nth >> 3;
-    int k = 0;
-    // Four columns per step on the FP64 tensor cores.  Phase A (one thread per row / column): Cholesky of the 4x4
-    // diagonal block, the four new columns of L, the four new rows of X and the inverse of the block; the block
-    // columns of the rows below are zeroed.  Phase B: one rank-4 update H[r][c] -= sum_j L[r][k+j] W_j[c] of every
-    // row below the block over ALL columns c <= r, with W_j[c] = X[k+j][c] (c < k), the inverse block (k <= c < k+4)
-    // and L[c][k+j] (c >= k+4): the Y part, the block columns and the trailing matrix in one pass of 8x8 tiles.
-    for (; k + 3 < s; k += 4) {
-      if (tid < s) {
-        const double* H0 = H + tri(k, k);
-        const double* H1 = H + tri(k + 1, k);
-        const double* H2 = H + tri(k + 2, k);
-        const double* H3 = H + tri(k + 3, k);
-        const double p0 = H0[0];
-        const double i0 = rsqrt(p0 > 0.0 ? p0 : 1.0);
-        const double l10 = H1[0] * i0, l20 = H2[0] * i0, l30 = H3[0] * i0;
-        const double p1 = H1[1] - l10 * l10;
-        const double i1 = rsqrt(p1 > 0.0 ? p1 : 1.0);
-        const double l21 = (H2[1] - l20 * l10) * i1, l31 = (H3[1] - l30 * l10) * i1;
-        const double p2 = H2[2] - l20 * l20 - l21 * l21;
-        const double i2 = rsqrt(p2 > 0.0 ? p2 : 1.0);
-        const double l32 = (H3[2] - l30 * l20 - l31 * l21) * i2;
-        const double p3 = H3[3] - l30 * l30 - l31 * l31 - l32 * l32;
-        const double i3 = rsqrt(p3 > 0.0 ? p3 : 1.0);
-        if (!(p0 > 0.0 && p1 > 0.0 && p2 > 0.0 && p3 > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
-        const int r = tid;
-        double w0, w1, w2, w3;
-        if (r > k + 3) {                         // row r of the four new columns of L
-          double* Hr = H + tri(r, k);
-          w0 = Hr[0] * i0;
-          w1 = (Hr[1] - w0 * l10) * i1;
-          w2 = (Hr[2] - w0 * l20 - w1 * l21) * i2;
-          w3 = (Hr[3] - w0 * l30 - w1 * l31 - w2 * l32) * i3;
-          La[r] = -w0; La[smax + r] = -w1; La[2 * smax + r] = -w2; La[3 * smax + r] = -w3;
-          Hr[0] = 0.0; Hr[1] = 0.0; Hr[2] = 0.0; Hr[3] = 0.0;
-        } else if (r < k) {                      // column r of the four new rows of X
-          w0 = H[tri(k, r)] * i0;
-          w1 = (H[tri(k + 1, r)] - l10 * w0) * i1;
-          w2 = (H[tri(k + 2, r)] - l20 * w0 - l21 * w1) * i2;
-          w3 = (H[tri(k + 3, r)] - l30 * w0 - l31 * w1 - l32 * w2) * i3;
-        } else {                                 // column q = r - k of the inverse of the diagonal block
-          const int q = r - k;
-          w0 = (q == 0) ? i0 : 0.0;
-          w1 = (q == 1) ? i1 : (q < 1 ? -(l10 * w0) * i1 : 0.0);
-          w2 = (q == 2) ? i2 : (q < 2 ? -(l20 * w0 + l21 * w1) * i2 : 0.0);
-          w3 = (q == 3) ? i3 : -(l30 * w0 + l31 * w1 + l32 * w2) * i3;
+    // ---- Cholesky H = L L^T and X = L^-1, in place (packed lower), blocked by eight columns with the inner products on
+    // the FP64 tensor cores (DMMA m8n8k4) and the accumulators in registers over the whole k-loop:
+    //   P1 (left-looking, block column J): H[j0:, J] -= L[j0:, 0:j0] L[J, 0:j0]^T (8x8 tiles dealt to the warps); warp 0
+    //      factors the 8x8 diagonal block and stores ITS INVERSE in its place (the block of L itself is not needed
+    //      again); one thread per row below solves L[r, J] = H[r, J] L_JJ^-T with that inverse.
+    //   P2 (row block I, top down): X[I, 0:i0] = -L_II^-1 (L[I, 0:i0] X[0:i0, 0:i0]), X[I, I] = L_II^-1 (already there):
+    //      tiles of the product into a scratch row block, then one thread per column applies -L_II^-1.
+    // Rows / columns beyond s (ragged last block) are masked; Tm (8 x smax scratch) aliases the step vectors.
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      constexpr int nw = QP_THREADS >> 5;
+      const int fr = lane >> 2, fk = lane & 3;
+      const int nb8 = (s + 7) >> 3;
+      double* Tm = colk;                    // [8][smax]: colk | rowk | col1 | row1 | La (contiguous)
+      double* dsc = K;                      // [64 + 8] scratch of the diagonal-block step (K is dead until the end of the stage)
+      for (int Jb = 0; Jb < nb8; ++Jb) {
+        const int j0 = 8 * Jb;
+        // (1) update of block column J
+        for (int t = warp; t < nb8 - Jb; t += nw) {
+          const int r0 = j0 + 8 * t;
+          const int ar = r0 + fr, br = j0 + fr;
+          const bool aok = ar < s, bok = br < s;
+          const double* Arow = H + tri(aok ? ar : 0, 0);
+          const double* Brow = H + tri(bok ? br : 0, 0);
+          const int cc = j0 + 2 * fk;
+          double* Cp = H + tri(aok ? ar : 0, 0) + cc;
+          const bool v0 = aok && cc <= ar && cc < s, v1 = aok && cc + 1 <= ar && cc + 1 < s;
+          double c0v = v0 ? Cp[0] : 0.0, c1v = v1 ? Cp[1] : 0.0;
+          for (int kk = 0; kk < j0; kk += 4) {
+            const double av = aok ? -Arow[kk + fk] : 0.0;
+            const double bv = bok ? Brow[kk + fk] : 0.0;
+            dmma884(c0v, c1v, av, bv, c0v, c1v);
+          }
+          if (v0) Cp[0] = c0v;
+          if (v1) Cp[1] = c1v;
         }
-        Wv[r] = w0; Wv[smax + r] = w1; Wv[2 * smax + r] = w2; Wv[3 * smax + r] = w3;
-      }
-      __syncthreads();
-      {
-        const int warp = tid >> 5, lane = tid & 31;
-        constexpr int nw = QP_THREADS >> 5;      // compile-time warp count: the round-robin arithmetic below must not divide
-        const int R0 = k + 4, ntr = (s - R0 + 7) >> 3;
-        const int fr = lane >> 2, fk = lane & 3;
-        // tiles of the lower triangle, dealt round robin to the warps (running tile count, no division)
-        int turn = warp;                         // tiles until this warp's next one
-        for (int tr = 0; tr < ntr; ++tr) {
-         const int r0 = R0 + 8 * tr, nc = ((r0 + 7 < s ? r0 + 7 : s - 1) >> 3) + 1;
-         int tc = turn;
-         turn = (turn >= nc) ? turn - nc : (nw - 1) - ((nc - 1 - turn) % nw);
-         for (; tc < nc; tc += nw) {
-          const int c0 = 8 * tc;
-          const int ar = r0 + fr, bc = c0 + fr;
-          const double a = ar < s ? La[fk * smax + ar] : 0.0;
-          const double bv = bc < s ? Wv[fk * smax + bc] : 0.0;
-          const int cc = c0 + 2 * fk;
-          double* Hc = H + tri(ar < s ? ar : 0, 0) + cc;
-          const bool v0 = ar < s && cc <= ar, v1 = ar < s && cc + 1 <= ar;
-          const double e0 = v0 ? Hc[0] : 0.0, e1 = v1 ? Hc[1] : 0.0;
-          double d0, d1;
-          dmma884(d0, d1, a, bv, e0, e1);
-          if (v0) Hc[0] = d0;
-          if (v1) Hc[1] = d1;
-         }
+        __syncthreads();
+        // (2) diagonal block: lane i = row i of the 8x8 block (identity beyond s); Cholesky by columns with shuffles, then
+        // lane c solves L x = e_c for column c of the inverse
+        if (warp == 0) {
+          const int mrows = min(8, s - j0);
+          const int ri = lane & 7;
+          double a8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a8[c] = (ri < mrows && c <= ri) ? H[tri(j0 + ri, 0) + j0 + c] : (c == ri ? 1.0 : 0.0);
+          double myinv = 1.0;
+          bool bad = false;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const double dcc = __shfl_sync(0xffffffffu, a8[c], c);
+            if (!(dcc > 0.0)) bad = true;
+            const double inv = rsqrt(dcc > 0.0 ? dcc : 1.0);
+            const double lic = a8[c] * inv;           // lane c: sqrt(d_cc); lanes i > c: L[i][c]
+            a8[c] = lic;
+            if (ri == c) myinv = inv;
+#pragma unroll
+            for (int j = c + 1; j < 8; ++j) {
+              const double ljc = __shfl_sync(0xffffffffu, lic, j);
+              if (ri >= j) a8[j] -= lic * ljc;
+            }
+          }
+          if (bad && lane == 0) atomicExch(&fail[b], i + 1);
+          if (lane < 8) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dsc[8 * lane + c] = a8[c];
+            dsc[64 + lane] = myinv;
+          }
+          __syncwarp();
+          if (lane < 8) {
+            // column `lane` of L_JJ^-1: x[r] for r >= lane
+            double x8[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              double acc = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+              for (int d = 0; d < 8; ++d)
+                if (d < r && d >= lane) acc -= dsc[8 * r + d] * x8[d];
+              x8[r] = (r >= lane) ? acc * dsc[64 + r] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (r >= lane && r < mrows && lane < mrows) H[tri(j0 + r, 0) + j0 + lane] = x8[r];
+          }
         }
-        // rows k .. k+3 of X are final (phase B touches only the rows below)
-        if (tid <= k + 3) {
-          for (int j = 0; j < 4; ++j)
-            if (tid <= k + j) H[tri(k + j, tid)] = Wv[j * smax + tid];
+        __syncthreads();
+        // (3) panel: L[r, J] = H[r, J] L_JJ^-T, one thread per row below the block
+        if (j0 + 8 < s) {
+          const int mc = min(8, s - j0);      // (= 8 here: rows below exist only for full blocks)
+          for (int r = j0 + 8 + tid; r < s; r += nth) {
+            double* Hr = H + tri(r, 0) + j0;
+            double h8[8], o8[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) h8[c] = (c < mc) ? Hr[c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              double acc = 0.0;
+#pragma unroll
+              for (int d = 0; d < 8; ++d)
+                if (d <= c) acc += h8[d] * H[tri(j0 + c, 0) + j0 + d];      // (L_JJ^-1)[c][d]
+              o8[c] = acc;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < mc) Hr[c] = o8[c];
+          }
+          __syncthreads();
         }
       }
-      __syncthreads();
-    }
-    for (; k + 1 < s; k += 2) {
-      if (tid < s) {                                               // (warps beyond the stage size skip the square roots)
-        const double piv0 = H[tri(k, k)];
-        const double d0 = 1.0 / sqrt(piv0 > 0.0 ? piv0 : 1.0);
-        const double l10 = H[tri(k + 1, k)] * d0;                  // L[k+1][k]
-        const double piv1 = H[tri(k + 1, k + 1)] - l10 * l10;
-        const double d1 = 1.0 / sqrt(piv1 > 0.0 ? piv1 : 1.0);
-        if (!(piv0 > 0.0 && piv1 > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
-        const int r = tid;
-        if (r > k + 1) {                                           // columns k, k+1 of L
-          const double* Hr = H + tri(r, 0);
-          const double c0 = Hr[k] * d0;
-          colk[r] = c0;
-          col1[r] = (Hr[k + 1] - c0 * l10) * d1;
+      // ---- P2: X = L^-1 row block by row block
+      for (int Ib = 1; Ib < nb8; ++Ib) {
+        const int i0 = 8 * Ib;
+        for (int t = warp; t < Ib; t += nw) {
+          const int c0 = 8 * t;
+          const int ar = i0 + fr;
+          const bool aok = ar < s;
+          const double* Arow = H + tri(aok ? ar : 0, 0);
+          const int bc = c0 + fr;                 // column of X in the B fragment
+          double c0v = 0.0, c1v = 0.0;
+          for (int kk = c0; kk < i0; kk += 4) {
+            const int xr = kk + fk;               // row of X in the B fragment (xr < i0 <= s)
+            const double av = aok ? Arow[kk + fk] : 0.0;
+            const double bv = (bc <= xr) ? H[tri(xr, 0) + bc] : 0.0;
+            dmma884(c0v, c1v, av, bv, c0v, c1v);
+          }
+          Tm[fr * smax + c0 + 2 * fk] = c0v;
+          Tm[fr * smax + c0 + 2 * fk + 1] = c1v;
         }
-        if (r <= k + 1) {                                          // rows k, k+1 of X (final)
-          const double x0 = (r == k) ? d0 : (r < k ? H[tri(k, r)] * d0 : 0.0);
-          rowk[r] = x0;
-          row1[r] = (r == k + 1) ? d1 : ((r < k ? H[tri(k + 1, r)] : 0.0) - l10 * x0) * d1;
+        __syncthreads();
+        {
+          const int mrows = min(8, s - i0);
+          for (int c = tid; c < i0; c += nth) {
+            double t8[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) t8[d] = Tm[d * smax + c];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if (r < mrows) {
+                double acc = 0.0;
+#pragma unroll
+                for (int d = 0; d < 8; ++d)
+                  if (d <= r) acc += H[tri(i0 + r, 0) + i0 + d] * t8[d];
+                H[tri(i0 + r, 0) + c] = -acc;
+              }
+            }
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
-      for (int r = k + 2 + slot; r < s; r += nslot) {
-        const double a0 = colk[r], a1 = col1[r];
-        double* Hr = H + tri(r, 0);
-        for (int c2 = k + 2 + lane8; c2 <= r; c2 += 8) Hr[c2] -= a0 * colk[c2] + a1 * col1[c2];     // trailing matrix
-        for (int c2 = lane8; c2 < k; c2 += 8) Hr[c2] -= a0 * rowk[c2] + a1 * row1[c2];              // Y, columns < k
-        if (lane8 == 0) Hr[k] = -(a0 * rowk[k] + a1 * row1[k]);                                     // Y, column k
-        if (lane8 == 1) Hr[k + 1] = -a1 * row1[k + 1];                                              // Y, column k+1
-      }
-      if (tid <= k + 1) {
-        if (tid <= k) H[tri(k, tid)] = rowk[tid];
-        H[tri(k + 1, tid)] = row1[tid];
-      }
-      __syncthreads();
-    }
-    for (; k < s; ++k) {
-      const double piv = H[tri(k, k)];
-      if (!(piv > 0.0) && tid == 0) atomicExch(&fail[b], i + 1);
-      const double dinv = 1.0 / sqrt(piv > 0.0 ? piv : 1.0);
-      for (int r = k + 1 + tid; r < s; r += nth) colk[r] = H[tri(r, k)] * dinv;
-      for (int c2 = tid; c2 <= k; c2 += nth) rowk[c2] = (c2 == k) ? dinv : H[tri(k, c2)] * dinv;   // row k of X is final
-      __syncthreads();
-      for (int r = k + 1 + slot; r < s; r += nslot) {
-        const double lrk = colk[r];
-        double* Hr = H + tri(r, 0);
-        for (int c2 = k + 1 + lane8; c2 <= r; c2 += 8) Hr[c2] -= lrk * colk[c2];     // trailing matrix
-        for (int c2 = lane8; c2 < k; c2 += 8) Hr[c2] -= lrk * rowk[c2];              // X, columns < k
-        if (lane8 == 0) Hr[k] = -lrk * rowk[k];                                      // X, column k (L[r][k] is consumed)
-      }
-      for (int c2 = tid; c2 <= k; c2 += nth) H[tri(k, c2)] = rowk[c2];
-      __syncthreads();
     }
     // ---- S_i^-1 = X^T X (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit).
     // 8x8 output tiles on the FP64 tensor cores: S[r][c] = sum_{t >= r} X[t][r] X[t][c], four rows t of X per DMMA.

@@ -42,7 +42,9 @@ for r in rows[h + 1:]:
 tot, ts, tw = sum(agg.values()), max(1, sum(samp.values())), max(1, sum(wf.values()))
 print("total warp instructions", tot, "samples", ts, "shared wavefronts", tw)
 srcs = {}
-for ln, c in agg.most_common(top):
+order = samp.most_common(top) if os.environ.get("NCU_LINES_BY_SAMPLES") else agg.most_common(top)
+for ln, _ in order:
+    c = agg[ln]
     text = ""
     if ln:
         for d in (os.path.dirname(os.path.abspath(obj)),):
