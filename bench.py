@@ -409,10 +409,10 @@ def main():
     if rank == 0 and not args.no_other_configs:
         from pino_locoman_b200.utils.robot import B2, Go2
 
-        def config_leg(robot_cls, dynamics, batch, sweep_only, bytes_node_eval):
+        def config_leg(robot_cls, dynamics, batch, sweep_only, bytes_node_eval, gait="trot"):
             nonlocal launches
             r = robot_cls()
-            r.set_gait_sequence("trot", 0.8)
+            r.set_gait_sequence(gait, 0.8)
             o = make_ocp(dynamics=dynamics, default_args=OCP_ARGS[dynamics], robot=r, nodes=NODES, solver="osqp", batch=batch, device=dev)
             xh, ph = synthetic_inputs(r, o, batch, 0)
             o.init_solver()
@@ -454,6 +454,9 @@ def main():
         other["go2_centroidal_vel_1"] = config_leg(Go2, "centroidal_vel", 1, False, 6144.0)
         other["b2g_whole_body_aba_1024"] = config_leg(B2G, "whole_body_aba", 1024, False, 20172.0)
         other["b2_centroidal_acc_4096_sweep"] = config_leg(B2, "centroidal_acc", 4096, True, 7320.0)
+        # the other gaits of utils/gait_sequence.py:53-75 on the bench formulation
+        other["b2g_whole_body_rnea_1024_walk"] = config_leg(B2G, DYNAMICS, 1024, False, BYTES_NODE_EVAL, gait="walk")
+        other["b2g_whole_body_rnea_1024_stand"] = config_leg(B2G, DYNAMICS, 1024, False, BYTES_NODE_EVAL, gait="stand")
     # ---- end to end through the plugin surface: host buffers in, host buffers out
     ocp.set_initial(x.cpu().numpy())
     for _ in range(min(W, 1)):
