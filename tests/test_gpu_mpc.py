@@ -17,10 +17,12 @@ def _configure(o, kind, x_init, t, dt_min):
         o.update_previous_torques(np.zeros(o.nj))
 
 
-@pytest.mark.parametrize("rn,kind,N,gait,warm", [("b2g", "whole_body_rnea", 6, "trot", True), ("go2", "centroidal_vel", 5, "walk", True),
-                                                 ("b2", "whole_body_acc", 5, "stand", True), ("b2g", "whole_body_rnea", 6, "trot", False),
-                                                 ("go2", "centroidal_vel", 5, "walk", False)])
-def test_device_resident_mpc_matches_host_loop(rn, kind, N, gait, warm):
+@pytest.mark.parametrize("rn,kind,N,gait,warm,kw", [("b2g", "whole_body_rnea", 6, "trot", True, {}), ("go2", "centroidal_vel", 5, "walk", True, {}),
+                                                    ("b2", "whole_body_acc", 5, "stand", True, {}), ("b2g", "whole_body_rnea", 6, "trot", False, {}),
+                                                    ("go2", "centroidal_vel", 5, "walk", False, {}),
+                                                    ("go2", "centroidal_vel", 5, "trot", True, {"include_base": False}),
+                                                    ("b2", "whole_body_rnea", 5, "trot", True, {"include_acc": False})])
+def test_device_resident_mpc_matches_host_loop(rn, kind, N, gait, warm, kw):
     from pino_locoman_b200 import OCP_ARGS
     from pino_locoman_b200.mpc import BatchedMPC
     from pino_locoman_b200.optimization import make_ocp
@@ -31,7 +33,7 @@ def test_device_resident_mpc_matches_host_loop(rn, kind, N, gait, warm):
     def make():
         r = {"b2g": prob.B2G, "go2": prob.Go2, "b2": prob.B2}[rn]()
         r.set_gait_sequence(gait, 0.8)
-        return make_ocp(dynamics=kind, default_args=OCP_ARGS[kind], robot=r, nodes=N, solver="osqp", batch=B)
+        return make_ocp(dynamics=kind, default_args=dict(OCP_ARGS[kind], **kw), robot=r, nodes=N, solver="osqp", batch=B)
 
     host, dev = make(), make()
     x_init = np.stack([host.x_nom] * B)
