@@ -458,13 +458,18 @@ def main():
         other["b2g_whole_body_rnea_1024_walk"] = config_leg(B2G, DYNAMICS, 1024, False, BYTES_NODE_EVAL, gait="walk")
         other["b2g_whole_body_rnea_1024_stand"] = config_leg(B2G, DYNAMICS, 1024, False, BYTES_NODE_EVAL, gait="stand")
     # ---- end to end through the plugin surface: host buffers in, host buffers out
+    # every step hands over that step's inputs from the host, as the reference's loop does (run_mpc.py:127-133: x_init,
+    # schedules -> parameters; starting point): p [B, np] and x [B, n] go host -> device, x_new and the statistics come back
     ocp.set_initial(x.cpu().numpy())
+    x_init_host = ocp._get("x_init").copy()
     for _ in range(min(W, 1)):
+        ocp.update_initial_state(x_init_host)
         ocp.solve(retract_all=False)
     barrier()
     t0 = time.perf_counter()
     ke = max(1, min(K, 3))
     for _ in range(ke):
+        ocp.update_initial_state(x_init_host)      # marks the parameter image dirty: p is uploaded again
         ocp.solve(retract_all=False)
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) / ke

@@ -277,7 +277,7 @@ class OCP:
             self._pin_out = [torch.empty(self.batch, self.n, dtype=torch.float64).pin_memory() for _ in range(2)]
             self._pin_stats = torch.empty(self.batch, 8, dtype=torch.float64).pin_memory()
             self._pin_sel = 0
-        self._pin_x.numpy()[:] = current_x
+        self._pin_x.copy_(torch.from_numpy(np.ascontiguousarray(current_x)))      # (multi-threaded host copy into pinned memory)
         xd = self._pin_x.to(h.device, non_blocking=True)
         pd = self._p_device()
         x_new, stats = h.sqp_step(xd, pd)
