@@ -98,20 +98,22 @@ int plm_create(const plm_robot_desc* robot, const plm_ocp_desc* ocp, int32_t max
   const PlmLayout& L = h->host.layout;
   h->tgt_ld = L.ndx + L.types[L.node_type[0]].nu;
   PLM_CHECK_CUDA(h, cudaMalloc(&h->d_tgt, (size_t)max_batch * h->tgt_ld * sizeof(double)));
-  h->node_ws_doubles = (int)node_ws_doubles(L, h->host.model.nv, L.nf, h->host.model.nbody, false);
-  {
+  for (int mode = 0; mode < 2; ++mode) {
+    h->node_ws_doubles[mode] = (int)node_ws_doubles(L, h->host.model.nv, L.nf, h->host.model.nbody, false, mode == 1);
     const size_t tables = ((sizeof(PlmModel) + 7) / 8 + (sizeof(PlmLayout) + 7) / 8) * 8;
-    const size_t per_warp = (size_t)h->node_ws_doubles * 8, cap = 227 * 1024;
+    const size_t per_warp = (size_t)h->node_ws_doubles[mode] * 8, cap = 227 * 1024;
     int best_w = 0, best = 0;
     for (int w = 1; w <= PLM_NODE_WARPS; ++w) {
       const size_t need = tables + w * per_warp + 1024;   // + per-CTA reservation
       if (need > cap) break;
-      const int resident = (int)(cap / need) * w;
+      // CTAs per SM: by shared memory and by registers (128 per thread under __launch_bounds__(256, 2): 16 warps per SM)
+      const int ctas = std::min((int)(cap / need), 16 / w);
+      const int resident = ctas * w;
       if (resident >= best) { best = resident; best_w = w; }
     }
     if (best_w == 0) { h->error = "node workspace exceeds shared memory"; return 6; }
-    h->node_warps = best_w;
-    h->node_smem = tables + best_w * per_warp;
+    h->node_warps[mode] = best_w;
+    h->node_smem[mode] = tables + best_w * per_warp;
   }
   int rc = plm_setup_node_kernels(h);
   if (rc) return rc;

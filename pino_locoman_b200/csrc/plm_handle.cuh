@@ -43,9 +43,11 @@ struct plm_handle {
   plm::DeviceTables tab;
   double* d_tgt = nullptr;   // [max_batch][tgt_ld] dx_des | u_des
   int tgt_ld = 0;
-  int node_ws_doubles = 0;
-  int node_warps = PLM_NODE_WARPS;   // warps (= node evaluations) per CTA, chosen to maximise resident warps per SM
-  size_t node_smem = 0;
+  // per-warp workspace, warps (= node evaluations) per CTA (chosen to maximise the resident warps per SM) and dynamic
+  // shared memory of the node kernel: [0] evaluation launches, [1] line-search trial launches (these stage x + alpha dx)
+  int node_ws_doubles[2] = {0, 0};
+  int node_warps[2] = {PLM_NODE_WARPS, PLM_NODE_WARPS};
+  size_t node_smem[2] = {0, 0};
   long long launches = 0;
   // QP workspaces (plm_qp.cu)
   plm::QpWork qp;

@@ -49,7 +49,7 @@ node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* _
   // Jacobian entries go straight to the instance's node block in HBM (every pattern entry is written exactly once)
   if (lane == 0)
     node_ws_bind(ws, L, sM->nv, sM->nbody, wsbase + (size_t)warp * ws_doubles + (sizeof(NodeWs) + 7) / 8,
-                 want_jac ? Jv + (size_t)b * L.nnz + L.nnz_off[node] : wsbase /* unused */);
+                 want_jac ? Jv + (size_t)b * L.nnz + L.nnz_off[node] : wsbase /* unused */, tr.part != nullptr);
   __syncwarp();
   NodeArgs A;
   A.M = sM;

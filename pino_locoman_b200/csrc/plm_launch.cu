@@ -13,7 +13,7 @@ static int setup_one(plm_handle* h) {
 }
 
 int plm_setup_node_kernels(plm_handle* h) {
-  if (h->node_smem > 227 * 1024) { h->error = "node workspace exceeds shared memory"; return 6; }
+  if (h->node_smem[0] > 227 * 1024 || h->node_smem[1] > 227 * 1024) { h->error = "node workspace exceeds shared memory"; return 6; }
   const bool nb = h->host.layout.nobase != 0;
   switch (h->host.layout.dynamics) {
     case PLM_CENTROIDAL_VEL: return nb ? setup_one<PLM_CENTROIDAL_VEL, true>(h) : setup_one<PLM_CENTROIDAL_VEL, false>(h);
@@ -35,9 +35,10 @@ int plm_launch_node_trials(plm_handle* h, const double* x, const double* p, int 
   const TrialArgs tr = *reinterpret_cast<const TrialArgs*>(trial_args);
   const PlmLayout& L = h->host.layout;
   const long long items = (long long)batch * L.nodes * (tr.part ? tr.ntrial : 1);
-  const int blocks = (int)((items + h->node_warps - 1) / h->node_warps);
-  const dim3 grid(blocks), block(h->node_warps * 32);
-#define PLM_NODE_LAUNCH(KIND, NB) node_eval_kernel<KIND, NB><<<grid, block, h->node_smem, s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles, tr)
+  const int mode = tr.part ? 1 : 0;      // line-search trial launches carry the staged trial point
+  const int blocks = (int)((items + h->node_warps[mode] - 1) / h->node_warps[mode]);
+  const dim3 grid(blocks), block(h->node_warps[mode] * 32);
+#define PLM_NODE_LAUNCH(KIND, NB) node_eval_kernel<KIND, NB><<<grid, block, h->node_smem[mode], s>>>(h->tab, x, p, batch, g, J, want_jac, h->node_ws_doubles[mode], tr)
   const bool nb = L.nobase != 0;
   switch (L.dynamics) {
     case PLM_CENTROIDAL_VEL: if (nb) PLM_NODE_LAUNCH(PLM_CENTROIDAL_VEL, true); else PLM_NODE_LAUNCH(PLM_CENTROIDAL_VEL, false); break;

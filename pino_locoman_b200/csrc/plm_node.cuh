@@ -29,8 +29,9 @@ namespace plm {
 #define PLM_REC_IB 10
 #define PLM_REC_H 16
 #define PLM_REC_B 22
-// column record: J(6) | phi_q(6) | chi_q(6) | psi(6) | omega_q(3)
-#define PLM_COLREC 27
+// column record: J(6) | phi_q(6) | chi_q(6) | psi(6)   (the angular q-direction of a joint column is J[3..5]; the
+// six base columns keep theirs in NodeWs::jqb)
+#define PLM_COLREC 24
 // contact record: p_k(3) | body velocity(6)
 #define PLM_CONREC 9
 
@@ -46,6 +47,7 @@ struct NodeWs {
   double Rb[9];
   double Rinit[9];
   double jr[9];
+  double jqb[6][3];           // angular q-direction of the base columns (right Jacobian of Exp mixes them)
   double* g;     // [max_rows]
   double* J;     // node block of the Jacobian values: the instance's block in HBM (kernel) or a staging array (host emulation)
   double* aba;   // ABA scratch: M/L, Minv, GQ, GV (nv x 32 each), GF (nv x nf)
@@ -418,7 +420,7 @@ PLM_HD void node_phase_d(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
   for (int i = 0; i < 6; ++i) st.dFq[i] += st.dFqn[i];
   double* c = ws.col[lane];
   for (int i = 0; i < 6; ++i) { c[i] = st.J[i]; c[6 + i] = phi[i]; c[12 + i] = chi[i]; c[18 + i] = psi[i]; }
-  c[24] = Jq[3]; c[25] = Jq[4]; c[26] = Jq[5];
+  if (lane < 6) { ws.jqb[lane][0] = Jq[3]; ws.jqb[lane][1] = Jq[4]; ws.jqb[lane][2] = Jq[5]; }
 }
 
 PLM_HD void shift_to(const double* F, const double* c, double* o) {   // wrench about the origin -> about c
@@ -568,7 +570,7 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
         for (int k = 0; k < M.ncontact; ++k) {
           if (!((mask >> k) & 1u)) continue;
           double g[3], wr[6];
-          cross3(cr + 24, u + L.f_idx + 3 * k, g);
+          cross3(c < 6 ? ws.jqb[c] : cr + 3, u + L.f_idx + 3 * k, g);
           point_wrench(ws.con[k], g, wr);
           tq += dot6(st.J, wr);
         }

@@ -30,17 +30,19 @@ struct HostExec {
 // Bytes of shared workspace one warp needs for a layout.
 // Doubles of workspace one warp needs.  stage_J: keep a staging copy of the node's J block in the workspace
 // (host emulation); the kernel writes J entries straight into the instance's block in HBM instead.
-PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf, int nbody, bool stage_J) {
+// with_xbuf: room for the staged trial point x + alpha dx (line-search launches only: evaluation launches run without it,
+// which is what lets a 16th warp share the SM).
+PLM_HD size_t node_ws_doubles(const PlmLayout& L, int nv, int nf, int nbody, bool stage_J, bool with_xbuf = true) {
   size_t base = (sizeof(NodeWs) + 7) / 8;
   size_t extra = (size_t)nbody * PLM_REC + (size_t)nv * PLM_COLREC + (size_t)L.max_rows + (stage_J ? (size_t)L.max_nnz : 0) +
-                 (size_t)(2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
+                 (with_xbuf ? (size_t)(2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx)) : 0);
   if (L.dynamics == PLM_WHOLE_BODY_ABA) extra += aba_ws_doubles(nv, nf);
   if (L.nobase) extra += PLM_VB_DOUBLES;
   return base + extra + 2;
 }
 
 // Records, row staging, trial staging and ABA scratch are carved from `tail` (doubles following the NodeWs struct).
-PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, int nv, int nbody, double* tail, double* J_external) {
+PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, int nv, int nbody, double* tail, double* J_external, bool with_xbuf = true) {
   ws.rec = reinterpret_cast<double (*)[PLM_REC]>(tail);
   tail += (size_t)nbody * PLM_REC;
   ws.col = reinterpret_cast<double (*)[PLM_COLREC]>(tail);
@@ -50,7 +52,7 @@ PLM_HD void node_ws_bind(NodeWs& ws, const PlmLayout& L, int nv, int nbody, doub
   if (J_external) ws.J = J_external;
   else { ws.J = tail; tail += L.max_nnz; }
   ws.xbuf = tail;
-  ws.aba = ws.xbuf + (2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx));
+  ws.aba = ws.xbuf + (with_xbuf ? (2 * L.ndx + (L.x_off[1] - L.x_off[0] - L.ndx)) : 0);
   ws.vb = ws.aba;      // (the ABA formulation has no variant without base inputs: the two scratch areas never coexist)
 }
 
