@@ -480,7 +480,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   for (int i = 0; i <= N; ++i) {
     const int s = (i < N) ? ndx + nu[i] : ndx;
     Q.fac_off[i] = fo;
-    fo += (s * (s + 1) / 2 + 1) & ~1;   // blocks start 16-byte aligned (bulk copies)
+    fo += (plm_sinv_rows(s) * s + 1) & ~1;   // cyclic-diagonal array of S_i^-1 (plm_qp_types.h); blocks start 16-byte aligned (bulk copies)
     Q.smax = std::max(Q.smax, s);
   }
   Q.fac_off[N + 1] = fo;
@@ -491,51 +491,26 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
   Q.bk_off[N] = fo;
   Q.fac_total = fo;
   {
-    // panel schedules: forward sweep stages 0..N (row panels of the packed S_i^-1), backward sweep stages N-1..0
-    // (column panels of B_i), panels of at most `capacity` doubles.  Two schedules: PLM_PANEL_DOUBLES panels for the throughput kernel (four CTAs per SM), whole stages
-    // for the latency kernel (one CTA per SM, shared memory to spare).
-    auto build = [&](int capacity, int32_t wr[PLM_WR_TABLES][5], int32_t& f_sched, int32_t& n_sched, int32_t& panel_doubles) {
+    // panel schedules: forward sweep stages 0..N (row panels of the cyclic-diagonal array of S_i^-1), backward sweep
+    // stages N-1..0 (column panels of B_i), panels of at most `capacity` doubles.  Two schedules: PLM_PANEL_DOUBLES panels
+    // for the throughput kernel (four CTAs per SM), whole stages for the latency kernel (one CTA per SM, shared memory to spare).
+    auto build = [&](int capacity, int32_t& f_sched, int32_t& n_sched, int32_t& panel_doubles) {
       std::vector<int> sched;
-      auto stage_cuts = [&](int s) {
-        std::vector<int> cuts(1, 0);
-        int r = 0;
-        while (r < s) {
-          int r1 = r + 1;
-          while (r1 < s && (r1 + 1) * (r1 + 2) / 2 - r * (r + 1) / 2 <= capacity) ++r1;
-          cuts.push_back(r1);
-          r = r1;
-        }
-        return cuts;
-      };
-      // rows owned by each of the four warps of a part: ranges of <= 32 rows that do not straddle a panel when four
-      // warps suffice for that, else plain blocks of 32 (table id = node type, PLM_WR_TABLES - 1 for the final stage)
-      auto warp_ranges = [&](int s, int32_t* w) {
-        const std::vector<int> cuts = stage_cuts(s);
-        std::vector<int> bnd(1, 0);
-        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
-          const int rows = cuts[k + 1] - cuts[k], nw = (rows + 31) / 32;
-          for (int q = 1; q <= nw; ++q) bnd.push_back(cuts[k] + (int)((long long)rows * q / nw));
-        }
-        if ((int)bnd.size() - 1 > 4) { bnd.assign(1, 0); for (int q = 1; q <= 4; ++q) bnd.push_back(std::min(s, 32 * q)); }
-        while ((int)bnd.size() < 5) bnd.push_back(s);
-        for (int q = 0; q < 5; ++q) w[q] = bnd[q];
-      };
-      for (int t = 0; t < L.ntypes; ++t) warp_ranges(ndx + L.types[t].nu, wr[t]);
-      warp_ranges(ndx, wr[PLM_WR_TABLES - 1]);
       int maxlen = 0;
       auto add_stage = [&](int i, int dir) {
         const int s = (i < N) ? ndx + nu[i] : ndx;
-        const std::vector<int> cuts = stage_cuts(s);
-        const int table = (i < N) ? L.node_type[i] : PLM_WR_TABLES - 1;
-        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
-          const int r0 = cuts[k], r1 = cuts[k + 1];
-          int o0 = r0 * (r0 + 1) / 2, o1 = r1 * (r1 + 1) / 2;
+        const int rows = plm_sinv_rows(s);
+        const int maxrows = std::max(1, (capacity - 2) / s);      // (- 2: the copy starts / ends on 16-byte boundaries)
+        const int npan = (rows + maxrows - 1) / maxrows;
+        for (int k = 0; k < npan; ++k) {
+          const int r0 = (int)((long long)rows * k / npan), r1 = (int)((long long)rows * (k + 1) / npan);
+          const int o0 = r0 * s, o1 = r1 * s;
           const int start = o0 & ~1;                       // 16-byte aligned start (stage blocks start even)
           const int len = ((o1 - start) + 1) & ~1;
           maxlen = std::max(maxlen, len);
           sched.push_back(Q.fac_off[i] + start); sched.push_back(len); sched.push_back(r0); sched.push_back(r1);
           sched.push_back(i);
-          sched.push_back(dir | ((k == 0) << 1) | ((k + 2 == cuts.size()) << 2) | (table << 3));
+          sched.push_back(dir | ((k == 0) << 1) | ((k + 1 == npan) << 2));
           sched.push_back(start);
           sched.push_back(s | (L.x_off[i] << 8));
         }
@@ -551,7 +526,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
           maxlen = std::max(maxlen, len);
           sched.push_back(Q.bk_off[i] + j0 * sp); sched.push_back(len); sched.push_back(j0); sched.push_back(j1);
           sched.push_back(i);
-          sched.push_back(1 | ((k == 0) << 1) | ((k + 1 == npan) << 2) | (L.node_type[i] << 3));
+          sched.push_back(1 | ((k == 0) << 1) | ((k + 1 == npan) << 2));
           sched.push_back(sp);
           sched.push_back(s | (L.x_off[i] << 8));
         }
@@ -564,8 +539,8 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       for (int v : sched) out.qp_idx32.push_back(v);
       panel_doubles = (maxlen + 1) & ~1;
     };
-    build(PLM_PANEL_DOUBLES, Q.wr, Q.f_sched, Q.n_sched, Q.panel_doubles);
-    build(Q.smax * (Q.smax + 1) / 2 + 2, Q.wr_lat, Q.f_sched_lat, Q.n_sched_lat, Q.panel_doubles_lat);
+    build(PLM_PANEL_DOUBLES, Q.f_sched, Q.n_sched, Q.panel_doubles);
+    build(plm_sinv_rows(Q.smax) * Q.smax + 4, Q.f_sched_lat, Q.n_sched_lat, Q.panel_doubles_lat);
     Q.g_doubles = 4 * ndx;                                         // compact coupling block of one stage: <= 4 entries per integrator row
   }
   Q.max_iter = ocp.osqp_max_iter; Q.check_termination = ocp.osqp_check_termination; Q.scaling = ocp.osqp_scaling;

@@ -411,7 +411,8 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
         __syncthreads();
       }
     }
-    // ---- S_i^-1 = X^T X (packed lower): what the ADMM sweeps multiply with (one symmetric product per stage visit).
+    // ---- S_i^-1 = X^T X, stored by cyclic diagonals (plm_qp_types.h): what the ADMM sweeps multiply with (one
+    // symmetric product per stage visit).
     // 8x8 output tiles on the FP64 tensor cores: S[r][c] = sum_{t >= r} X[t][r] X[t][c], four rows t of X per DMMA.
     {
       const int warp = tid >> 5, lane = tid & 31;
@@ -437,11 +438,13 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
         }
         const int cc = c0 + 2 * fk;
         if (ra < s) {
-          if (cc <= ra) So[tri(ra, cc)] = d0;
-          if (cc + 1 <= ra) So[tri(ra, cc + 1)] = d1;
+          if (cc <= ra) So[plm_sinv_index(s, ra, cc)] = d0;
+          if (cc + 1 <= ra) So[plm_sinv_index(s, ra, cc + 1)] = d1;
         }
        }
       }
+      // even s: the second half of the last cyclic diagonal repeats the first; it is stored as zeros
+      if (!(s & 1) && tid < (s >> 1)) So[(s >> 1) * s + (s >> 1) + tid] = 0.0;
     }
     if (last) break;
     // ---- coupling to stage i+1: G = diag(g) * A_int,loc ; W = X G^T ; K = W^T W
@@ -465,7 +468,7 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
           const int ja = sv.ccol[ea];
           for (int eb = eb0; eb < eb1; ++eb) {
             const int jb = sv.ccol[eb];
-            acc += As[ea] * As[eb] * Sg[ja >= jb ? tri(ja, jb) : tri(jb, ja)];
+            acc += As[ea] * As[eb] * Sg[ja >= jb ? plm_sinv_index(s, ja, jb) : plm_sinv_index(s, jb, ja)];
           }
         }
         K[o] = rs[r] * As[ea1] * rs[c2] * As[eb1] * acc;
@@ -482,7 +485,7 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
             const int e0 = sv.rptr[c2], e1 = sv.rptr[c2 + 1] - 1;
             for (int e = e0; e < e1; ++e) {
               const int j = sv.ccol[e];
-              acc += As[e] * Sg[kk >= j ? tri(kk, j) : tri(j, kk)];
+              acc += As[e] * Sg[kk >= j ? plm_sinv_index(s, kk, j) : plm_sinv_index(s, j, kk)];
             }
             acc *= rs[c2] * As[e1];
           }
@@ -620,7 +623,7 @@ __device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const
     if (ADD && o >= 0) add = addv ? addv[o] : sigma * x[o] - __ldg(q + o);      // (x is rewritten by this kernel: coherent load)
     double acc = 0.0;
     // every slot row of a slice is 32 wide (padded), so the row count is warp uniform: full groups of ELL_B rows run
-    // without predicates, the remaining rows one at a time
+    // without predicates
     int p = b0;
     for (; p + 32 * (ELL_B - 1) < b1; p += 32 * ELL_B) {
       double a[ELL_B];
@@ -633,7 +636,18 @@ __device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const
 #pragma unroll
       for (int j = 0; j < ELL_B; ++j) acc += a[j] * v[c[j]];
     }
-    for (; p < b1; p += 32) acc += __ldg(vals + p) * v[(int)__ldg(ind + p)];
+    if (p < b1) {                                 // the remaining rows as one predicated group (all loads in flight at once)
+      double a[ELL_B - 1];
+      int c[ELL_B - 1];
+#pragma unroll
+      for (int j = 0; j < ELL_B - 1; ++j) {
+        const bool ok = p + 32 * j < b1;
+        a[j] = ok ? __ldg(vals + p + 32 * j) : 0.0;
+        c[j] = ok ? (int)__ldg(ind + p + 32 * j) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < ELL_B - 1; ++j) acc += a[j] * v[c[j]];
+    }
     if (o >= 0) out[o] = acc + add;
   }
 }
@@ -677,10 +691,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// The inverse stage blocks S_i^-1 (symmetric, packed lower triangles, row-major) are streamed through shared memory in
-// panels of consecutive rows (<= PLM_PANEL_DOUBLES) by bulk asynchronous copies, NBUF panels deep, following a host-built schedule
-// of one ADMM iteration.  A sweep step is one symmetric product out = S_i^-1 in; each stored element S[t][k] is read
-// once and used twice (row part out[t] += S[t][k] in[k], column part out[k] += S[t][k] in[t], k < t):
+// The inverse stage blocks S_i^-1 (stored by cyclic diagonals, plm_qp_types.h) are streamed through shared memory in
+// panels of consecutive rows j of the stored array (<= PLM_PANEL_DOUBLES) by bulk asynchronous copies, NBUF panels deep,
+// following a host-built schedule of one ADMM iteration.  A sweep step is one symmetric product out = S_i^-1 in; each
+// stored element M[j][c] = S^-1[c][(c + j) mod s] is used twice (out[c] += M in[c + j], out[c + j] += M in[c]):
 //   forward  stage i: tv_i = S_i^-1 (b_i - G_{i-1} tv_{i-1})
 //   backward stage i: x_i  = tv_i - B_i x_{i+1}[0:ndx],  B_i = S_i^-1 G_i^T (s x ndx, from the factor kernel; x_N = tv_N):
 //                     a plain product, column panels of B_i, every element read from shared memory once
@@ -695,94 +709,32 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #define SYM_PARTS_MAX (ADMM_THREADS_LAT / SYM_K)
 static_assert(ADMM_THREADS % SYM_K == 0 && ADMM_THREADS_LAT % SYM_K == 0 && true, "thread layout of sym_panel");
 
-// Thread (k, part) accumulates output k of out = S^-1 in over the resident panel rows [r0, r1): the column walk
-// S[t][k] in[t], t > k (lanes read consecutive addresses) and, when row k is resident, the row walk S[k][e] in[e], e <= k;
-// both walks are split over the SYM_PARTS parts.  No cross-thread reduction inside a stage: the sums live in registers
-// across the panels of the stage.  A warp owns the rows [ws, we) (host table: at most 32 rows, inside one panel
-// whenever four warps suffice for that); the column walk maps lane l to k = ws + l, the row walk to even rows in lanes
-// 0-15 and odd rows in lanes 16-31 (the addresses tri(ws + 2 l) + e of a half-warp fall in 16 distinct 8-byte banks).
-// Both walks advance two rows / columns at a time so that the pair in[t], in[t+1] is one 16-byte load (the walk starts
-// on the 16-byte boundary of `vin`; a leading odd element is handled alone).  `pan` points at the panel buffer,
-// `zp` at a 0.0 in shared memory: masked elements load the zero instead of branching.
-__device__ __forceinline__ double2 lds_pair(const double* p) { return *reinterpret_cast<const double2*>(p); }
-
+// Thread (k, part) accumulates output k of out = S^-1 in over the rows j = r0 + part, r0 + part + P, ... < r1 of the
+// resident panel: the term M[j][k] in[k + j] and the term M[j][k - j] in[k - j] (indices mod s) of every row; row 0 (the
+// diagonal) has the first term only.  Lanes read consecutive addresses in all four loads, every thread of the stage has
+// the same trip count, nothing is masked.  `vd` is the input vector stored twice in a row ([in, in], 2 s doubles), which
+// takes the index wrap off the vector loads; the wrap of the matrix column is one select.  `pan` is the panel buffer
+// moved back by the offset of the copy inside the stage block (element (j, c) at pan[j s + c]).  No cross-thread
+// reduction inside a stage: the sums live in registers across the panels of the stage.
 template <int P>
-__device__ __forceinline__ void sym_panel(const double* __restrict__ pan, const double* __restrict__ zp, int shift, int r0, int r1,
-                                          const double* __restrict__ vin, int ws, int we, double& acc0, double& acc1, double& racc) {
-  const int part = threadIdx.x / SYM_K, lane = threadIdx.x & 31;
-  const int vodd = (int)((reinterpret_cast<size_t>(vin) >> 3) & 1);      // vin + t is 16-byte aligned iff (t + vodd) is even
-  if (ws + 1 < r1 && ws < we) {
-    // ---- column walk: element S[t][k] at tri(t) + k, rows t > k of the panel
-    const int k = ws + lane;
-    const int kk = k < we ? k : 1 << 20;        // lanes beyond the warp's range own nothing: every row is "above" them
-    const int kc = min(k, we - 1);
-    int t = max(r0, ws + 1);                    // warp-uniform start; rows t <= k are masked
-    if ((t + vodd) & 1) {                       // leading row off the 16-byte grid of vin: part 0 takes it alone
-      if (part == 0) {
-        const double* q = (t > kk) ? pan + (tri(t, 0) - shift + kc) : zp;
-        acc0 += *q * vin[t];
-      }
-      ++t;
-    }
-    t += 2 * part;
-    const double* pa = pan + (tri(t, 0) - shift + kc);
-    int dd = 2 * P * t + P * (2 * P + 1);       // tri(t + 2P) - tri(t)
-    const int tm = min(r1, we);
-#pragma unroll 2
-    for (; t < tm; t += 2 * P) {                // masked: the diagonal block of the warp
-      const bool in1 = t + 1 < r1;
-      const double* q0 = (t > kk) ? pa : zp;
-      const double* q1 = (in1 && t + 1 > kk) ? pa + t + 1 : zp;
-      const double a0 = *q0, a1 = *q1;
-      const double2 v = lds_pair(vin + t);      // v.y is finite even beyond the panel (the vectors are zero-initialised)
-      acc0 += a0 * v.x;
-      acc1 += a1 * v.y;
-      pa += dd; dd += 4 * P * P;
-    }
-    if (k < we) {
-#pragma unroll 2
-      for (; t + 1 < r1; t += 2 * P) {
-        const double a0 = pa[0], a1 = pa[t + 1];
-        const double2 v = lds_pair(vin + t);
-        acc0 += a0 * v.x;
-        acc1 += a1 * v.y;
-        pa += dd; dd += 4 * P * P;
-      }
-      if (t < r1) acc0 += pa[0] * vin[t];
-    }
+__device__ __forceinline__ void sym_panel(const double* __restrict__ pan, int s, int r0, int r1, const double* __restrict__ vd, int k, int part,
+                                          double& acc0, double& acc1) {
+  int j = r0 + part;
+  if (j == 0) {
+    acc0 += pan[k] * vd[k];
+    j = P;
   }
-  if (ws < r1 && we > r0) {                      // warp-uniform: some row of this warp is resident
-    // ---- row walk: S[k][e], e <= k.  Lanes whose row is not resident walk a resident row and drop the sums.
-    const int lo = max(ws, r0), hi = min(we, r1);           // resident rows of the warp
-    const int k = ws + ((lane & 15) << 1) + (lane >> 4);
-    const bool mine = k >= lo && k < hi;
-    const int km = mine ? k : -1;
-    const double* row = pan + (tri(min(max(k, lo), hi - 1), 0) - shift);
-    double ra0 = 0.0, ra1 = 0.0;
-    int e = 0;
-    if (vodd) {                                  // column 0 off the 16-byte grid of vin
-      if (part == 0) ra0 += *((0 <= km) ? row : zp) * vin[0];
-      e = 1;
-    }
-    e += 2 * part;
-#pragma unroll 2
-    for (; e + 1 <= lo; e += 2 * P) {            // columns e, e+1 <= lo: below the diagonal block for every lane
-      const double a0 = row[e], a1 = row[e + 1];
-      const double2 v = lds_pair(vin + e);
-      ra0 += a0 * v.x;
-      ra1 += a1 * v.y;
-    }
-    const int kend = hi - 1;
-#pragma unroll 2
-    for (; e <= kend; e += 2 * P) {              // the diagonal block, masked
-      const double* q0 = (e <= km) ? row + e : zp;
-      const double* q1 = (e + 1 <= km) ? row + e + 1 : zp;
-      const double a0 = *q0, a1 = *q1;
-      const double2 v = lds_pair(vin + e);
-      ra0 += a0 * v.x;
-      ra1 += a1 * v.y;
-    }
-    if (mine) racc += ra0 + ra1;
+  const double* pf = pan + j * s + k;         // M[j][k]
+  const double* vf = vd + k + j;               // in[(k + j) mod s]
+  const double* vb = vd + s + k - j;           // in[(k - j) mod s]
+  const int ps = P * s;
+#pragma unroll 4
+  for (; j < r1; j += P) {
+    const int ob = (k < j ? s : 0) - j;        // M[j][(k - j) mod s] relative to M[j][k]
+    const double af = pf[0], ab = pf[ob];
+    acc0 += af * vf[0];
+    acc1 += ab * vb[0];
+    pf += ps; vf += P; vb -= P;
   }
 }
 
@@ -830,15 +782,13 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* gbuf = sm + NB * pdb;                      // [NB][gd] compact coupling block travelling with a stage's first panel
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + ring_al);  // [NB] "panel landed" barriers
   int* cnt = reinterpret_cast<int*>(sm + ring_al + NB);                          // [NB] warps done with the panel (running count)
-  int* wrs = cnt + NB;                                                                // [PLM_WR_TABLES][5] warp row ranges
-  double* xt = sm + ring_al + 2 * NB + 16;   // [n]  rhs -> forward solution y -> x~ -> delta_x
+  double* xt = sm + ring_al + 2 * NB;        // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = ALIAS ? sm : xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   constexpr int SYM_PARTS = NT / SYM_K;
-  constexpr int CP_SLICES = 2 * SYM_PARTS;    // partial sums of the forward product: one slice per part and stage parity
-  double* cpart = xt + n + (ALIAS ? 0 : m);       // [CP_SLICES][smax]
-  double* red = cpart + CP_SLICES * smax;     // [32]
-  double* zp = red + 32;       // one 0.0 (target of masked loads in sym_panel)
-  double* gcs = zp + 2;        // [ncoup_max] general coupling only: rho_q (a_q . tv_{i-1}) of the coupling rows
+  double* cpart = xt + n + (ALIAS ? 0 : m);       // [SYM_PARTS][smax] partial sums of the forward product, one slice per part
+  double* vd = cpart + SYM_PARTS * smax;      // [2 smax] input of the forward product, stored twice in a row (sym_panel)
+  double* red = vd + 2 * smax;                // [32]
+  double* gcs = red + 32;      // [ncoup_max] general coupling only: rho_q (a_q . tv_{i-1}) of the coupling rows
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
   const double* AR = W.AhatR + (size_t)b * Q.rell_total;
@@ -881,13 +831,9 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   // mbarrier, and the last warp to finish step q refills the buffer with step q + NB.
   if (tid == 0) {
     for (int k = 0; k < NB; ++k) { mbar_init(&bars[k], 1); cnt[k] = 0; }
-    for (int k = 0; k < PLM_WR_TABLES * 5; ++k) wrs[k] = LAT ? Q.wr_lat[k / 5][k % 5] : Q.wr[k / 5][k % 5];
-    *zp = 0.0;
-    zp[1] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // 16-byte loads of sym_panel may read one element past a stage vector: keep every shared vector finite
-  for (int j = tid; j < (int)(zp + 2 - xt); j += nth) xt[j] = 0.0;
+  for (int j = tid; j < (int)(gcs - xt); j += nth) xt[j] = 0.0;
   if (ALIAS) for (int j = tid; j < ring_al; j += nth) sm[j] = 0.0;
   __syncthreads();
   unsigned used = 0;
@@ -951,8 +897,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     }
     PROF_ADD(0);
     // ---- forward and backward sweeps, one schedule step = one row panel of one inverse stage block
-    double acc0 = 0.0, acc1 = 0.0, racc = 0.0;
-    int ws = 0, we = 0;                       // rows of the current stage owned by this warp
+    double acc0 = 0.0, acc1 = 0.0;
     int bk = -1;                              // backward steps: output of this thread (-1: none)
     int pend = -1, pend_st = 0;               // lane 0: deferred refill check of the previous step
     int4 S0 = __ldg(reinterpret_cast<const int4*>(sched));
@@ -962,11 +907,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const int s = S1.w & 255;
       double* bi = xt + (S1.w >> 8);
       const int bsel = (int)(used % NB);
-      if (first) {
-        if (dir == 0) { ws = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3)]; we = wrs[(S1.y >> 3) * 5 + ((tid >> 5) & 3) + 1]; }
-        else bk = tid < s ? tid : -1;     // backward: one warp per 32 outputs over all the columns (no partial sums: the
-                                          // result goes straight into x_i and the stage needs one CTA barrier)
-      }
+      if (first && dir) bk = tid < s ? tid : -1;     // backward: one warp per 32 outputs over all the columns (no partial
+                                                     // sums: the result goes straight into x_i and the stage needs one CTA barrier)
       {   // schedule entry of the next step (consumed at the end of this one)
         const int nst = st + 1 < nsched ? st + 1 : 0;
         S0 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS));
@@ -984,12 +926,18 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (first) {
         const double* g = gbuf + bsel * gd;
         if (dir == 0) {
+          // the input b_i of the product goes to vd twice in a row (sym_panel); its first ndx entries come out of the
+          // coupling step below
+          {
+            const int c = (i > 0 ? ndx : 0) + tid;
+            if (c < s) { const double v = bi[c]; vd[c] = v; vd[c + s] = v; }
+          }
           if (i > 0) {     // b_i -= G_{i-1} tv_{i-1}
             const StageView sp = stage_view(L, Q, idx, i - 1);
-            // tv_{i-1} still sits in the partial sums of the parts (one slice set per stage parity): they are added up
-            // here, on read, which saves the combine pass and its CTA barrier; the sum also goes to stage i-1's slice
-            // of xt, where the backward sweep expects it
-            const double* pp = cpart + ((i - 1) & 1) * SYM_PARTS * smax;
+            // tv_{i-1} still sits in the partial sums of the parts: they are added up here, on read, which saves the
+            // combine pass and its CTA barrier; the sum also goes to stage i-1's slice of xt, where the backward sweep
+            // expects it
+            const double* pp = cpart;
             auto tprev = [&](int k) {
               double v = pp[k];
 #pragma unroll
@@ -1025,7 +973,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
               if (tid < ndx) {
                 double acc = 0.0;
                 for (int e = sp.cptr[sprev + tid]; e < sp.cptr[sprev + tid + 1]; ++e) acc += Ap[sp.cpos[e]] * gcs[rowq[sp.crow[e]]];
-                bi[tid] -= acc;
+                const double nv = bi[tid] - acc;
+                vd[tid] = nv; vd[tid + s] = nv;
               }
             } else if (sparse) {
               if (tid < ndx) {
@@ -1033,7 +982,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
                 double acc = 0.0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc += g[4 * tid + j] * tprev(sp.ccol[e0 + (j < ne ? j : 0)]);
-                bi[tid] -= acc;
+                const double nv = bi[tid] - acc;
+                vd[tid] = nv; vd[tid + s] = nv;
               }
             } else {
               // dense integrator rows (whole_body_aba, centroidal_vel): eight lanes per row, shuffle reduction
@@ -1051,16 +1001,21 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
                 acc += __shfl_xor_sync(0xffffffffu, acc, 4);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                if (c2 < ndx && sub == 0) bi[c2] -= rp[c2] * Ap[e1] * acc;
+                if (c2 < ndx && sub == 0) {
+                  const double nv = bi[c2] - rp[c2] * Ap[e1] * acc;
+                  vd[c2] = nv; vd[c2 + s] = nv;
+                }
               }
             }
-            __syncthreads();
           }
+          __syncthreads();
           PROF_ADD(1);
         }
-        acc0 = 0.0; acc1 = 0.0; racc = 0.0;
+        acc0 = 0.0; acc1 = 0.0;
       }
-      if (dir == 0) sym_panel<SYM_PARTS>(pbuf + bsel * pdb, zp, shift, r0, r1, bi, ws, we, acc0, acc1, racc);
+      if (dir == 0) {
+        if ((tid & (SYM_K - 1)) < s) sym_panel<SYM_PARTS>(pbuf + bsel * pdb - shift, s, r0, r1, vd, tid & (SYM_K - 1), tid / SYM_K, acc0, acc1);
+      }
       else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
       if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
       {
@@ -1068,22 +1023,15 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         // shared-memory read of the panel by this warp has returned; the refill check is deferred past the next wait
         const double sum = acc0 + acc1;
         int zero;
-        // (racc depends on the row-walk loads the same way: fold it into the dependency)
-        asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(__double2loint(sum) ^ __double2loint(racc)));
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(__double2loint(sum)));
         __syncwarp();
         if ((tid & 31) == 0) { pend = atomicAdd(&cnt[bsel], 1 + zero); pend_st = st; }
         ++used;
         PROF_ADD(3);
         if (last) {
-          // combine: out[k] = sum over the parts; the column-walk sums and the row-walk sums of a warp cover the same
-          // rows in two lane orders
+          // forward: the sum of this part goes to its slice (the parts are added up by the reader)
           if (dir == 0) {
-            const int lane = tid & 31;
-            const int k = ws + lane, kr = ws + ((lane & 15) << 1) + (lane >> 4);
-            double* cp = cpart + ((i & 1) * SYM_PARTS + tid / SYM_K) * smax;
-            if (k < we) cp[k] = sum;
-            __syncwarp();
-            if (kr < we) cp[kr] += racc;
+            if ((tid & (SYM_K - 1)) < s) cpart[(tid / SYM_K) * smax + (tid & (SYM_K - 1))] = sum;
           }
           else if (bk >= 0) bi[bk] -= sum;       // nothing else reads stage i's slice of xt during its backward step
         }
@@ -1102,9 +1050,9 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         // the last one (x_N = tv_N is the first input of the backward sweep)
         if (dir == 1 || i < N) continue;
         if (tid < s) {
-          double o = cpart[(i & 1) * SYM_PARTS * smax + tid];
+          double o = cpart[tid];
 #pragma unroll
-          for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[((i & 1) * SYM_PARTS + w2) * smax + tid];
+          for (int w2 = 1; w2 < SYM_PARTS; ++w2) o += cpart[w2 * smax + tid];
           bi[tid] = o;
         }
         __syncthreads();
@@ -1346,8 +1294,8 @@ int plm_qp_alloc(plm_handle* h) {
   if (Q.general_coupling) h->smem_factor += (size_t)(smax * Q.ncoup_max + Q.ncoup_max * ndx) * 8;     // Y, Nn
   // throughput kernel: w aliases the panel ring
   const int gcn = Q.general_coupling ? Q.ncoup_max : 0;
-  h->smem_admm = (size_t)(((std::max(NBUF * (Q.panel_doubles + Q.g_doubles), L.m) + 1) & ~1) + 2 * NBUF + L.n + 2 * (ADMM_THREADS / SYM_K) * smax + 32 + 2 + 16 + gcn) * 8;
-  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + 2 * (ADMM_THREADS_LAT / SYM_K) * smax + 32 + 2 + 16 + gcn) * 8;
+  h->smem_admm = (size_t)(((std::max(NBUF * (Q.panel_doubles + Q.g_doubles), L.m) + 1) & ~1) + 2 * NBUF + L.n + (ADMM_THREADS / SYM_K + 2) * smax + 32 + gcn) * 8;
+  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + (ADMM_THREADS_LAT / SYM_K + 2) * smax + 32 + gcn) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024 || h->smem_admm_lat > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";

@@ -6,15 +6,30 @@
 
 namespace plm {
 
-// A stage factor (packed lower triangle, row-major) is streamed through shared memory in panels of consecutive rows.
-#define PLM_PANEL_DOUBLES 2192        // 17 KB: two panels per B2G stage in either sweep, four CTAs per SM
+// The symmetric inverse S^-1 of a stage block (s x s) is stored by cyclic diagonals: row j of the stored array M
+// (j = 0 .. s/2, s doubles each) holds M[j][k] = S^-1[k][(k + j) mod s].  Every unordered pair {a, b} appears exactly
+// once (for even s the second half of row s/2 repeats the first and is stored as zeros), so the array has the size of
+// the packed triangle, and the product out = S^-1 in needs no masks:
+//   out[k] = M[0][k] in[k] + sum_{j >= 1} ( M[j][k] in[(k + j) mod s] + M[j][(k - j) mod s] in[(k - j) mod s] ).
+// Element (r, c), r >= c, lives at plm_sinv_index(s, r, c).  The array is streamed through shared memory in panels of
+// consecutive rows j.
+#define PLM_PANEL_DOUBLES 2192        // 17 KB: three panels per B2G stage in either sweep, four CTAs per SM
 // schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage,
-// flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage,
-// bits 3.. warp row-range table),
+// flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage),
 // offset of the copy inside the stage block, stage size | x_off << 8}
 // A backward step streams columns [first, end) of B_i instead (all s rows of each); the seventh int is the column stride sp.
 #define PLM_SCHED_INTS 8
-#define PLM_WR_TABLES 5   // warp row-range tables: one per node type + the final stage
+
+#if defined(__CUDACC__)
+#define PLM_QP_HD __host__ __device__
+#else
+#define PLM_QP_HD
+#endif
+PLM_QP_HD inline int plm_sinv_rows(int s) { return (s >> 1) + 1; }
+PLM_QP_HD inline int plm_sinv_index(int s, int r, int c) {      // r >= c
+  const int d = r - c;
+  return d <= (s >> 1) ? d * s + c : (s - d) * s + r;
+}
 
 // Per node-type local sparsity tables (offsets into one int16 pool).  Local columns of a node block are
 // [0, s) = this stage (DX_i | U_i) and [s, s + ndx) = DX_{i+1}; local rows are the node's rows in g order.
@@ -50,12 +65,10 @@ struct QpLayout {
   int32_t f_cell_base, f_cell_src, f_cell_ind, n_cslices, cell_total;
   int32_t f_sched, n_sched;            // int32 pool: panel schedule of one ADMM iteration, 8 ints per step
   int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
-  int32_t wr[PLM_WR_TABLES][5];        // rows [wr[q], wr[q+1]) of a stage are owned by warp q of each part (ADMM kernel)
   // the same for the latency kernel (whole stages as panels)
   int32_t f_sched_lat, n_sched_lat, panel_doubles_lat;
-  int32_t wr_lat[PLM_WR_TABLES][5];
   int32_t g_doubles;                   // doubles of one stage's compact coupling block (4 per integrator row)
-  int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's packed inverse factor
+  int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's inverse block (cyclic diagonals, see above)
   int32_t bk_off[PLM_MAXNODES + 1];    // offset (doubles) of stage i's back-substitution block B_i = S_i^-1 G_i^T, i < N:
                                        // column major [ndx][sp], sp = s rounded up to even
   int32_t fac_total;                   // everything the ADMM iterations stream: the S_i^-1 and the B_i
@@ -84,7 +97,7 @@ struct QpWork {
   double* lh = nullptr;      // [m]     E l
   double* uh = nullptr;      // [m]     E u
   double* rho = nullptr;     // [m]     rho_vec
-  double* Linv = nullptr;    // [fac_total] packed inverse stage blocks S_i^-1, then the back-substitution blocks B_i
+  double* Linv = nullptr;    // [fac_total] inverse stage blocks S_i^-1 (cyclic diagonals), then the back-substitution blocks B_i
   double* Gc = nullptr;      // [nodes][ndx][4] compact coupling blocks diag(rho n) A_int (sparse couplings only)
   double* x = nullptr;       // [n]     persistent scaled ADMM iterates
   double* z = nullptr;       // [m]

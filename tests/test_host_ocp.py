@@ -100,8 +100,9 @@ def test_retract_integrates_on_the_manifold(robots):
 @pytest.mark.parametrize("rn,kind,N", [("b2g", "whole_body_rnea", 20), ("b2", "centroidal_acc", 7), ("go2", "centroidal_vel", 5),
                                        ("b2g", "whole_body_aba", 6)])
 def test_stored_qp_factor_size(robots, rn, kind, N):
-    """kkt_factor_doubles (the nnz(F) of SURVEY 8d that bench.py reports) = packed inverse stage blocks S_i^-1 (stages 0..N,
-    16-byte aligned) plus the back-substitution blocks B_i = S_i^-1 G_i^T (ndx columns of the stage size rounded up to even)."""
+    """kkt_factor_doubles (the nnz(F) of SURVEY 8d that bench.py reports) = inverse stage blocks S_i^-1 stored by cyclic
+    diagonals (stages 0..N: s/2 + 1 rows of s doubles, the size of the packed triangle for odd s, 16-byte aligned) plus the
+    back-substitution blocks B_i = S_i^-1 G_i^T (ndx columns of the stage size rounded up to even)."""
     from pino_locoman_b200 import OCP_ARGS
     from pino_locoman_b200.optimization import make_ocp
     prod, _ = robots
@@ -109,11 +110,11 @@ def test_stored_qp_factor_size(robots, rn, kind, N):
     h = ocp.handle
     ndx = h.ndx
     sizes = [ndx + nu for nu in h.nu] + [ndx]
-    packed = sum((s * (s + 1) // 2 + 1) & ~1 for s in sizes)
+    packed = sum(((s // 2 + 1) * s + 1) & ~1 for s in sizes)
     back = sum(ndx * ((s + 1) & ~1) for s in sizes[:-1])
     assert h.dims.kkt_factor_doubles == packed + back
     if (rn, kind, N) == ("b2g", "whole_body_rnea", 20):
-        assert (h.n, h.m) == (1842, 2665) and h.dims.kkt_factor_doubles == 170022
+        assert (h.n, h.m) == (1842, 2665) and h.dims.kkt_factor_doubles == 170046
 
 
 @pytest.mark.parametrize("rn,kind", [("go2", "centroidal_vel"), ("b2g", "whole_body_aba"), ("b2", "centroidal_acc"), ("b2g", "whole_body_rnea"),
