@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace plm {
 
@@ -539,7 +540,9 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       for (int v : sched) out.qp_idx32.push_back(v);
       panel_doubles = (maxlen + 1) & ~1;
     };
-    build(PLM_PANEL_DOUBLES, Q.f_sched, Q.n_sched, Q.panel_doubles);
+    int cap = PLM_PANEL_DOUBLES;
+    if (const char* e = getenv("PLM_PANEL_DOUBLES")) cap = std::max(256, atoi(e));      // tuning hook (tools/ab_libs.sh)
+    build(cap, Q.f_sched, Q.n_sched, Q.panel_doubles);
     build(plm_sinv_rows(Q.smax) * Q.smax + 4, Q.f_sched_lat, Q.n_sched_lat, Q.panel_doubles_lat);
     Q.g_doubles = 4 * ndx;                                         // compact coupling block of one stage: <= 4 entries per integrator row
   }

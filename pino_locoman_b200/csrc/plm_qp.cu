@@ -187,7 +187,10 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
-__global__ void __launch_bounds__(QP_THREADS, 3)
+#ifndef PLM_FACTOR_MIN_CTAS
+#define PLM_FACTOR_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(QP_THREADS, PLM_FACTOR_MIN_CTAS)
 qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, QpWork W, int* __restrict__ fail) {
   extern __shared__ double sm[];
   const PlmLayout& L = *tab.layout;
@@ -197,15 +200,15 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   const int tsz = smax * (smax + 1) / 2;
   double* H = sm;                      // [tsz]  stage block -> (in place) inverse X = L^-1 of its Cholesky factor, packed lower
   double* Wm = H + tsz;                // [smax][ndx]  W = X G^T (dense coupling only)
-  double* K = Wm + (Q.sparse_coupling ? 0 : smax * ndx);   // [ndx (ndx+1)/2] Schur term for the next stage, packed lower
-  double* gsc = K + ndx * (ndx + 1) / 2;   // [ndx]  rho_r * (next entry)^2 of the integrator rows
-  double* colk = gsc + ndx;            // [smax] current Cholesky column
-  double* rowk = colk + smax;          // [smax] current row of the inverse
-  double* col1 = rowk + smax;          // [smax] second column / row of a rank-2 step
-  double* row1 = col1 + smax;
-  double* La = row1 + smax;            // [4][smax] rank-4 step: minus the four new columns of L (rows below the block)
-  double* As = La + 4 * smax;          // [max_nnz] scaled A values of the node block
-  double* rs = As + L.max_nnz;         // [max_rows] rho of the node rows
+  // K: [ndx (ndx+1)/2] Schur term for the next stage, packed lower.  It is written at the end of a stage and consumed by
+  // the assembly of the next one; in between (factorisation) the same shared memory is the scratch of the blocked steps:
+  // Tm [8][smax] and dsc [72].
+  double* K = Wm + (Q.sparse_coupling ? 0 : smax * ndx);
+  const int ksz = max(ndx * (ndx + 1) / 2, 8 * smax + 72);
+  double* gsc = K + ksz;               // [ndx]  rho_r * (next entry)^2 of the integrator rows
+  double* rs = gsc + ndx;              // [max_rows] rho of the node rows
+  // The scaled A values of the node block are staged behind the stage block when the stage is smaller than the largest
+  // one (17 of the 20 B2G stages), else read from global memory (L1 / L2): what this saves lets four CTAs share an SM.
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* Ph = W.Ph + (size_t)b * n;
   const double* rho = W.rho + (size_t)b * m;
@@ -218,11 +221,17 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     if (!last) sv = stage_view(L, Q, idx, i);
     const int s = last ? ndx : sv.s;
     const int xo = L.x_off[i];
+    const double* As = nullptr;
     if (!last) {   // stage the node's values in shared memory: every entry is used many times below
       const double* An = Ah + L.nnz_off[i];
       const double* rh = rho + L.row_off[i];
       const int nnz_i = L.types[L.node_type[i]].nnz;
-      for (int e = tid; e < nnz_i; e += nth) As[e] = An[e];
+      const int hsz = (s * (s + 1) / 2 + 1) & ~1;
+      if (tsz - hsz >= nnz_i) {
+        double* Asm = H + hsz;
+        for (int e = tid; e < nnz_i; e += nth) Asm[e] = An[e];
+        As = Asm;
+      } else As = An;
       for (int r = tid; r < sv.nrows; r += nth) rs[r] = rh[r];
     }
     __syncthreads();
@@ -269,14 +278,14 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
     //      again); one thread per row below solves L[r, J] = H[r, J] L_JJ^-T with that inverse.
     //   P2 (row block I, top down): X[I, 0:i0] = -L_II^-1 (L[I, 0:i0] X[0:i0, 0:i0]), X[I, I] = L_II^-1 (already there):
     //      tiles of the product into a scratch row block, then one thread per column applies -L_II^-1.
-    // Rows / columns beyond s (ragged last block) are masked; Tm (8 x smax scratch) aliases the step vectors.
+    // Rows / columns beyond s (ragged last block) are masked; Tm (8 x smax scratch) and dsc alias K.
     {
       const int warp = tid >> 5, lane = tid & 31;
       constexpr int nw = QP_THREADS >> 5;
       const int fr = lane >> 2, fk = lane & 3;
       const int nb8 = (s + 7) >> 3;
-      double* Tm = colk;                    // [8][smax]: colk | rowk | col1 | row1 | La (contiguous)
-      double* dsc = K;                      // [64 + 8] scratch of the diagonal-block step (K is dead until the end of the stage)
+      double* Tm = K;                       // [8][smax] (K is dead until the end of the stage)
+      double* dsc = K + 8 * smax;           // [64 + 8] scratch of the diagonal-block step
       for (int Jb = 0; Jb < nb8; ++Jb) {
         const int j0 = 8 * Jb;
         // (1) update of block column J
@@ -703,7 +712,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #define ADMM_THREADS 256
 #define ADMM_MIN_CTAS 4
 #define ADMM_THREADS_LAT 512
+#ifndef NBUF
 #define NBUF 2        // ring of panel buffers, throughput kernel
+#endif
 #define NBUF_LAT 3    // latency kernel (whole stages)
 #define SYM_K 128    // threads per part: thread (k, part) owns output k of the stage (stage size <= SYM_K), part = tid / SYM_K
 #define SYM_PARTS_MAX (ADMM_THREADS_LAT / SYM_K)
@@ -755,6 +766,30 @@ __device__ __forceinline__ void rect_panel(const double* __restrict__ pan, int s
     a += 4 * sp;
   }
   for (; j < j1; ++j) { acc0 += a[0] * vin[j]; a += sp; }
+  acc0 += s2;
+  acc1 += s3;
+}
+// The same with the columns dealt to the two halves of a warp (lanes 0-15: even columns of the panel, lanes 16-31: odd
+// ones; output k = 16 warp + (lane & 15)): all eight warps share the step, the halves are added up by one shuffle at
+// the end of the stage.
+#ifndef PLM_RECT_SPLIT
+#define PLM_RECT_SPLIT 0
+#endif
+__device__ __forceinline__ void rect_panel_split(const double* __restrict__ pan, int sp, int j0, int j1, const double* __restrict__ vin, int k,
+                                                 int half, double& acc0, double& acc1) {
+  int j = j0 + half;
+  const double* a = pan + half * sp + k;
+  const int sp2 = 2 * sp;
+  double s2 = 0.0, s3 = 0.0;
+  for (; j + 6 < j1; j += 8) {
+    const double a0 = a[0], a1 = a[sp2], a2 = a[2 * sp2], a3 = a[3 * sp2];
+    acc0 += a0 * vin[j];
+    acc1 += a1 * vin[j + 2];
+    s2 += a2 * vin[j + 4];
+    s3 += a3 * vin[j + 6];
+    a += 4 * sp2;
+  }
+  for (; j < j1; j += 2) { acc0 += a[0] * vin[j]; a += sp2; }
   acc0 += s2;
   acc1 += s3;
 }
@@ -907,8 +942,12 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const int s = S1.w & 255;
       double* bi = xt + (S1.w >> 8);
       const int bsel = (int)(used % NB);
+#if PLM_RECT_SPLIT
+      if (first && dir) { const int kb2 = 16 * (tid >> 5) + (tid & 15); bk = kb2 < s ? kb2 : -1; }
+#else
       if (first && dir) bk = tid < s ? tid : -1;     // backward: one warp per 32 outputs over all the columns (no partial
                                                      // sums: the result goes straight into x_i and the stage needs one CTA barrier)
+#endif
       {   // schedule entry of the next step (consumed at the end of this one)
         const int nst = st + 1 < nsched ? st + 1 : 0;
         S0 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS));
@@ -1016,7 +1055,11 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (dir == 0) {
         if ((tid & (SYM_K - 1)) < s) sym_panel<SYM_PARTS>(pbuf + bsel * pdb - shift, s, r0, r1, vd, tid & (SYM_K - 1), tid / SYM_K, acc0, acc1);
       }
+#if PLM_RECT_SPLIT
+      else if (bk >= 0) rect_panel_split(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, (tid >> 4) & 1, acc0, acc1);
+#else
       else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
+#endif
       if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
@@ -1033,7 +1076,14 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           if (dir == 0) {
             if ((tid & (SYM_K - 1)) < s) cpart[(tid / SYM_K) * smax + (tid & (SYM_K - 1))] = sum;
           }
+#if PLM_RECT_SPLIT
+          else {
+            const double tot = sum + __shfl_xor_sync(0xffffffffu, sum, 16);
+            if (bk >= 0 && !(tid & 16)) bi[bk] -= tot;
+          }
+#else
           else if (bk >= 0) bi[bk] -= sum;       // nothing else reads stage i's slice of xt during its backward step
+#endif
         }
       }
       if (last) {
@@ -1289,7 +1339,7 @@ int plm_qp_alloc(plm_handle* h) {
   const int smax = Q.smax, ndx = L.ndx;
   h->smem_scale = (size_t)(L.n + L.m + 32) * 8;
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
-  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + ndx * (ndx + 1) / 2 + ndx + 8 * smax + L.max_nnz + L.max_rows + 2) * 8;
+  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + std::max(ndx * (ndx + 1) / 2, 8 * smax + 72) + ndx + L.max_rows + 2) * 8;
   if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
   if (Q.general_coupling) h->smem_factor += (size_t)(smax * Q.ncoup_max + Q.ncoup_max * ndx) * 8;     // Y, Nn
   // throughput kernel: w aliases the panel ring
