@@ -81,4 +81,21 @@ void emu_node_eval(const Emu* e, const double* x, const double* p, int batch, do
         default: run_node<PLM_WHOLE_BODY_RNEA>(e->t, x, p, b, i, g, Jv, want_jac); break;
       }
 }
+// storage of a symmetric inverse stage block by cyclic diagonals (plm_qp_types.h): the index arithmetic shared by the
+// factor kernel (writer) and the ADMM kernel (reader), and the forward panels of the host-built schedule
+int emu_sinv_rows(int s) { return plm_sinv_rows(s); }
+int emu_sinv_index(int s, int r, int c) { return plm_sinv_index(s, r, c); }
+int emu_qp_schedule(const Emu* e, int latency, int* out, int cap) {
+  const QpLayout& Q = e->t.qp;
+  const int n = latency ? Q.n_sched_lat : Q.n_sched, off = latency ? Q.f_sched_lat : Q.f_sched;
+  for (int k = 0; k < n * PLM_SCHED_INTS && k < cap; ++k) out[k] = e->t.qp_idx32[off + k];
+  return n;
+}
+void emu_qp_factor_offsets(const Emu* e, int* fac_off, int* bk_off, int* panel_doubles) {
+  const QpLayout& Q = e->t.qp;
+  const int N = e->t.layout.nodes;
+  for (int i = 0; i <= N + 1; ++i) fac_off[i] = Q.fac_off[i];
+  for (int i = 0; i <= N; ++i) bk_off[i] = Q.bk_off[i];
+  panel_doubles[0] = Q.panel_doubles; panel_doubles[1] = Q.panel_doubles_lat; panel_doubles[2] = Q.fac_total;
+}
 }

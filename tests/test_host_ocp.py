@@ -142,3 +142,78 @@ def test_bench_synthetic_inputs_cover_every_formulation(robots, rn, kind):
         assert np.all(f[..., 2] >= 0.0)
     x2, p2 = bench.synthetic_inputs(prod[rn], ocp, B, 0)      # seeded: identical bits on every call (CPU and GPU arms)
     assert np.array_equal(x, x2) and np.array_equal(p, p2)
+
+
+def test_cyclic_diagonal_storage_of_the_inverse_blocks():
+    """S^-1 of a stage is stored by cyclic diagonals M[j][k] = S^-1[k][(k + j) mod s] (plm_qp_types.h): every pair (r >= c)
+    has one slot, the array has the size of the packed triangle (plus s/2 zeros for even s), and the mask-free product of
+    the ADMM kernel's sym_panel reproduces S^-1 v."""
+    from emu_util import build_emu
+    lib = build_emu()
+    rng = np.random.default_rng(3)
+    for s in (1, 2, 5, 48, 87, 105, 128):
+        rows = lib.emu_sinv_rows(s)
+        assert rows == s // 2 + 1
+        S = rng.standard_normal((s, s))
+        S = S + S.T
+        M = np.zeros(rows * s)
+        hit = np.zeros(rows * s, dtype=int)
+        for r in range(s):
+            for c in range(r + 1):
+                k = lib.emu_sinv_index(s, r, c)
+                assert 0 <= k < rows * s
+                hit[k] += 1
+                M[k] = S[r, c]
+        assert hit.max() == 1
+        free = np.flatnonzero(hit == 0)
+        if s % 2:
+            assert free.size == 0 and rows * s == s * (s + 1) // 2
+        else:      # second half of the last diagonal: stored as zeros
+            assert np.array_equal(free, (s // 2) * s + s // 2 + np.arange(s // 2))
+        M = M.reshape(rows, s)
+        v = rng.standard_normal(s)
+        k = np.arange(s)
+        out = M[0] * v
+        for j in range(1, rows):
+            out += M[j] * v[(k + j) % s] + M[j][(k - j) % s] * v[(k - j) % s]
+        assert np.abs(out - S @ v).max() < 1e-12 * max(1.0, np.abs(S @ v).max())
+
+
+@pytest.mark.parametrize("rn,kind,N", [("b2g", "whole_body_rnea", 20), ("go2", "centroidal_vel", 5), ("b2g", "whole_body_aba", 6)])
+def test_admm_panel_schedule_covers_every_stored_double_once(robots, rn, kind, N):
+    """The host-built panel schedules of one ADMM iteration (throughput and latency kernels): bulk copies are 16-byte
+    aligned, fit the panel buffer, and the forward / backward steps together visit every row of every S_i^-1 array and
+    every column of every B_i exactly once."""
+    import ctypes
+    from emu_util import Emu
+    prod, _ = robots
+    e = Emu(prod[rn], kind, N)
+    fac_off = (ctypes.c_int * (N + 2))()
+    bk_off = (ctypes.c_int * (N + 1))()
+    pd = (ctypes.c_int * 3)()
+    e.lib.emu_qp_factor_offsets(e.h, fac_off, bk_off, pd)
+    for latency in (0, 1):
+        buf = (ctypes.c_int * (8 * 4096))()
+        ns = e.lib.emu_qp_schedule(e.h, latency, buf, len(buf))
+        sched = np.array(buf[:8 * ns]).reshape(ns, 8)
+        seen_rows = {i: [] for i in range(N + 1)}
+        seen_cols = {i: [] for i in range(N)}
+        for off, length, a, b, i, flags, start, ss in sched:
+            s = ss & 255
+            assert off % 2 == 0 and length % 2 == 0 and 0 < length <= pd[latency]
+            if flags & 1:      # backward: columns [a, b) of B_i, stride `start`
+                assert off == bk_off[i] + a * start and length == (b - a) * start and start == (s + 1) & ~1
+                seen_cols[i] += list(range(a, b))
+            else:
+                assert off == fac_off[i] + start and start <= a * s and a * s - start <= 1 and start + length >= b * s
+                assert off + length <= fac_off[i + 1]
+                seen_rows[i] += list(range(a, b))
+        for i in range(N + 1):
+            rows = sorted(seen_rows[i])
+            assert rows == list(range(len(rows)))
+        for i in range(N):
+            assert sorted(seen_cols[i]) == list(range(e.ndx))
+        # the forward steps of a stage cover rows 0 .. s/2 of its array
+        for off, length, a, b, i, flags, start, ss in sched:
+            if not (flags & 1) and (flags & 4):
+                assert b == (ss & 255) // 2 + 1
