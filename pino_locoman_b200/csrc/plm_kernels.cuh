@@ -105,15 +105,15 @@ node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* _
   }
   // coalesced write-out
   double* go = g + (size_t)b * L.m + L.row_off[node];
-  for (int r = lane; r < T.nrows; r += 32) go[r] = ws.g[r];
+  for (int r = lane; r < T.nrows; r += 32) store_j(go + r, ws.g[r]);
   if (node == 0) {   // DX_0 == 0 rows (optimization/ocp.py:109)
     double* g0 = g + (size_t)b * L.m;
-    for (int r = lane; r < L.ndx; r += 32) g0[r] = A.xs[r];
+    for (int r = lane; r < L.ndx; r += 32) store_j(g0 + r, A.xs[r]);
   }
   if (want_jac) {
     if (node == 0) {
       double* J0 = Jv + (size_t)b * L.nnz;
-      for (int e = lane; e < L.ndx; e += 32) J0[e] = 1.0;
+      for (int e = lane; e < L.ndx; e += 32) store_j(J0 + e, 1.0);
     }
   }
 }

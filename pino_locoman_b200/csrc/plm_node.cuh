@@ -82,14 +82,32 @@ struct LaneState {
   double Tq[6], Tv[6];   // centroidal_vel without base inputs: d v_b / d dq_lane, d v_b / d v_lane
 };
 
+#ifndef PLM_EMIT_HINTS
+#define PLM_EMIT_HINTS 1
+#endif
+// Jacobian entry store: written once and never read by this kernel -> streaming store on the device
+PLM_HD void store_j(double* dst, double val) {
+#if defined(__CUDA_ARCH__) && PLM_EMIT_HINTS
+  __stcs(dst, val);
+#else
+  *dst = val;
+#endif
+}
 PLM_HD void emit(const NodeWs& ws, const NodeArgs& A, int src, int idx, double val) {
-#if defined(__CUDA_ARCH__)
-  // read-only path: the lookups of a run of emits can be issued ahead of the stores of the earlier ones
+#if defined(__CUDA_ARCH__) && PLM_EMIT_HINTS
+  // read-only path: the lookups of a run of emits can be issued ahead of the stores of the earlier ones; the table is
+  // asked to stay in L1 (evict_last) and the entries, written once and never read here, stream past it (st.global.cs)
+  short pos16;
+  asm("ld.global.nc.L1::evict_last.s16 %0, [%1];" : "=h"(pos16) : "l"(A.lut + A.T->src_off[src] + idx));
+  const int pos = pos16;
+  if (pos >= 0) store_j(ws.J + pos, val);
+#elif defined(__CUDA_ARCH__)
   int pos = __ldg(A.lut + A.T->src_off[src] + idx);
+  if (pos >= 0) ws.J[pos] = val;
 #else
   int pos = A.lut[A.T->src_off[src] + idx];
-#endif
   if (pos >= 0) ws.J[pos] = val;
+#endif
 }
 
 PLM_HD bool kind_has_state_v(int kind) { return kind != PLM_CENTROIDAL_VEL; }
@@ -888,13 +906,13 @@ PLM_HD void node_phase_f(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
     }
     if (A.want_jac) {
       const int p0 = T.pos_foot[k];
-      ws.J[p0] = c;
-      ws.J[p0 + 1] = c * 2.0 * f[0];
-      ws.J[p0 + 2] = c * 2.0 * f[1];
-      ws.J[p0 + 3] = -c * mu2 * 2.0 * f[2];
-      ws.J[p0 + 4] = 1.0 - c;
-      ws.J[p0 + 5] = 1.0 - c;
-      ws.J[p0 + 6] = 1.0 - c;
+      store_j(ws.J + p0, c);
+      store_j(ws.J + p0 + 1, c * 2.0 * f[0]);
+      store_j(ws.J + p0 + 2, c * 2.0 * f[1]);
+      store_j(ws.J + p0 + 3, -c * mu2 * 2.0 * f[2]);
+      store_j(ws.J + p0 + 4, 1.0 - c);
+      store_j(ws.J + p0 + 5, 1.0 - c);
+      store_j(ws.J + p0 + 6, 1.0 - c);
     }
   }
   if (M.has_ext && lane == M.nfeet) {
@@ -941,7 +959,7 @@ PLM_HD void node_phase_consts(NodeWs& ws, const NodeArgs& A, int lane, int nlane
       case 4: v = contact[ce.arg]; break;
       default: v = 1.0 - contact[ce.arg]; break;
     }
-    ws.J[ce.pos] = v;
+    store_j(ws.J + ce.pos, v);
   }
 }
 
