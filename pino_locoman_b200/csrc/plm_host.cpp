@@ -353,7 +353,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       std::stable_sort(row.begin(), row.end(), [](const Entry& a, const Entry& b) { return a.col < b.col; });
       for (const Entry& e : row) {
         if (e.kind == 0) lut[T.src_off[e.src] + e.idx] = (int16_t)pos;
-        else if (e.kind == 1) out.consts.push_back({pos, e.src, e.idx});
+        else if (e.kind == 1) out.consts.push_back({pos, (int16_t)e.src, (int16_t)e.idx});
         else if (e.idx == 0) T.pos_foot[e.src] = pos;
         ++pos;
       }

@@ -48,6 +48,7 @@ struct NodeWs {
   double Rinit[9];
   double jr[9];
   double jqb[6][3];           // angular q-direction of the base columns (right Jacobian of Exp mixes them)
+  double fx[3 * PLM_MAXC];    // contact / external forces of this node (staged once: every phase reads them)
   double* g;     // [max_rows]
   double* J;     // node block of the Jacobian values: the instance's block in HBM (kernel) or a staging array (host emulation)
   double* aba;   // ABA scratch: M/L, Minv, GQ, GV (nv x 32 each), GF (nv x nf)
@@ -132,6 +133,7 @@ PLM_HD void node_phase_a(NodeWs& ws, const NodeArgs& A, int lane) {
   const int dqoff = (KIND == PLM_CENTROIDAL_VEL) ? 6 : 0;      // dx = [dh | dq]
   const double* dx = A.xs;
   const double* u = A.xs + L.ndx;
+  if (lane < L.nf) ws.fx[lane] = u[L.f_idx + lane];
   if (lane < nv) {
     ws.cq[lane] = dx[dqoff + lane];
     // without base inputs the leading block of U holds the joint part only; the base part starts at zero and is
@@ -226,7 +228,6 @@ PLM_HD void lane_q_direction(const NodeWs& ws, LaneState& st, int lane, int body
 template <int KIND>
 PLM_HD void node_phase_b(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane) {
   const PlmModel& M = *A.M;
-  const PlmLayout& L = *A.L;
   if (lane >= M.nv) return;
   const double* Rb = ws.Rb;
   double R[9], p[3] = {0, 0, 0};
@@ -301,13 +302,12 @@ PLM_HD void node_phase_b(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
   mxf(Vj, H, t6);
   for (int i = 0; i < 6; ++i) F[i] += t6[i];
   // external forces on this body (world force f_k at world point p_k)
-  const double* u = A.xs + L.ndx;
   for (int k = 0; k < M.ncontact; ++k) {
     if (M.contact_body[k] != body) continue;
     double pk[3];
     matvec3(R, M.contact_off[k], pk);
     pk[0] += p[0]; pk[1] += p[1]; pk[2] += p[2];
-    const double* fk = u + L.f_idx + 3 * k;
+    const double* fk = ws.fx + 3 * k;
     double n[3];
     cross3(pk, fk, n);
     F[0] -= fk[0]; F[1] -= fk[1]; F[2] -= fk[2];
@@ -399,7 +399,6 @@ PLM_HD void point_wrench(const double* pk, const double* g, double* o) {
 template <int KIND>
 PLM_HD void node_phase_d(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane) {
   const PlmModel& M = *A.M;
-  const PlmLayout& L = *A.L;
   if (lane >= M.nv) return;
   const int body = M.col_body[lane];
   const double* rec = ws.rec[body];
@@ -425,12 +424,11 @@ PLM_HD void node_phase_d(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
   inertia_mul(mC, mcC, IbC, chi, st.dFqn);
   bc_mul(rec, phi, t6);
   for (int i = 0; i < 6; ++i) st.dFqn[i] += t6[i];
-  const double* u = A.xs + L.ndx;
   const unsigned mask = M.col_contacts[lane];
   for (int k = 0; k < M.ncontact; ++k) {
     if (!((mask >> k) & 1u)) continue;
     double g[3], wr[6];
-    cross3(Jq + 3, u + L.f_idx + 3 * k, g);
+    cross3(Jq + 3, ws.fx + 3 * k, g);
     point_wrench(ws.con[k], g, wr);
     for (int i = 0; i < 6; ++i) st.dFqn[i] += wr[i];
   }
@@ -588,7 +586,7 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
         for (int k = 0; k < M.ncontact; ++k) {
           if (!((mask >> k) & 1u)) continue;
           double g[3], wr[6];
-          cross3(c < 6 ? ws.jqb[c] : cr + 3, u + L.f_idx + 3 * k, g);
+          cross3(c < 6 ? ws.jqb[c] : cr + 3, ws.fx + 3 * k, g);
           point_wrench(ws.con[k], g, wr);
           tq += dot6(st.J, wr);
         }
@@ -643,7 +641,7 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
       if (lane == 1) {
         double hd[6] = {0, 0, -M.gravity_z * Mtot, 0, 0, 0};
         for (int k = 0; k < M.ncontact; ++k) {
-          const double* fk = u + L.f_idx + 3 * k;
+          const double* fk = ws.fx + 3 * k;
           double r3[3] = {ws.con[k][0] - com[0], ws.con[k][1] - com[1], ws.con[k][2] - com[2]};
           hd[0] += fk[0]; hd[1] += fk[1]; hd[2] += fk[2];
           cross3_acc(r3, fk, hd + 3);
@@ -706,7 +704,7 @@ PLM_HD void node_phase_e(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
           cross3(st.Jq + 3, ws.con[k], t3);
           for (int i = 0; i < 3; ++i) dp[i] += st.Jq[i] + t3[i];
         }
-        cross3_acc(dp, u + L.f_idx + 3 * k, acc);
+        cross3_acc(dp, ws.fx + 3 * k, acc);
       }
       for (int r = 0; r < 3; ++r) emit(ws, A, PLM_SRC_XQ, (3 + r) * nv + lane, -A.dt * acc[r] / Mtot);
     }
@@ -886,7 +884,7 @@ PLM_HD void node_phase_f(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
   if (lane < M.nfeet) {
     const int k = lane;
     const double c = contact[k];
-    const double* f = u + L.f_idx + 3 * k;
+    const double* f = ws.fx + 3 * k;
     const int r0 = T.row_foot[k];
     const double mu2 = L.mu * L.mu;
     ws.g[r0] = c * f[2];
@@ -916,7 +914,7 @@ PLM_HD void node_phase_f(NodeWs& ws, const NodeArgs& A, LaneState& st, int lane)
     }
   }
   if (M.has_ext && lane == M.nfeet) {
-    for (int t = 0; t < 3; ++t) ws.g[T.row_ext + t] = u[L.f_idx + 3 * M.nfeet + t];
+    for (int t = 0; t < 3; ++t) ws.g[T.row_ext + t] = ws.fx[3 * M.nfeet + t];
   }
   // ---- arm rows values (lane 5): base-relative linear velocity, world z
   if (T.row_arm >= 0 && lane == 5) {
@@ -949,7 +947,16 @@ PLM_HD void node_phase_consts(NodeWs& ws, const NodeArgs& A, int lane, int nlane
   const PlmNodeType& T = *A.T;
   const double* contact = A.p + A.L->p_contact + 4 * A.node;
   for (int e = lane; e < T.nconst; e += nlanes) {
+#if defined(__CUDA_ARCH__) && PLM_EMIT_HINTS
+    PlmConstEntry ce;      // (the table is shared by every evaluation: kept in L1 like the lookup table)
+    {
+      int lo, hi;
+      asm("ld.global.nc.L1::evict_last.v2.s32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(A.consts + e));
+      ce.pos = lo; ce.code = (int16_t)(hi & 0xffff); ce.arg = (int16_t)(hi >> 16);
+    }
+#else
     const PlmConstEntry ce = A.consts[e];
+#endif
     double v;
     switch (ce.code) {
       case 0: v = 1.0; break;

@@ -114,7 +114,7 @@ PLM_HD void aba_solve_and_derivatives(Exec& ex, NodeWs& ws, const NodeArgs& A) {
         for (int k = 0; k < M.ncontact; ++k) {
           if (!((mask >> k) & 1u)) continue;
           double g[3], wr[6];
-          cross3(c < 6 ? ws.jqb[c] : cr + 3, u + L.f_idx + 3 * k, g);
+          cross3(c < 6 ? ws.jqb[c] : cr + 3, ws.fx + 3 * k, g);
           point_wrench(ws.con[k], g, wr);
           tq += dot6(st.J, wr);
         }

@@ -71,10 +71,10 @@ enum PlmSrc {
 };
 
 // A constant (x-independent) Jacobian entry of a node block.
-struct PlmConstEntry {
+struct alignas(8) PlmConstEntry {      // one 8-byte load per entry
   int32_t pos;     // position in the node's J block
-  int32_t code;    // 0: +1, 1: -1, 2: -dt, 3: -mass, 4: contact k (c_k), 5: 1-c_k   (k in arg)
-  int32_t arg;
+  int16_t code;    // 0: +1, 1: -1, 2: -dt, 3: -mass, 4: contact k (c_k), 5: 1-c_k   (k in arg)
+  int16_t arg;
 };
 
 // Per node-type tables (a node type fixes the row list: first-node skip, torque rows).
