@@ -11,6 +11,7 @@
 //                     dual update, termination tests every check_termination iterations (unscaled residuals,
 //                     primal / dual infeasibility certificates), persistent warm-started iterates.
 #include <math.h>
+#include <stdlib.h>
 
 #include "plm_handle.cuh"
 
@@ -62,7 +63,11 @@ __device__ __forceinline__ StageView stage_view(const PlmLayout& L, const QpLayo
 // Scaling.  mode 0: data update (A = J values, q, l, u given).  mode 1: setup-time scaling with the dummy data of
 // optimization/ocp.py:305-310 (A = ones on the pattern, q = 1, l = -1, u = 1); only E is kept (as Eprev).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(QP_THREADS, 4)
+#ifndef PLM_SCALE_THREADS
+#define PLM_SCALE_THREADS 256
+#define PLM_SCALE_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(PLM_SCALE_THREADS, PLM_SCALE_MIN_CTAS)
 qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, int mode, int first,
                 const double* __restrict__ hess, const double* __restrict__ qin, const double* __restrict__ Jv,
                 const double* __restrict__ lin, const double* __restrict__ uin, QpWork W) {
@@ -86,30 +91,58 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   const double* q = qin ? qin + (size_t)b * n : nullptr;
   double* Dg = W.D + (size_t)b * n;      // also the exchange buffers of the Jacobi-style update
   double* Eg = W.E + (size_t)b * m;
-  // A is read from L2 / HBM in every pass (27 GB at 8192 instances: the values do not survive in L2 between passes).
-  // Measured alternatives of round 2, none faster than this form (16.6 ms at 8192 instances; profiles/ncu_r02_summary.md):
-  // values resident in shared memory with one 1024-thread CTA per SM, thread per row (17.7 ms) or warp per sliced-ELL
-  // slice with packed index words (19 ms: barrier stalls of the 32-warp CTA take over); a whole warp per row / column of
-  // more than 32 entries with a shuffle reduction (16.4 ms).  55 % of the instructions are the two pass loops below.
+  // The passes walk the two sliced-ELL copies of A that the ADMM products use (rows / columns sorted by length, 32 per
+  // slice, warp per slice, lane per item: coalesced value and index streams).  The copies are first filled with the
+  // unscaled values (one gather pass each), read by the ten passes, and scaled in place at the end; the CSR / CSC
+  // copies for the factorisation and the termination tests are written once from the final scaling.
+  // (Before: thread per row / column over the CSR values and a CSC gather, 16.6 ms at 8192 instances; alternatives
+  // measured then: values resident in shared memory with one 1024-thread CTA per SM 17.7 ms, warp per row 16.4 ms.)
   const double* A = Ag;
+  const int32_t* rbase = idx32 + Q.f_rell_base;
+  const int32_t* cbase = idx32 + Q.f_cell_base;
+  const int16_t* rind = idx + Q.f_rell_ind;
+  const int16_t* cind = idx + Q.f_cell_ind;
+  double* AR = W.AhatR + (size_t)b * Q.rell_total;
+  double* AC = W.AhatC + (size_t)b * Q.cell_total;
+  {
+    const int32_t* rsrc = idx32 + Q.f_rell_src;
+    const int32_t* csrc = idx32 + Q.f_cell_src;
+    for (int e = tid; e < Q.rell_total; e += nth) { const int sp = rsrc[e]; AR[e] = sp >= 0 ? (A ? A[sp] : 1.0) : 0.0; }
+    for (int e = tid; e < Q.cell_total; e += nth) { const int sp = csrc[e]; AC[e] = sp >= 0 ? (A ? A[sp] : 1.0) : 0.0; }
+  }
   for (int j = tid; j < n; j += nth) D[j] = 1.0;
   for (int r = tid; r < m; r += nth) E[r] = 1.0;
   double c = 1.0;
   __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+  // max_j |vals| * v[ind] of every item (padding slots hold 0 and index 0)
+  auto ell_max = [&](const int32_t* __restrict__ base, const int16_t* __restrict__ ind, int sl, const double* vals, const double* v) {      // (vals: written by this kernel, coherent loads)
+    const int b0 = base[sl] + lane, b1 = base[sl + 1];
+    double acc = 0.0;
+    int p = b0;
+    for (; p + 96 < b1; p += 128) {
+      const double a0 = fabs(vals[p]), a1 = fabs(vals[p + 32]), a2 = fabs(vals[p + 64]), a3 = fabs(vals[p + 96]);
+      const int c0 = ind[p], c1 = ind[p + 32], c2 = ind[p + 64], c3 = ind[p + 96];
+      acc = fmax(fmax(acc, a0 * v[c0]), fmax(a1 * v[c1], fmax(a2 * v[c2], a3 * v[c3])));
+    }
+    for (; p < b1; p += 32) acc = fmax(acc, fabs(vals[p]) * v[ind[p]]);
+    return acc;
+  };
   for (int pass = 0; pass < Q.scaling; ++pass) {
     // row norms of the current scaled A: E_r * max_k |A_rk| D_col ; column norms: max(|P^_jj|, D_j * max_r E_r |A_rj|)
-    for (int i = tid; i < m; i += nth) {
-      const int r = rperm[i];
-      double v = 0.0;
-      for (int e = rptr[r]; e < rptr[r + 1]; ++e) v = fmax(v, (A ? fabs(A[e]) : 1.0) * D[rcol[e]]);
-      Eg[r] = E[r] / sqrt(limit_scaling(E[r] * v));
+    for (int sl = warp; sl < Q.n_rslices; sl += nw) {
+      const double v = ell_max(rbase, rind, sl, AR, D);
+      const int item = 32 * sl + lane;
+      if (item < m) { const int r = rperm[item]; Eg[r] = E[r] / sqrt(limit_scaling(E[r] * v)); }
     }
-    for (int i = tid; i < n; i += nth) {
-      const int j = cperm[i];
-      double v = 0.0;
-      for (int e = tptr[j]; e < tptr[j + 1]; ++e) v = fmax(v, (A ? fabs(A[tsrc[e]]) : 1.0) * E[trow[e]]);
-      v = fmax(D[j] * v, c * D[j] * D[j] * fabs(P[j]));
-      Dg[j] = D[j] / sqrt(limit_scaling(v));
+    for (int sl = warp; sl < Q.n_cslices; sl += nw) {
+      double v = ell_max(cbase, cind, sl, AC, E);
+      const int item = 32 * sl + lane;
+      if (item < n) {
+        const int j = cperm[item];
+        v = fmax(D[j] * v, c * D[j] * D[j] * fabs(P[j]));
+        Dg[j] = D[j] / sqrt(limit_scaling(v));
+      }
     }
     __syncthreads();
     for (int j = tid; j < n; j += nth) D[j] = Dg[j];
@@ -146,15 +179,16 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
     W.qh[(size_t)b * n + j] = c * D[j] * q[j];
   }
   if (tid == 0) W.cscale[b] = c;
-  {
-    // sliced-ELL copies (same values, execution order of the ADMM products)
-    __syncthreads();
-    const int32_t* rsrc = idx32 + Q.f_rell_src;
-    const int32_t* csrc = idx32 + Q.f_cell_src;
-    double* AR = W.AhatR + (size_t)b * Q.rell_total;
-    double* AC = W.AhatC + (size_t)b * Q.cell_total;
-    for (int e = tid; e < Q.rell_total; e += nth) { const int sp = rsrc[e]; AR[e] = sp >= 0 ? Ah[sp] : 0.0; }
-    for (int e = tid; e < Q.cell_total; e += nth) { const int sp = csrc[e]; AC[e] = sp >= 0 ? Ah[sp] : 0.0; }
+  // the sliced-ELL copies are scaled in place: (E_r a) D_c, the same product as the CSR copy
+  for (int sl = warp; sl < Q.n_rslices; sl += nw) {
+    const int item = 32 * sl + lane;
+    const double er = item < m ? E[rperm[item]] : 0.0;
+    for (int p2 = rbase[sl] + lane; p2 < rbase[sl + 1]; p2 += 32) AR[p2] = er * AR[p2] * D[rind[p2]];
+  }
+  for (int sl = warp; sl < Q.n_cslices; sl += nw) {
+    const int item = 32 * sl + lane;
+    const double dc = item < n ? D[cperm[item]] : 0.0;
+    for (int p2 = cbase[sl] + lane; p2 < cbase[sl + 1]; p2 += 32) AC[p2] = E[cind[p2]] * AC[p2] * dc;
   }
   const double* l = lin + (size_t)b * m;
   const double* u = uin + (size_t)b * m;
@@ -1372,7 +1406,7 @@ int plm_qp_setup_impl(plm_handle* h, int first, int count, const double* d_hess,
   QP_CUDA(h, cudaMemsetAsync(W.x + (size_t)first * L.n, 0, (size_t)count * L.n * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.z + (size_t)first * L.m, 0, (size_t)count * L.m * sizeof(double), s));
   QP_CUDA(h, cudaMemsetAsync(W.y + (size_t)first * L.m, 0, (size_t)count * L.m * sizeof(double), s));
-  qp_scale_kernel<<<count, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, first, d_hess, nullptr, nullptr, nullptr, nullptr, W);
+  qp_scale_kernel<<<count, PLM_SCALE_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 1, first, d_hess, nullptr, nullptr, nullptr, nullptr, W);
   PLM_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1380,7 +1414,7 @@ int plm_qp_setup_impl(plm_handle* h, int first, int count, const double* d_hess,
 int plm_qp_update_impl(plm_handle* h, int batch, const double* d_hess, const double* d_q, const double* d_J,
                        const double* d_l, const double* d_u, cudaStream_t s) {
   QpWork& W = h->qp;
-  qp_scale_kernel<<<batch, QP_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, 0, d_hess, d_q, d_J, d_l, d_u, W);
+  qp_scale_kernel<<<batch, PLM_SCALE_THREADS, h->smem_scale, s>>>(h->tab, W.d_ql, W.d_idx, W.d_idx32, 0, 0, d_hess, d_q, d_J, d_l, d_u, W);
   PLM_LAUNCH_CHECK(h);
   qp_factor_kernel<<<batch, QP_THREADS, h->smem_factor, s>>>(h->tab, W.d_ql, W.d_idx, W, h->d_qp_fail);
   PLM_LAUNCH_CHECK(h);
