@@ -96,7 +96,10 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
   // unscaled values (one gather pass each), read by the ten passes, and scaled in place at the end; the CSR / CSC
   // copies for the factorisation and the termination tests are written once from the final scaling.
   // (Before: thread per row / column over the CSR values and a CSC gather, 16.6 ms at 8192 instances; alternatives
-  // measured then: values resident in shared memory with one 1024-thread CTA per SM 17.7 ms, warp per row 16.4 ms.)
+  // measured then: values resident in shared memory with one 1024-thread CTA per SM 17.7 ms, warp per row 16.4 ms.
+  // Measured on this form, both slower: 512- / 1024-thread CTAs that keep the copies of the instances in flight in L2
+  // (+2 / +3 ms), one walk of the row copy per pass with the column maxima gathered by shared-memory atomicMax on the
+  // bit patterns (64-bit shared atomicMax is a compare-and-swap loop: +4.5 ms).)
   const double* A = Ag;
   const int32_t* rbase = idx32 + Q.f_rell_base;
   const int32_t* cbase = idx32 + Q.f_cell_base;
