@@ -325,8 +325,10 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
       double* dsc = K + 8 * smax;           // [64 + 8] scratch of the diagonal-block step
       for (int Jb = 0; Jb < nb8; ++Jb) {
         const int j0 = 8 * Jb;
-        // (1) update of block column J
-        for (int t = warp; t < nb8 - Jb; t += nw) {
+        // (1) update of block column J: warp 0 takes the diagonal tile and goes straight on to factor it (2) while the
+        // other warps share the tiles below (the factorisation of the 8x8 block is a serial chain of one warp)
+        const int ntile = nb8 - Jb;
+        for (int t = (warp == 0) ? 0 : warp; t < (warp == 0 ? 1 : ntile); t += nw - 1) {
           const int r0 = j0 + 8 * t;
           const int ar = r0 + fr, br = j0 + fr;
           const bool aok = ar < s, bok = br < s;
@@ -344,10 +346,10 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
           if (v0) Cp[0] = c0v;
           if (v1) Cp[1] = c1v;
         }
-        __syncthreads();
         // (2) diagonal block: lane i = row i of the 8x8 block (identity beyond s); Cholesky by columns with shuffles, then
-        // lane c solves L x = e_c for column c of the inverse
+        // lane c solves L x = e_c for column c of the inverse.  (The other warps only read columns < j0 of these rows.)
         if (warp == 0) {
+          __syncwarp();
           const int mrows = min(8, s - j0);
           const int ri = lane & 7;
           double a8[8];
@@ -393,25 +395,21 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
           }
         }
         __syncthreads();
-        // (3) panel: L[r, J] = H[r, J] L_JJ^-T, one thread per row below the block
-        if (j0 + 8 < s) {
-          const int mc = min(8, s - j0);      // (= 8 here: rows below exist only for full blocks)
-          for (int r = j0 + 8 + tid; r < s; r += nth) {
-            double* Hr = H + tri(r, 0) + j0;
-            double h8[8], o8[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) h8[c] = (c < mc) ? Hr[c] : 0.0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              double acc = 0.0;
-#pragma unroll
-              for (int d = 0; d < 8; ++d)
-                if (d <= c) acc += h8[d] * H[tri(j0 + c, 0) + j0 + d];      // (L_JJ^-1)[c][d]
-              o8[c] = acc;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (c < mc) Hr[c] = o8[c];
+        // (3) panel: L[R, J] = H[R, J] L_JJ^-T for the 8-row tiles R below the block, two DMMAs per tile:
+        // D[r][c] = sum_d H[r][j0 + d] (L_JJ^-1)[c][d]  (rows below exist only for full blocks)
+        if (ntile > 1) {
+          for (int t = 1 + warp; t < ntile; t += nw) {
+            const int ar = j0 + 8 * t + fr;
+            const bool aok = ar < s;
+            double* Hr = H + tri(aok ? ar : 0, 0) + j0;
+            const double* Li = H + tri(j0 + fr, 0) + j0;          // row fr of the inverse block (column index of D)
+            const double a0 = aok ? Hr[fk] : 0.0, a1 = aok ? Hr[4 + fk] : 0.0;
+            const double b0 = (fk <= fr) ? Li[fk] : 0.0, b1 = (4 + fk <= fr) ? Li[4 + fk] : 0.0;
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, a0, b0, d0, d1);
+            dmma884(d0, d1, a1, b1, d0, d1);
+            __syncwarp();
+            if (aok) { Hr[2 * fk] = d0; Hr[2 * fk + 1] = d1; }
           }
           __syncthreads();
         }
@@ -437,20 +435,21 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
         }
         __syncthreads();
         {
-          const int mrows = min(8, s - i0);
-          for (int c = tid; c < i0; c += nth) {
-            double t8[8];
-#pragma unroll
-            for (int d = 0; d < 8; ++d) t8[d] = Tm[d * smax + c];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              if (r < mrows) {
-                double acc = 0.0;
-#pragma unroll
-                for (int d = 0; d < 8; ++d)
-                  if (d <= r) acc += H[tri(i0 + r, 0) + i0 + d] * t8[d];
-                H[tri(i0 + r, 0) + c] = -acc;
-              }
+          // X[I, 0:i0] = -L_II^-1 Tm, 8-column tiles, two DMMAs each: D[r][c] = sum_d (L_II^-1)[r][d] Tm[d][c]
+          const int ar = i0 + fr;
+          const bool aok = ar < s;
+          const double* Li = H + tri(aok ? ar : 0, 0) + i0;
+          const double a0 = (aok && fk <= fr) ? Li[fk] : 0.0, a1 = (aok && 4 + fk <= fr) ? Li[4 + fk] : 0.0;
+          for (int t = warp; t < Ib; t += nw) {
+            const int c0 = 8 * t;
+            const double b0 = Tm[fk * smax + c0 + fr], b1 = Tm[(4 + fk) * smax + c0 + fr];
+            double d0 = 0.0, d1 = 0.0;
+            dmma884(d0, d1, a0, b0, d0, d1);
+            dmma884(d0, d1, a1, b1, d0, d1);
+            if (aok) {
+              double* Xo = H + tri(ar, 0) + c0 + 2 * fk;
+              Xo[0] = -d0;
+              Xo[1] = -d1;
             }
           }
         }
