@@ -717,7 +717,8 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 #ifndef PLM_ADMM_PREFETCH_STEPS
-#define PLM_ADMM_PREFETCH_STEPS 0   // measured (round 2, tools/admm_quick.sh): 4 steps ahead 592 instances 24.2 -> 25.6 ms, 148 instances (latency kernel) 10.2 -> 10.4 ms: no gain, off
+#define PLM_ADMM_PREFETCH_STEPS 0   // measured (round 2): 4 steps ahead 592 instances 24.2 -> 25.6 ms, 148 instances (latency kernel) 10.2 -> 10.4 ms; again with
+                                    // the cyclic-diagonal layout at 8192 instances: 2 steps ahead +4 %, 4 steps ahead +5 %: no gain, off
 #endif
 #ifndef PLM_MBAR_SUSPEND_NS
 #define PLM_MBAR_SUSPEND_NS 1000
@@ -749,7 +750,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #define ADMM_MIN_CTAS 4
 #define ADMM_THREADS_LAT 512
 #ifndef NBUF
-#define NBUF 2        // ring of panel buffers, throughput kernel
+#define NBUF 2        // ring of panel buffers, throughput kernel (three buffers of 1368 doubles within the same shared memory: +12 %)
 #endif
 #define NBUF_LAT 3    // latency kernel (whole stages)
 #define SYM_K 128    // threads per part: thread (k, part) owns output k of the stage (stage size <= SYM_K), part = tid / SYM_K
@@ -805,31 +806,6 @@ __device__ __forceinline__ void rect_panel(const double* __restrict__ pan, int s
   acc0 += s2;
   acc1 += s3;
 }
-// The same with the columns dealt to the two halves of a warp (lanes 0-15: even columns of the panel, lanes 16-31: odd
-// ones; output k = 16 warp + (lane & 15)): all eight warps share the step, the halves are added up by one shuffle at
-// the end of the stage.
-#ifndef PLM_RECT_SPLIT
-#define PLM_RECT_SPLIT 0
-#endif
-__device__ __forceinline__ void rect_panel_split(const double* __restrict__ pan, int sp, int j0, int j1, const double* __restrict__ vin, int k,
-                                                 int half, double& acc0, double& acc1) {
-  int j = j0 + half;
-  const double* a = pan + half * sp + k;
-  const int sp2 = 2 * sp;
-  double s2 = 0.0, s3 = 0.0;
-  for (; j + 6 < j1; j += 8) {
-    const double a0 = a[0], a1 = a[sp2], a2 = a[2 * sp2], a3 = a[3 * sp2];
-    acc0 += a0 * vin[j];
-    acc1 += a1 * vin[j + 2];
-    s2 += a2 * vin[j + 4];
-    s3 += a3 * vin[j + 6];
-    a += 4 * sp2;
-  }
-  for (; j < j1; j += 2) { acc0 += a[0] * vin[j]; a += sp2; }
-  acc0 += s2;
-  acc1 += s3;
-}
-
 template <int NT, int MINB, int NB, bool LAT>
 __global__ void __launch_bounds__(NT, MINB)
 qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t* __restrict__ idx, const int32_t* __restrict__ idx32, QpWork W,
@@ -978,12 +954,10 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const int s = S1.w & 255;
       double* bi = xt + (S1.w >> 8);
       const int bsel = (int)(used % NB);
-#if PLM_RECT_SPLIT
-      if (first && dir) { const int kb2 = 16 * (tid >> 5) + (tid & 15); bk = kb2 < s ? kb2 : -1; }
-#else
       if (first && dir) bk = tid < s ? tid : -1;     // backward: one warp per 32 outputs over all the columns (no partial
-                                                     // sums: the result goes straight into x_i and the stage needs one CTA barrier)
-#endif
+                                                     // sums: the result goes straight into x_i and the stage needs one CTA barrier;
+                                                     // dealing the columns to the two halves of every warp, all eight warps busy and one
+                                                     // shuffle at the end, measured +1 %)
       {   // schedule entry of the next step (consumed at the end of this one)
         const int nst = st + 1 < nsched ? st + 1 : 0;
         S0 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS));
@@ -1091,11 +1065,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (dir == 0) {
         if ((tid & (SYM_K - 1)) < s) sym_panel<SYM_PARTS>(pbuf + bsel * pdb - shift, s, r0, r1, vd, tid & (SYM_K - 1), tid / SYM_K, acc0, acc1);
       }
-#if PLM_RECT_SPLIT
-      else if (bk >= 0) rect_panel_split(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, (tid >> 4) & 1, acc0, acc1);
-#else
       else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
-#endif
       if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
@@ -1112,14 +1082,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
           if (dir == 0) {
             if ((tid & (SYM_K - 1)) < s) cpart[(tid / SYM_K) * smax + (tid & (SYM_K - 1))] = sum;
           }
-#if PLM_RECT_SPLIT
-          else {
-            const double tot = sum + __shfl_xor_sync(0xffffffffu, sum, 16);
-            if (bk >= 0 && !(tid & 16)) bi[bk] -= tot;
-          }
-#else
           else if (bk >= 0) bi[bk] -= sum;       // nothing else reads stage i's slice of xt during its backward step
-#endif
         }
       }
       if (last) {
