@@ -91,7 +91,7 @@ PLM_HD void aba_solve_and_derivatives(Exec& ex, NodeWs& ws, const NodeArgs& A) {
   if (!A.want_jac) return;
   // 5. recompute the recursion at the solved acceleration
   ex.run([&](int lane, LaneState& st) { node_phase_b<PLM_WHOLE_BODY_ABA>(ws, A, st, lane); });
-  for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
+  ex.run([&](int lane, LaneState&) { node_phase_c(ws, M, lane); });
   ex.run([&](int lane, LaneState& st) {
     for (int e = lane; e < 2 * PLM_LD * nv + nv * nf; e += 32) GQ[e] = 0.0;   // GQ, GV, GF are contiguous
     node_phase_d<PLM_WHOLE_BODY_ABA>(ws, A, st, lane);

@@ -67,14 +67,14 @@ PLM_HD void node_eval_body(Exec& ex, NodeWs& ws, const NodeArgs& A) {
   (void)T;
   ex.run([&](int lane, LaneState&) { node_phase_a<KIND>(ws, A, lane); });
   ex.run([&](int lane, LaneState& st) { node_phase_b<KIND>(ws, A, st, lane); });
-  for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
+  ex.run([&](int lane, LaneState&) { node_phase_c(ws, M, lane); });
   if (NOBASE) {
     // inputs without the base part: solve the six gap rows for it (first pass ran with a zero base part), then
     // repeat the chain walk and the composites with it in place
     ex.run([&](int lane, LaneState& st) { node_phase_base_cols<KIND>(ws, A, st, lane); });
     ex.run([&](int lane, LaneState&) { node_phase_base_solve<KIND>(ws, lane); });
     ex.run([&](int lane, LaneState& st) { node_phase_b<KIND>(ws, A, st, lane); });
-    for (int s = 0; s < M.nbody - 1; ++s) ex.run([&](int lane, LaneState&) { node_phase_c_step(ws, M, s, lane); });
+    ex.run([&](int lane, LaneState&) { node_phase_c(ws, M, lane); });
   }
   if (KIND == PLM_WHOLE_BODY_ABA) {
     aba_solve_and_derivatives<Exec>(ex, ws, A);
