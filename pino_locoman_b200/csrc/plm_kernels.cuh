@@ -27,6 +27,13 @@ node_eval_kernel(DeviceTables tab, const double* __restrict__ x, const double* _
   PlmModel* sM = reinterpret_cast<PlmModel*>(smem);
   PlmLayout* sL = reinterpret_cast<PlmLayout*>(smem + (sizeof(PlmModel) + 7) / 8);
   double* wsbase = smem + (sizeof(PlmModel) + 7) / 8 + (sizeof(PlmLayout) + 7) / 8;
+  if (tr.part && tr.accepted) {
+    // later line-search launches: a CTA whose instances have all finished leaves before staging the tables
+    const PlmLayout& Lg = *tab.layout;
+    const long long it0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const bool live = it0 < (long long)batch * tr.ntrial * Lg.nodes && !tr.accepted[(int)(it0 / Lg.nodes) / tr.ntrial];
+    if (!__syncthreads_or(live)) return;
+  }
   {
     const int* src = reinterpret_cast<const int*>(tab.model);
     int* dst = reinterpret_cast<int*>(sM);
