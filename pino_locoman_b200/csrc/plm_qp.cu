@@ -747,7 +747,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // Two instantiations: throughput (256 threads, 4 CTAs per SM) and, for batches that leave SMs idle, latency (512
 // threads, one CTA per SM, no register pressure).
 #define ADMM_THREADS 256
-#define ADMM_MIN_CTAS 4
+#ifndef ADMM_MIN_CTAS
+#define ADMM_MIN_CTAS 4     // (three CTAs per SM with 80 registers and two panels per stage: 313 -> 332 ms at 8192 instances)
+#endif
 #define ADMM_THREADS_LAT 512
 #ifndef NBUF
 #define NBUF 2        // ring of panel buffers, throughput kernel (three buffers of 1368 doubles within the same shared memory: +12 %)
