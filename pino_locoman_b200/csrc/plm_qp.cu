@@ -236,11 +236,12 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
   const int tsz = smax * (smax + 1) / 2;
   double* H = sm;                      // [tsz]  stage block -> (in place) inverse X = L^-1 of its Cholesky factor, packed lower
-  double* Wm = H + tsz;                // [smax][ndx]  W = X G^T (dense coupling only)
+  const int wld = ((ndx + 15) & ~15) + 8;      // leading dimension of W: = 8 mod 16, so that the four rows of a DMMA fragment fall in distinct banks
+  double* Wm = H + tsz;                // [smax][wld]  W = X G^T (dense coupling only)
   // K: [ndx (ndx+1)/2] Schur term for the next stage, packed lower.  It is written at the end of a stage and consumed by
   // the assembly of the next one; in between (factorisation) the same shared memory is the scratch of the blocked steps:
   // Tm [8][smax] and dsc [72].
-  double* K = Wm + (Q.sparse_coupling ? 0 : smax * ndx);
+  double* K = Wm + (Q.sparse_coupling ? 0 : smax * wld);
   const int ksz = max(ndx * (ndx + 1) / 2, 8 * smax + 72);
   double* gsc = K + ksz;               // [ndx]  rho_r * (next entry)^2 of the integrator rows
   double* rs = gsc + ndx;              // [max_rows] rho of the node rows
@@ -576,7 +577,7 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
         const int t = o / ndx, c2 = o - t * ndx;
         double acc = 0.0;
         for (int q = 0; q < nc; ++q) acc += Nn[q * ndx + c2] * Y[t * ncm + q];
-        Wm[t * ndx + c2] = acc;
+        Wm[t * wld + c2] = acc;
       }
     } else
     {   // lanes of a warp share the integrator row c2 (uniform entry loop: dense and sparse rows do not mix) and take
@@ -593,41 +594,63 @@ qp_factor_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_
           const int k = sv.ccol[e];
           if (k <= t) acc += As[e] * Xt[k];
         }
-        Wm[t * ndx + c2] = g * acc;
+        Wm[t * wld + c2] = g * acc;
       }
     }
     __syncthreads();
-    {   // B_i = S_i^-1 G_i^T = X^T W (see the sparse branch)
+    {   // B_i = S_i^-1 G_i^T = X^T W and K = W^T W (- carry) as 8x8 tiles on the FP64 tensor cores
+      const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fk = lane & 3;
+      constexpr int nw = QP_THREADS >> 5;
       const int sp = (s + 1) & ~1;
       double* Bo = Lout + Q.bk_off[i];
-      for (int o = tid; o < ndx * sp; o += nth) {
-        const int c2 = o / sp, kk = o - c2 * sp;
-        double a0 = 0.0, a1 = 0.0;
-        if (kk < s) {
-          int t = kk;
-          for (; t + 1 < s; t += 2) { a0 += H[tri(t, kk)] * Wm[t * ndx + c2]; a1 += H[tri(t + 1, kk)] * Wm[(t + 1) * ndx + c2]; }
-          if (t < s) a0 += H[tri(t, kk)] * Wm[t * ndx + c2];
+      const int nkt = (s + 7) >> 3, nct = (ndx + 7) >> 3;
+      // D[kk][c2] = sum_{t >= kk} X[t][kk] W[t][c2]
+      for (int tile = warp; tile < nkt * nct; tile += nw) {
+        const int kt = tile / nct, ct = tile - kt * nct;
+        const int kk = 8 * kt + fr;           // row of the A fragment
+        const int cb = 8 * ct + fr;           // column of the B fragment
+        double d0 = 0.0, d1 = 0.0;
+        for (int t0 = 8 * kt; t0 < s; t0 += 4) {
+          const int t = t0 + fk;
+          const double a = (t < s && t >= kk) ? H[tri(t, kk)] : 0.0;      // (t >= kk and t < s imply kk < s)
+          const double bv = (t < s && cb < ndx) ? Wm[t * wld + cb] : 0.0;
+          dmma884(d0, d1, a, bv, d0, d1);
         }
-        Bo[o] = a0 + a1;
+        const int c2 = 8 * ct + 2 * fk;
+        if (kk < s) {
+          if (c2 < ndx) Bo[c2 * sp + kk] = d0;
+          if (c2 + 1 < ndx) Bo[(c2 + 1) * sp + kk] = d1;
+        }
       }
-    }
-    for (int o = tid; o < ndx * (ndx + 1) / 2; o += nth) {
-      int r = (int)((sqrt(8.0 * o + 1.0) - 1.0) * 0.5);
-      while (tri(r + 1, 0) <= o) ++r;
-      while (tri(r, 0) > o) --r;
-      const int c2 = o - tri(r, 0);
-      double a0 = 0.0, a1 = 0.0;
-      int t = 0;
-      for (; t + 1 < s; t += 2) { a0 += Wm[t * ndx + r] * Wm[t * ndx + c2]; a1 += Wm[(t + 1) * ndx + r] * Wm[(t + 1) * ndx + c2]; }
-      if (t < s) a0 += Wm[t * ndx + r] * Wm[t * ndx + c2];
-      double carry = 0.0;                   // general coupling: H_{i+1,i+1} += sum_q rho_q n_q n_q^T (K is subtracted from H)
-      if (Q.general_coupling) {
-        const QpTypeIdx& I = Q.type[L.node_type[i]];
-        const int16_t* crows = idx + I.gc_rows;
-        const double* Nn = rs + L.max_rows + smax * Q.ncoup_max;
-        for (int q = 0; q < I.ncoup; ++q) carry += rs[crows[q]] * Nn[q * ndx + r] * Nn[q * ndx + c2];
+      if (sp > s)
+        for (int c2 = tid; c2 < ndx; c2 += nth) Bo[c2 * sp + s] = 0.0;      // padding row of the column-major block
+      // K[r][c2] = sum_t W[t][r] W[t][c2] - carry, lower tiles
+      const QpTypeIdx& I = Q.type[L.node_type[i]];
+      const int16_t* crows = idx + I.gc_rows;
+      const double* Nn = rs + L.max_rows + smax * Q.ncoup_max;
+      for (int tile = warp; tile < nct * (nct + 1) / 2; tile += nw) {
+        int rt = 0;
+        while ((rt + 1) * (rt + 2) / 2 <= tile) ++rt;
+        const int ct = tile - rt * (rt + 1) / 2;
+        const int ra = 8 * rt + fr, cb = 8 * ct + fr;
+        double d0 = 0.0, d1 = 0.0;
+        for (int t0 = 0; t0 < s; t0 += 4) {
+          const int t = t0 + fk;
+          const double a = (t < s && ra < ndx) ? Wm[t * wld + ra] : 0.0;
+          const double bv = (t < s && cb < ndx) ? Wm[t * wld + cb] : 0.0;
+          dmma884(d0, d1, a, bv, d0, d1);
+        }
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+          const int c2 = 8 * ct + 2 * fk + q2;
+          if (ra < ndx && c2 <= ra) {
+            double carry = 0.0;               // general coupling: H_{i+1,i+1} += sum_q rho_q n_q n_q^T (K is subtracted from H)
+            if (Q.general_coupling)
+              for (int q = 0; q < I.ncoup; ++q) carry += rs[crows[q]] * Nn[q * ndx + ra] * Nn[q * ndx + c2];
+            K[tri(ra, c2)] = (q2 ? d1 : d0) - carry;
+          }
+        }
       }
-      K[o] = a0 + a1 - carry;
     }
     __syncthreads();
   }
@@ -1340,8 +1363,9 @@ int plm_qp_alloc(plm_handle* h) {
   const int smax = Q.smax, ndx = L.ndx;
   h->smem_scale = (size_t)(L.n + L.m + 32) * 8;
   // staging J in shared memory (1 CTA/SM) loses against reading it from L2 with 5-6 resident CTAs per SM (measured)
-  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * ndx + std::max(ndx * (ndx + 1) / 2, 8 * smax + 72) + ndx + L.max_rows + 2) * 8;
-  if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * ndx * 8;     // no W buffer
+  const int wld = ((ndx + 15) & ~15) + 8;
+  h->smem_factor = (size_t)(smax * (smax + 1) / 2 + smax * wld + std::max(ndx * (ndx + 1) / 2, 8 * smax + 72) + ndx + L.max_rows + 2) * 8;
+  if (Q.sparse_coupling) h->smem_factor -= (size_t)smax * wld * 8;     // no W buffer
   if (Q.general_coupling) h->smem_factor += (size_t)(smax * Q.ncoup_max + Q.ncoup_max * ndx) * 8;     // Y, Nn
   // throughput kernel: w aliases the panel ring
   const int gcn = Q.general_coupling ? Q.ncoup_max : 0;

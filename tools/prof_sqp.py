@@ -17,10 +17,11 @@ from pino_locoman_b200.utils.robot import B2G  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=296)
 ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--dynamics", default=bench.DYNAMICS)
 args = ap.parse_args()
 robot = B2G()
 robot.set_gait_sequence("trot", 0.8)
-ocp = make_ocp(dynamics=bench.DYNAMICS, default_args=OCP_ARGS[bench.DYNAMICS], robot=robot, nodes=bench.NODES, solver="osqp",
+ocp = make_ocp(dynamics=args.dynamics, default_args=OCP_ARGS[args.dynamics], robot=robot, nodes=bench.NODES, solver="osqp",
                batch=args.batch, device="cuda:0")
 x_host, p_host = bench.synthetic_inputs(robot, ocp, args.batch, 0)
 ocp.init_solver()
