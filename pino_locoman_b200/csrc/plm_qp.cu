@@ -773,7 +773,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #ifndef ADMM_MIN_CTAS
 #define ADMM_MIN_CTAS 4     // (three CTAs per SM with 80 registers and two panels per stage: 313 -> 332 ms at 8192 instances)
 #endif
-#define ADMM_THREADS_LAT 512
+#ifndef ADMM_THREADS_LAT
+#define ADMM_THREADS_LAT 512     // (one B2G instance, 100 iterations: 256 threads 7.81 ms, 512 threads 7.85 ms, 1024 threads 9.23 ms; 148 instances: 9.88 / 9.44 / 10.64 ms)
+#endif
 #ifndef NBUF
 #define NBUF 2        // ring of panel buffers, throughput kernel (three buffers of 1368 doubles within the same shared memory: +12 %)
 #endif
