@@ -511,7 +511,8 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
           maxlen = std::max(maxlen, len);
           sched.push_back(Q.fac_off[i] + start); sched.push_back(len); sched.push_back(r0); sched.push_back(r1);
           sched.push_back(i);
-          sched.push_back(dir | ((k == 0) << 1) | ((k + 1 == npan) << 2));
+          // (bits 8.. of the flags: size of the previous stage, for the coupling step of the first panel)
+          sched.push_back(dir | ((k == 0) << 1) | ((k + 1 == npan) << 2) | ((i > 0 ? ndx + nu[i - 1] : 0) << 8));
           sched.push_back(start);
           sched.push_back(s | (L.x_off[i] << 8));
         }
@@ -544,7 +545,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     if (const char* e = getenv("PLM_PANEL_DOUBLES")) cap = std::max(256, atoi(e));      // tuning hook (tools/ab_libs.sh)
     build(cap, Q.f_sched, Q.n_sched, Q.panel_doubles);
     build(plm_sinv_rows(Q.smax) * Q.smax + 4, Q.f_sched_lat, Q.n_sched_lat, Q.panel_doubles_lat);
-    Q.g_doubles = 4 * ndx;                                         // compact coupling block of one stage: <= 4 entries per integrator row
+    Q.g_doubles = (5 * ndx + 1) & ~1;                              // compact coupling block of one stage: <= 4 entries per integrator row + their columns (packed)
   }
   Q.max_iter = ocp.osqp_max_iter; Q.check_termination = ocp.osqp_check_termination; Q.scaling = ocp.osqp_scaling;
   Q.rho = ocp.osqp_rho; Q.sigma = ocp.osqp_sigma; Q.alpha = ocp.osqp_alpha;

@@ -896,7 +896,13 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       const int e0 = sp.rptr[c2], e1 = sp.rptr[c2 + 1] - 1;
       const double coef = rho[L.row_off[i] + c2] * Ap[e1];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Gc[(size_t)q * 4 + j] = (e0 + j < e1) ? coef * Ap[e0 + j] : 0.0;
+      for (int j = 0; j < 4; ++j) Gc[(size_t)i * gd + 5 * c2 + j] = (e0 + j < e1) ? coef * Ap[e0 + j] : 0.0;
+      // the own-stage columns of the (up to) four entries ride along in the fifth word: the coupling step of the
+      // iterations then runs without a single global load
+      unsigned long long pk = 0ull;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk |= (unsigned long long)(unsigned short)sp.ccol[e0 + (e0 + j < e1 ? j : 0)] << (16 * j);
+      Gc[(size_t)i * gd + 5 * c2 + 4] = __longlong_as_double((long long)pk);
     }
     asm volatile("fence.proxy.async;" ::: "memory");     // the bulk copies below read Gc through the async proxy
   }
@@ -978,6 +984,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     int4 S1 = __ldg(reinterpret_cast<const int4*>(sched) + 1);
     for (int st = 0; st < nsched; ++st) {
       const int r0 = S0.z, r1 = S0.w, i = S1.x, dir = S1.y & 1, first = S1.y & 2, last = S1.y & 4, shift = S1.z;
+      const int sprev_sched = S1.y >> 8;      // forward steps: size of the previous stage
       const int s = S1.w & 255;
       double* bi = xt + (S1.w >> 8);
       const int bsel = (int)(used % NB);
@@ -1009,7 +1016,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
             if (c < s) { const double v = bi[c]; vd[c] = v; vd[c + s] = v; }
           }
           if (i > 0) {     // b_i -= G_{i-1} tv_{i-1}
-            const StageView sp = stage_view(L, Q, idx, i - 1);
+            const int sprev = sprev_sched;      // size of stage i - 1 (schedule entry)
             // tv_{i-1} still sits in the partial sums of the parts: they are added up here, on read, which saves the
             // combine pass and its CTA barrier; the sum also goes to stage i-1's slice of xt, where the backward sweep
             // expects it
@@ -1020,15 +1027,16 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
               for (int w2 = 1; w2 < SYM_PARTS; ++w2) v += pp[w2 * smax + k];
               return v;
             };
-            if (tid < L.x_off[i] - L.x_off[i - 1]) xt[L.x_off[i - 1] + tid] = tprev(tid);
+            if (tid < sprev) bi[tid - sprev] = tprev(tid);      // (stage i - 1's slice of xt ends where b_i starts)
             if (Q.general_coupling) {
+              const StageView sp = stage_view(L, Q, idx, i - 1);
               // b_i -= sum_q n_q rho_q (a_q . tv_{i-1}) over the coupling rows q of node i-1 (see the factor kernel)
               const QpTypeIdx& I = Q.type[L.node_type[i - 1]];
               const int16_t* crows = idx + I.gc_rows;
               const int16_t* rowq = idx + I.gc_rowq;
               const double* Ap = Ah + L.nnz_off[i - 1];
               const double* rp = rho + L.row_off[i - 1];
-              const int sub = tid & 7, sprev = sp.s;
+              const int sub = tid & 7;
               for (int q0 = 0; q0 < I.ncoup; q0 += nth >> 3) {
                 const int q = q0 + (tid >> 3);
                 double acc = 0.0;
@@ -1054,15 +1062,17 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
               }
             } else if (sparse) {
               if (tid < ndx) {
-                const int e0 = sp.rptr[tid], ne = sp.rptr[tid + 1] - 1 - e0;
+                const double* gr = g + 5 * tid;
+                const unsigned long long pk = (unsigned long long)__double_as_longlong(gr[4]);
                 double acc = 0.0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc += g[4 * tid + j] * tprev(sp.ccol[e0 + (j < ne ? j : 0)]);
+                for (int j = 0; j < 4; ++j) acc += gr[j] * tprev((int)((pk >> (16 * j)) & 0xffffull));
                 const double nv = bi[tid] - acc;
                 vd[tid] = nv; vd[tid + s] = nv;
               }
             } else {
               // dense integrator rows (whole_body_aba, centroidal_vel): eight lanes per row, shuffle reduction
+              const StageView sp = stage_view(L, Q, idx, i - 1);
               const double* Ap = Ah + L.nnz_off[i - 1];
               const double* rp = rho + L.row_off[i - 1];
               const int sub = tid & 7;

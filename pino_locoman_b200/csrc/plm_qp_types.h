@@ -15,7 +15,8 @@ namespace plm {
 // consecutive rows j.
 #define PLM_PANEL_DOUBLES 2192        // 17 KB: three panels per B2G stage in either sweep, four CTAs per SM
 // schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage,
-// flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage),
+// flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage,
+// forward steps: bits 8.. size of the previous stage),
 // offset of the copy inside the stage block, stage size | x_off << 8}
 // A backward step streams columns [first, end) of B_i instead (all s rows of each); the seventh int is the column stride sp.
 #define PLM_SCHED_INTS 8
@@ -67,7 +68,8 @@ struct QpLayout {
   int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
   // the same for the latency kernel (whole stages as panels)
   int32_t f_sched_lat, n_sched_lat, panel_doubles_lat;
-  int32_t g_doubles;                   // doubles of one stage's compact coupling block (4 per integrator row)
+  int32_t g_doubles;                   // doubles of one stage's compact coupling block (5 per integrator row: 4 values and their
+                                       // own-stage columns packed into the fifth word)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's inverse block (cyclic diagonals, see above)
   int32_t bk_off[PLM_MAXNODES + 1];    // offset (doubles) of stage i's back-substitution block B_i = S_i^-1 G_i^T, i < N:
                                        // column major [ndx][sp], sp = s rounded up to even
@@ -98,7 +100,7 @@ struct QpWork {
   double* uh = nullptr;      // [m]     E u
   double* rho = nullptr;     // [m]     rho_vec
   double* Linv = nullptr;    // [fac_total] inverse stage blocks S_i^-1 (cyclic diagonals), then the back-substitution blocks B_i
-  double* Gc = nullptr;      // [nodes][ndx][4] compact coupling blocks diag(rho n) A_int (sparse couplings only)
+  double* Gc = nullptr;      // [nodes][g_doubles] compact coupling blocks diag(rho n) A_int (sparse couplings only)
   double* x = nullptr;       // [n]     persistent scaled ADMM iterates
   double* z = nullptr;       // [m]
   double* y = nullptr;       // [m]
