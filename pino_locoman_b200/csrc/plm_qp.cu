@@ -844,7 +844,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const int n = L.n, m = L.m, ndx = L.ndx, N = L.nodes, smax = Q.smax;
   const int pdb = LAT ? Q.panel_doubles_lat : Q.panel_doubles;
   const int gd = Q.g_doubles;
-  const bool sparse = Q.sparse_coupling != 0;
+  const bool sparse = Q.sparse_coupling != 0, general = Q.general_coupling != 0;
   // panel buffers and coupling-block buffers first (16-byte aligned), then the mbarriers, then the gathered vectors.
   // Throughput kernel: the row vector w is dead during the sweeps and no panel is resident outside them, so w ALIASES
   // the panel buffers (the ring is filled at the start of each iteration's sweeps and runs empty at their end); this
@@ -1028,7 +1028,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
               return v;
             };
             if (tid < sprev) bi[tid - sprev] = tprev(tid);      // (stage i - 1's slice of xt ends where b_i starts)
-            if (Q.general_coupling) {
+            if (general) {
               const StageView sp = stage_view(L, Q, idx, i - 1);
               // b_i -= sum_q n_q rho_q (a_q . tv_{i-1}) over the coupling rows q of node i-1 (see the factor kernel)
               const QpTypeIdx& I = Q.type[L.node_type[i - 1]];
@@ -1102,7 +1102,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       if (dir == 0) {
         if ((tid & (SYM_K - 1)) < s) sym_panel<SYM_PARTS>(pbuf + bsel * pdb - shift, s, r0, r1, vd, tid & (SYM_K - 1), tid / SYM_K, acc0, acc1);
       }
-      else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, xt + L.x_off[i + 1], bk, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
+      else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, bi + s, bk, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
       if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
