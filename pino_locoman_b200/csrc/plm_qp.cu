@@ -856,13 +856,17 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   double* gbuf = sm + NB * pdb;                      // [NB][gd] compact coupling block travelling with a stage's first panel
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + ring_al);  // [NB] "panel landed" barriers
   int* cnt = reinterpret_cast<int*>(sm + ring_al + NB);                          // [NB] warps done with the panel (running count)
-  double* xt = sm + ring_al + 2 * NB;        // [n]  rhs -> forward solution y -> x~ -> delta_x
+  // the schedule of one iteration, 16 bytes per step, lives in shared memory: the step loop and the refills then run
+  // without global loads (packed from the host table at kernel start)
+  const int nsched = LAT ? Q.n_sched_lat : Q.n_sched;
+  uint4* sch = reinterpret_cast<uint4*>(sm + ring_al + 2 * NB);     // [nsched] {offset, len | r0 << 16 | r1 << 24, stage | flags << 8 | s_prev << 16 | s << 24, shift | x_off << 16}
+  double* xt = sm + ring_al + 2 * NB + 2 * nsched;        // [n]  rhs -> forward solution y -> x~ -> delta_x
   double* w = ALIAS ? sm : xt + n;          // [m]  rho z - y, then z~ = A x~, then delta_y
   constexpr int SYM_PARTS = NT / SYM_K;
   double* cpart = xt + n + (ALIAS ? 0 : m);       // [SYM_PARTS][smax] partial sums of the forward product, one slice per part
   double* vd = cpart + SYM_PARTS * smax;      // [2 smax] input of the forward product, stored twice in a row (sym_panel)
-  double* red = vd + 2 * smax;                // [32]
-  double* gcs = red + 32;      // [ncoup_max] general coupling only: rho_q (a_q . tv_{i-1}) of the coupling rows
+  double* red = vd + 2 * smax;                // [16] (one entry per warp, at most 16 warps)
+  double* gcs = red + 16;      // [ncoup_max] general coupling only: rho_q (a_q . tv_{i-1}) of the coupling rows
   const double* Ah = W.Ahat + (size_t)b * L.nnz;
   const double* AT = W.AhatT + (size_t)b * L.nnz;
   const double* AR = W.AhatR + (size_t)b * Q.rell_total;
@@ -870,7 +874,6 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   FlatIdx F;
   F.rptr = idx32 + Q.f_rptr; F.tptr = idx32 + Q.f_tptr; F.rcol = idx + Q.f_rcol; F.trow = idx + Q.f_trow; F.rperm = idx + Q.f_rperm; F.cperm = idx + Q.f_cperm;
   const int32_t* sched = idx32 + (LAT ? Q.f_sched_lat : Q.f_sched);
-  const int nsched = LAT ? Q.n_sched_lat : Q.n_sched;
   const double* Ph = W.Ph + (size_t)b * n;
   const double* qh = W.qh + (size_t)b * n;
   const double* lh = W.lh + (size_t)b * m;
@@ -914,27 +917,29 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int j = tid; j < (int)(gcs - xt); j += nth) xt[j] = 0.0;
+  for (int st = tid; st < nsched; st += nth) {
+    const int4 S0 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS));
+    const int4 S1 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS) + 1);
+    sch[st] = make_uint4((unsigned)S0.x, (unsigned)S0.y | ((unsigned)S0.z << 16) | ((unsigned)S0.w << 24),
+                         (unsigned)S1.x | (((unsigned)S1.y & 255u) << 8) | (((unsigned)S1.y >> 8) << 16) | (((unsigned)S1.w & 255u) << 24),
+                         (unsigned)S1.z | (((unsigned)S1.w >> 8) << 16));
+  }
   if (ALIAS) for (int j = tid; j < ring_al; j += nth) sm[j] = 0.0;
   __syncthreads();
   unsigned used = 0;
   auto issue_step = [&](int st, int buf) {            // one thread: schedule step st into buffer buf
-    const int4 S0 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS));
-    const int4 S1 = __ldg(reinterpret_cast<const int4*>(sched + st * PLM_SCHED_INTS) + 1);
-#ifdef PLM_EXP_HALF_BYTES
-    const unsigned bytes = (((unsigned)S0.y * 8u) / PLM_EXP_HALF_BYTES + 15u) & ~15u;     // timing experiment only (wrong results)
-#else
-    const unsigned bytes = (unsigned)S0.y * 8u;
-#endif
-    const int i = S1.x, dir = S1.y & 1;
-    const bool with_g = sparse && (S1.y & 2) && dir == 0 && i > 0;     // forward coupling b_i -= G_{i-1} tv_{i-1}
+    const uint4 E = sch[st];
+    const unsigned bytes = (E.y & 0xffffu) * 8u;
+    const int i = (int)(E.z & 255u), fl = (int)((E.z >> 8) & 255u);
+    const bool with_g = sparse && (fl & 2) && !(fl & 1) && i > 0;     // forward coupling b_i -= G_{i-1} tv_{i-1}
     mbar_expect_tx(&bars[buf], bytes + (with_g ? (unsigned)gd * 8u : 0u));
-    bulk_g2s(pbuf + (size_t)buf * pdb, Lf + S0.x, bytes, &bars[buf]);
+    bulk_g2s(pbuf + (size_t)buf * pdb, Lf + E.x, bytes, &bars[buf]);
     if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
     if (PLM_ADMM_PREFETCH_STEPS > 0) {      // the panel PLM_ADMM_PREFETCH_STEPS steps further on (wraps into the next iteration)
       int pf = st + PLM_ADMM_PREFETCH_STEPS;
       if (pf >= nsched) pf -= nsched;
-      const int4 P0 = __ldg(reinterpret_cast<const int4*>(sched + pf * PLM_SCHED_INTS));
-      bulk_prefetch_l2(Lf + P0.x, (unsigned)P0.y * 8u);
+      const uint4 P0 = sch[pf];
+      bulk_prefetch_l2(Lf + P0.x, (P0.y & 0xffffu) * 8u);
     }
   };
   if (!ALIAS && tid == 0)
@@ -980,23 +985,18 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     double acc0 = 0.0, acc1 = 0.0;
     int bk = -1;                              // backward steps: output of this thread (-1: none)
     int pend = -1, pend_st = 0;               // lane 0: deferred refill check of the previous step
-    int4 S0 = __ldg(reinterpret_cast<const int4*>(sched));
-    int4 S1 = __ldg(reinterpret_cast<const int4*>(sched) + 1);
     for (int st = 0; st < nsched; ++st) {
-      const int r0 = S0.z, r1 = S0.w, i = S1.x, dir = S1.y & 1, first = S1.y & 2, last = S1.y & 4, shift = S1.z;
-      const int sprev_sched = S1.y >> 8;      // forward steps: size of the previous stage
-      const int s = S1.w & 255;
-      double* bi = xt + (S1.w >> 8);
+      const uint4 E = sch[st];
+      const int r0 = (int)((E.y >> 16) & 255u), r1 = (int)(E.y >> 24), i = (int)(E.z & 255u), fl = (int)((E.z >> 8) & 255u);
+      const int dir = fl & 1, first = fl & 2, last = fl & 4, shift = (int)(E.w & 0xffffu);
+      const int sprev_sched = (int)((E.z >> 16) & 255u);      // forward steps: size of the previous stage
+      const int s = (int)(E.z >> 24);
+      double* bi = xt + (E.w >> 16);
       const int bsel = (int)(used % NB);
       if (first && dir) bk = tid < s ? tid : -1;     // backward: one warp per 32 outputs over all the columns (no partial
                                                      // sums: the result goes straight into x_i and the stage needs one CTA barrier;
                                                      // dealing the columns to the two halves of every warp, all eight warps busy and one
                                                      // shuffle at the end, measured +1 %)
-      {   // schedule entry of the next step (consumed at the end of this one)
-        const int nst = st + 1 < nsched ? st + 1 : 0;
-        S0 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS));
-        S1 = __ldg(reinterpret_cast<const int4*>(sched + nst * PLM_SCHED_INTS) + 1);
-      }
       mbar_wait(&bars[bsel], (used / NB) & 1u);
       if (pend >= 0) {      // the previous step's buffer: refill it if this warp was the last one out
         if ((pend + 1) % nwarps == 0) {
@@ -1381,8 +1381,8 @@ int plm_qp_alloc(plm_handle* h) {
   if (Q.general_coupling) h->smem_factor += (size_t)(smax * Q.ncoup_max + Q.ncoup_max * ndx) * 8;     // Y, Nn
   // throughput kernel: w aliases the panel ring
   const int gcn = Q.general_coupling ? Q.ncoup_max : 0;
-  h->smem_admm = (size_t)(((std::max(NBUF * (Q.panel_doubles + Q.g_doubles), L.m) + 1) & ~1) + 2 * NBUF + L.n + (ADMM_THREADS / SYM_K + 2) * smax + 32 + gcn) * 8;
-  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + L.n + L.m + (ADMM_THREADS_LAT / SYM_K + 2) * smax + 32 + gcn) * 8;
+  h->smem_admm = (size_t)(((std::max(NBUF * (Q.panel_doubles + Q.g_doubles), L.m) + 1) & ~1) + 2 * NBUF + 2 * Q.n_sched + L.n + (ADMM_THREADS / SYM_K + 2) * smax + 16 + gcn) * 8;
+  h->smem_admm_lat = (size_t)(NBUF_LAT * (Q.panel_doubles_lat + Q.g_doubles) + 2 * NBUF_LAT + 2 * Q.n_sched_lat + L.n + L.m + (ADMM_THREADS_LAT / SYM_K + 2) * smax + 16 + gcn) * 8;
   if (smax > SYM_K) { h->error = "stage size exceeds the thread-column capacity of the ADMM kernel"; return 7; }
   if (h->smem_scale > 227 * 1024 || h->smem_factor > 227 * 1024 || h->smem_admm > 227 * 1024 || h->smem_admm_lat > 227 * 1024) {
     h->error = "QP workspace exceeds shared memory";
