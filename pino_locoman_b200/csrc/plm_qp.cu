@@ -677,7 +677,9 @@ struct FlatIdx {
 
 // Sliced-ELL product: warp per slice of 32 items, lane per item, coalesced value / index streams.
 //   out[perm[item]] = sum_j vals[slot] v[ind[slot]] (+ sigma x - q for the column product)
-#define ELL_B 8
+#ifndef ELL_B
+#define ELL_B 8     // rows of a slice in flight per lane (4, 12, 16 measured: equal or slower)
+#endif
 template <bool ADD>
 __device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const int16_t* __restrict__ ind, const int16_t* __restrict__ perm, int nitems,
                                          int nsl, const double* __restrict__ vals, const double* v, double* out, double sigma,
