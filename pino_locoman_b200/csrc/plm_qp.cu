@@ -123,12 +123,26 @@ qp_scale_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t
     const int b0 = base[sl] + lane, b1 = base[sl + 1];
     double acc = 0.0;
     int p = b0;
-    for (; p + 96 < b1; p += 128) {
-      const double a0 = fabs(vals[p]), a1 = fabs(vals[p + 32]), a2 = fabs(vals[p + 64]), a3 = fabs(vals[p + 96]);
-      const int c0 = ind[p], c1 = ind[p + 32], c2 = ind[p + 64], c3 = ind[p + 96];
-      acc = fmax(fmax(acc, a0 * v[c0]), fmax(a1 * v[c1], fmax(a2 * v[c2], a3 * v[c3])));
+    for (; p + 32 * 7 < b1; p += 32 * 8) {
+      double a[8];
+      int c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = fabs(vals[p + 32 * j]); c[j] = ind[p + 32 * j]; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmax(acc, a[j] * v[c[j]]);
     }
-    for (; p < b1; p += 32) acc = fmax(acc, fabs(vals[p]) * v[ind[p]]);
+    if (p < b1) {      // the remaining rows as one predicated group (all loads in flight at once)
+      double a[7];
+      int c[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const bool ok = p + 32 * j < b1;
+        a[j] = ok ? fabs(vals[p + 32 * j]) : 0.0;
+        c[j] = ok ? (int)ind[p + 32 * j] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc = fmax(acc, a[j] * v[c[j]]);
+    }
     return acc;
   };
   for (int pass = 0; pass < Q.scaling; ++pass) {
