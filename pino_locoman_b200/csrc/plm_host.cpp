@@ -495,6 +495,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     // panel schedules: forward sweep stages 0..N (row panels of the cyclic-diagonal array of S_i^-1), backward sweep
     // stages N-1..0 (column panels of B_i), panels of at most `capacity` doubles.  Two schedules: PLM_PANEL_DOUBLES panels
     // for the throughput kernel (four CTAs per SM), whole stages for the latency kernel (one CTA per SM, shared memory to spare).
+    bool sched_ok = true;
     auto build = [&](int capacity, int32_t& f_sched, int32_t& n_sched, int32_t& panel_doubles) {
       std::vector<int> sched;
       int maxlen = 0;
@@ -536,6 +537,12 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
       for (int i = 0; i <= N; ++i) add_stage(i, 0);
       for (int i = N - 1; i >= 0; --i) add_back(i);         // x_N = S_N^-1 r_N needs no backward work
       n_sched = (int)sched.size() / PLM_SCHED_INTS;
+      // the ADMM kernel packs an entry into 16 bytes (plm_qp.cu): field widths
+      for (int k = 0; k < n_sched; ++k) {
+        const int* e = sched.data() + k * PLM_SCHED_INTS;
+        if (e[1] > 0xffff || e[2] > 255 || e[3] > 255 || e[4] > 255 || (e[5] >> 8) > 255 || e[6] > 0xffff || (e[7] >> 8) > 0xffff)
+          sched_ok = false;
+      }
       while (out.qp_idx32.size() % 4) out.qp_idx32.push_back(0);     // schedule entries are read as two 16-byte words
       f_sched = (int)out.qp_idx32.size();
       for (int v : sched) out.qp_idx32.push_back(v);
@@ -545,6 +552,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     if (const char* e = getenv("PLM_PANEL_DOUBLES")) cap = std::max(256, atoi(e));      // tuning hook (tools/ab_libs.sh)
     build(cap, Q.f_sched, Q.n_sched, Q.panel_doubles);
     build(plm_sinv_rows(Q.smax) * Q.smax + 4, Q.f_sched_lat, Q.n_sched_lat, Q.panel_doubles_lat);
+    if (!sched_ok || Q.smax > 255 || N > 254) { out.error = "problem too large for the packed ADMM schedule (stage size / node count / offsets)"; return false; }
     Q.g_doubles = (5 * ndx + 1) & ~1;                              // compact coupling block of one stage: <= 4 entries per integrator row + their columns (packed)
   }
   Q.max_iter = ocp.osqp_max_iter; Q.check_termination = ocp.osqp_check_termination; Q.scaling = ocp.osqp_scaling;
