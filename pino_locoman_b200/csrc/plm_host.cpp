@@ -534,7 +534,26 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
           sched.push_back(s | (L.x_off[i] << 8));
         }
       };
-      for (int i = 0; i <= N; ++i) add_stage(i, 0);
+      // dense integrator rows: the coupling block of node i - 1 travels through the ring ahead of stage i's panels
+      auto add_coupling = [&](int i) {
+        const int gld = Q.gdense_ld;
+        const int maxrows = std::max(1, capacity / gld);
+        const int npan = (ndx + maxrows - 1) / maxrows;
+        for (int k = 0; k < npan; ++k) {
+          const int c0 = (int)((long long)ndx * k / npan), c1 = (int)((long long)ndx * (k + 1) / npan);
+          const int len = (c1 - c0) * gld;
+          maxlen = std::max(maxlen, len);
+          sched.push_back(((i - 1) * ndx + c0) * gld); sched.push_back(len); sched.push_back(c0); sched.push_back(c1);
+          sched.push_back(i);
+          sched.push_back(8 | ((k == 0) << 4) | ((ndx + nu[i - 1]) << 8));
+          sched.push_back(gld);
+          sched.push_back((i < N ? ndx + nu[i] : ndx) | (L.x_off[i] << 8));
+        }
+      };
+      for (int i = 0; i <= N; ++i) {
+        if (Q.gdense_ld > 0 && i > 0) add_coupling(i);
+        add_stage(i, 0);
+      }
       for (int i = N - 1; i >= 0; --i) add_back(i);         // x_N = S_N^-1 r_N needs no backward work
       n_sched = (int)sched.size() / PLM_SCHED_INTS;
       // the ADMM kernel packs an entry into 16 bytes (plm_qp.cu): field widths
@@ -550,6 +569,7 @@ bool build_tables(const plm_robot_desc& robot, const plm_ocp_desc& ocp, HostTabl
     };
     int cap = PLM_PANEL_DOUBLES;
     if (const char* e = getenv("PLM_PANEL_DOUBLES")) cap = std::max(256, atoi(e));      // tuning hook (tools/ab_libs.sh)
+    Q.gdense_ld = (!Q.sparse_coupling && !Q.general_coupling) ? ((Q.smax + 1) & ~1) : 0;
     build(cap, Q.f_sched, Q.n_sched, Q.panel_doubles);
     build(plm_sinv_rows(Q.smax) * Q.smax + 4, Q.f_sched_lat, Q.n_sched_lat, Q.panel_doubles_lat);
     if (!sched_ok || Q.smax > 255 || N > 254) { out.error = "problem too large for the packed ADMM schedule (stage size / node count / offsets)"; return false; }

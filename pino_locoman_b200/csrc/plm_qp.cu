@@ -906,7 +906,8 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
   const double alpha = Q.alpha, sigma = Q.sigma;
   // ---- compact coupling blocks G_i[c][j] = rho_c n_c A_int[c][j-th own-stage entry] (the ADMM iterations only ever
   // need these products); written once per solve, then streamed with the panels.
-  double* Gc = W.Gc + (size_t)b * N * gd;
+  const int gld = Q.gdense_ld;      // dense integrator rows: leading dimension of the zero-filled coupling blocks
+  double* Gc = W.Gc + (size_t)b * N * max(gd, ndx * gld);
   if (sparse) {
     for (int q = tid; q < N * ndx; q += nth) {
       const int i = q / ndx, c2 = q - i * ndx;
@@ -924,6 +925,22 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
       Gc[(size_t)i * gd + 5 * c2 + 4] = __longlong_as_double((long long)pk);
     }
     asm volatile("fence.proxy.async;" ::: "memory");     // the bulk copies below read Gc through the async proxy
+  }
+  if (gld > 0) {
+    // dense integrator rows (whole_body_aba, centroidal_vel): zero-filled blocks G_i[c][k] = rho_c n_c A_int[c][k], k < s_i,
+    // streamed through the panel ring ahead of stage i + 1 (coupling panels of the schedule)
+    for (int q = tid; q < N * ndx * gld; q += nth) Gc[q] = 0.0;
+    __syncthreads();
+    for (int q = tid >> 3; q < N * ndx; q += nth >> 3) {
+      const int i = q / ndx, c2 = q - i * ndx;
+      const StageView sp = stage_view(L, Q, idx, i);
+      const double* Ap = Ah + L.nnz_off[i];
+      const int e1 = sp.rptr[c2 + 1] - 1;
+      const double coef = rho[L.row_off[i] + c2] * Ap[e1];
+      for (int e = sp.rptr[c2] + (tid & 7); e < e1; e += 8) Gc[(size_t)q * gld + sp.ccol[e]] = coef * Ap[e];
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");
   }
   // ---- panel pipeline.  `used` counts schedule steps (uniform across the CTA); step q lives in buffer q % NB.  Warps
   // consume the panels of a stage at their own pace (no CTA barrier between panels): every warp waits on the buffer's
@@ -949,7 +966,7 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
     const int i = (int)(E.z & 255u), fl = (int)((E.z >> 8) & 255u);
     const bool with_g = sparse && (fl & 2) && !(fl & 1) && i > 0;     // forward coupling b_i -= G_{i-1} tv_{i-1}
     mbar_expect_tx(&bars[buf], bytes + (with_g ? (unsigned)gd * 8u : 0u));
-    bulk_g2s(pbuf + (size_t)buf * pdb, Lf + E.x, bytes, &bars[buf]);
+    bulk_g2s(pbuf + (size_t)buf * pdb, ((fl & 8) ? Gc : Lf) + E.x, bytes, &bars[buf]);
     if (with_g) bulk_g2s(gbuf + (size_t)buf * gd, Gc + (size_t)(i - 1) * gd, (unsigned)gd * 8u, &bars[buf]);
     if (PLM_ADMM_PREFETCH_STEPS > 0) {      // the panel PLM_ADMM_PREFETCH_STEPS steps further on (wraps into the next iteration)
       int pf = st + PLM_ADMM_PREFETCH_STEPS;
@@ -1022,27 +1039,56 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         pend = -1;
       }
       PROF_ADD(2);
-      if (first) {
+      // tv_{i-1} still sits in the partial sums of the parts: they are added up on read, which saves the combine pass and
+      // its CTA barrier; the sum also goes to stage i-1's slice of xt, where the backward sweep expects it
+      const double* pp = cpart;
+      auto tprev = [&](int k) {
+        double v = pp[k];
+#pragma unroll
+        for (int w2 = 1; w2 < SYM_PARTS; ++w2) v += pp[w2 * smax + k];
+        return v;
+      };
+      const bool coup = (fl & 8) != 0;
+      double csum = 0.0;
+      if (coup) {
+        // coupling panel (dense integrator rows): rows [r0, r1) of G_{i-1}, b_i[c] -= G_{i-1}[c][:] . tv_{i-1}, eight lanes
+        // per row; the first one of a stage also moves tv_{i-1} to xt and the rest of b_i to vd
+        const int sprev = sprev_sched;
+        if (fl & 16) {
+          if (tid < sprev) bi[tid - sprev] = tprev(tid);
+          const int c = ndx + tid;
+          if (c < s) { const double v = bi[c]; vd[c] = v; vd[c + s] = v; }
+        }
+        const double* pan = pbuf + bsel * pdb;
+        const int sub = tid & 7;
+        for (int c0 = r0; c0 < r1; c0 += nth >> 3) {
+          const int c2 = c0 + (tid >> 3);
+          double acc = 0.0;
+          if (c2 < r1) {
+            const double* gr = pan + (c2 - r0) * shift;      // (the seventh schedule word of a coupling panel: leading dimension)
+            for (int k = sub; k < sprev; k += 8) acc += gr[k] * tprev(k);
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          if (c2 < r1 && sub == 0) {
+            const double nv = bi[c2] - acc;
+            vd[c2] = nv; vd[c2 + s] = nv;
+          }
+          csum += acc;
+        }
+        PROF_ADD(11);
+      } else if (first) {
         const double* g = gbuf + bsel * gd;
         if (dir == 0) {
           // the input b_i of the product goes to vd twice in a row (sym_panel); its first ndx entries come out of the
-          // coupling step below
-          {
+          // coupling step below (dense integrator rows: out of the coupling panels, which also moved the rest)
+          if (!(gld > 0 && i > 0)) {
             const int c = (i > 0 ? ndx : 0) + tid;
             if (c < s) { const double v = bi[c]; vd[c] = v; vd[c + s] = v; }
           }
-          if (i > 0) {     // b_i -= G_{i-1} tv_{i-1}
+          if (i > 0 && gld == 0) {     // b_i -= G_{i-1} tv_{i-1}
             const int sprev = sprev_sched;      // size of stage i - 1 (schedule entry)
-            // tv_{i-1} still sits in the partial sums of the parts: they are added up here, on read, which saves the
-            // combine pass and its CTA barrier; the sum also goes to stage i-1's slice of xt, where the backward sweep
-            // expects it
-            const double* pp = cpart;
-            auto tprev = [&](int k) {
-              double v = pp[k];
-#pragma unroll
-              for (int w2 = 1; w2 < SYM_PARTS; ++w2) v += pp[w2 * smax + k];
-              return v;
-            };
             if (tid < sprev) bi[tid - sprev] = tprev(tid);      // (stage i - 1's slice of xt ends where b_i starts)
             if (general) {
               const StageView sp = stage_view(L, Q, idx, i - 1);
@@ -1086,28 +1132,6 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
                 const double nv = bi[tid] - acc;
                 vd[tid] = nv; vd[tid + s] = nv;
               }
-            } else {
-              // dense integrator rows (whole_body_aba, centroidal_vel): eight lanes per row, shuffle reduction
-              const StageView sp = stage_view(L, Q, idx, i - 1);
-              const double* Ap = Ah + L.nnz_off[i - 1];
-              const double* rp = rho + L.row_off[i - 1];
-              const int sub = tid & 7;
-              for (int c0 = 0; c0 < ndx; c0 += nth >> 3) {
-                const int c2 = c0 + (tid >> 3);
-                double acc = 0.0;
-                int e1 = 0;
-                if (c2 < ndx) {
-                  e1 = sp.rptr[c2 + 1] - 1;
-                  for (int e = sp.rptr[c2] + sub; e < e1; e += 8) acc += Ap[e] * tprev(sp.ccol[e]);
-                }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                if (c2 < ndx && sub == 0) {
-                  const double nv = bi[c2] - rp[c2] * Ap[e1] * acc;
-                  vd[c2] = nv; vd[c2 + s] = nv;
-                }
-              }
             }
           }
           __syncthreads();
@@ -1115,15 +1139,16 @@ qp_admm_kernel(DeviceTables tab, const QpLayout* __restrict__ Qp, const int16_t*
         }
         acc0 = 0.0; acc1 = 0.0;
       }
-      if (dir == 0) {
+      if (coup) {
+      } else if (dir == 0) {
         if ((tid & (SYM_K - 1)) < s) sym_panel<SYM_PARTS>(pbuf + bsel * pdb - shift, s, r0, r1, vd, tid & (SYM_K - 1), tid / SYM_K, acc0, acc1);
       }
       else if (bk >= 0) rect_panel(pbuf + bsel * pdb, shift, r0, r1, bi + s, bk, acc0, acc1);   // x_i = tv_i - B_i x_{i+1}[0:ndx]
-      if (dir == 0) PROF_ADD(9); else PROF_ADD(5);
+      if (!coup) { if (dir == 0) PROF_ADD(9); else PROF_ADD(5); }
       {
         // release the buffer: the count is bumped by an instruction that depends on the sums, i.e. after every
         // shared-memory read of the panel by this warp has returned; the refill check is deferred past the next wait
-        const double sum = acc0 + acc1;
+        const double sum = coup ? csum : acc0 + acc1;
         int zero;
         asm volatile("and.b32 %0, %1, 0;" : "=r"(zero) : "r"(__double2loint(sum)));
         __syncwarp();
@@ -1374,7 +1399,7 @@ int plm_qp_alloc(plm_handle* h) {
   auto al = [&](double** p, size_t per) { return cudaMalloc(p, B * per * sizeof(double)); };
   QP_CUDA(h, al(&W.Ahat, L.nnz)); QP_CUDA(h, al(&W.AhatT, L.nnz)); QP_CUDA(h, al(&W.AhatR, Q.rell_total)); QP_CUDA(h, al(&W.AhatC, Q.cell_total)); QP_CUDA(h, al(&W.D, L.n)); QP_CUDA(h, al(&W.E, L.m)); QP_CUDA(h, al(&W.Eprev, L.m));
   QP_CUDA(h, al(&W.cscale, 1)); QP_CUDA(h, al(&W.Ph, L.n)); QP_CUDA(h, al(&W.qh, L.n)); QP_CUDA(h, al(&W.lh, L.m));
-  QP_CUDA(h, al(&W.uh, L.m)); QP_CUDA(h, al(&W.rho, L.m)); QP_CUDA(h, al(&W.Linv, Q.fac_total)); QP_CUDA(h, al(&W.Gc, (size_t)L.nodes * Q.g_doubles));
+  QP_CUDA(h, al(&W.uh, L.m)); QP_CUDA(h, al(&W.rho, L.m)); QP_CUDA(h, al(&W.Linv, Q.fac_total)); QP_CUDA(h, al(&W.Gc, (size_t)L.nodes * std::max((int)Q.g_doubles, (int)(L.ndx * Q.gdense_ld))));
   QP_CUDA(h, al(&W.x, L.n)); QP_CUDA(h, al(&W.z, L.m)); QP_CUDA(h, al(&W.y, L.m));
   QP_CUDA(h, cudaMalloc(&h->d_qp_fail, B * sizeof(int)));
   QP_CUDA(h, cudaMemset(W.x, 0, B * L.n * sizeof(double)));

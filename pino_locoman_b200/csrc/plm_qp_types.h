@@ -16,6 +16,8 @@ namespace plm {
 #define PLM_PANEL_DOUBLES 2192        // 17 KB: three panels per B2G stage in either sweep, four CTAs per SM
 // schedule step: {offset in the instance's factor (doubles), doubles to copy (even), first row, end row, stage,
 // flags (bit 0 direction: 0 forward / 1 backward, bit 1 first panel of the stage, bit 2 last panel of the stage,
+// bit 3 coupling panel (dense integrator rows: rows [first, end) of the zero-filled block diag(rho n) A_int of node
+// stage - 1, streamed from the Gc workspace ahead of the stage's own panels), bit 4 first coupling panel of the stage;
 // forward steps: bits 8.. size of the previous stage),
 // offset of the copy inside the stage block, stage size | x_off << 8}
 // A backward step streams columns [first, end) of B_i instead (all s rows of each); the seventh int is the column stride sp.
@@ -68,6 +70,8 @@ struct QpLayout {
   int32_t panel_doubles;               // capacity of one shared-memory panel buffer (doubles)
   // the same for the latency kernel (whole stages as panels)
   int32_t f_sched_lat, n_sched_lat, panel_doubles_lat;
+  int32_t gdense_ld;                   // dense integrator rows (neither sparse nor general coupling): leading dimension of a stage's
+                                       // zero-filled coupling block [ndx][gdense_ld]; 0 otherwise
   int32_t g_doubles;                   // doubles of one stage's compact coupling block (5 per integrator row: 4 values and their
                                        // own-stage columns packed into the fifth word)
   int32_t fac_off[PLM_MAXNODES + 2];   // offset (doubles) of stage i's inverse block (cyclic diagonals, see above)

@@ -198,9 +198,16 @@ def test_admm_panel_schedule_covers_every_stored_double_once(robots, rn, kind, N
         sched = np.array(buf[:8 * ns]).reshape(ns, 8)
         seen_rows = {i: [] for i in range(N + 1)}
         seen_cols = {i: [] for i in range(N)}
+        seen_coup = {i: [] for i in range(1, N + 1)}
         for off, length, a, b, i, flags, start, ss in sched:
             s = ss & 255
             assert off % 2 == 0 and length % 2 == 0 and 0 < length <= pd[latency]
+            if flags & 8:      # coupling panel (dense integrator rows): rows [a, b) of the block of node i - 1, leading dimension `start`
+                assert kind in ("whole_body_aba", "centroidal_vel") and not (flags & 7) and i >= 1
+                assert off == ((i - 1) * e.ndx + a) * start and length == (b - a) * start and start % 2 == 0
+                assert bool(flags & 16) == (a == 0)
+                seen_coup[i] += list(range(a, b))
+                continue
             if flags & 1:      # backward: columns [a, b) of B_i, stride `start`
                 assert off == bk_off[i] + a * start and length == (b - a) * start and start == (s + 1) & ~1
                 seen_cols[i] += list(range(a, b))
@@ -213,7 +220,10 @@ def test_admm_panel_schedule_covers_every_stored_double_once(robots, rn, kind, N
             assert rows == list(range(len(rows)))
         for i in range(N):
             assert sorted(seen_cols[i]) == list(range(e.ndx))
+        if kind in ("whole_body_aba", "centroidal_vel"):      # every stage after the first is preceded by its coupling panels
+            for i in range(1, N + 1):
+                assert seen_coup[i] == list(range(e.ndx))
         # the forward steps of a stage cover rows 0 .. s/2 of its array
         for off, length, a, b, i, flags, start, ss in sched:
-            if not (flags & 1) and (flags & 4):
+            if not (flags & 9) and (flags & 4):
                 assert b == (ss & 255) // 2 + 1
