@@ -699,10 +699,20 @@ __device__ __forceinline__ void spmv_ell(const int32_t* __restrict__ base, const
                                          int nsl, const double* __restrict__ vals, const double* v, double* out, double sigma,
                                          const double* x, const double* __restrict__ q, const double* addv = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // (the slice bounds and the output index of the next slice are loaded one slice ahead: they head the dependency chain
+  // bounds -> values / indices -> gather of every slice)
+  int nb0 = 0, nb1 = 0, no = -1;
+  if (warp < nsl) {
+    nb0 = __ldg(base + warp); nb1 = __ldg(base + warp + 1);
+    no = 32 * warp + lane < nitems ? (int)__ldg(perm + 32 * warp + lane) : -1;
+  }
   for (int sl = warp; sl < nsl; sl += nw) {
-    const int b0 = __ldg(base + sl) + lane, b1 = __ldg(base + sl + 1);
-    const int item = 32 * sl + lane;
-    const int o = item < nitems ? (int)__ldg(perm + item) : -1;
+    const int b0 = nb0 + lane, b1 = nb1;
+    const int o = no;
+    if (sl + nw < nsl) {
+      nb0 = __ldg(base + sl + nw); nb1 = __ldg(base + sl + nw + 1);
+      no = 32 * (sl + nw) + lane < nitems ? (int)__ldg(perm + 32 * (sl + nw) + lane) : -1;
+    }
     double add = 0.0;
     if (ADD && o >= 0) add = addv ? addv[o] : sigma * x[o] - __ldg(q + o);      // (x is rewritten by this kernel: coherent load)
     double acc = 0.0;
