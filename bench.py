@@ -529,7 +529,11 @@ def main():
                                        "592 instances; the counters overflow at 8192) x the batch: not measured in this run",
                      "peak_source": peak_src,
                      "algorithmic_bytes": bytes_admm, "nnz_F_stored": nnzF, "nnz_F_minimal": nnzF_min,
-                     "frac_minimal_factor": ach_admm_min / peak, "ms_per_step_kernel": ms_admm},
+                     "frac_minimal_factor": ach_admm_min / peak, "ms_per_step_kernel": ms_admm,
+                     # the same time against the DRAM bytes ncu counts for the kernel (they include the two streams of the
+                     # scaled constraint matrix, which SURVEY 8d's formula leaves out)
+                     "frac_of_peak_with_ncu_traffic": (traffic["qp_admm_kernel"] / (ms_admm / 1e3) / 1e9 / peak
+                                                       if traffic.get("qp_admm_kernel") else None)},
         "roofline_node_eval": {"kernel": "node_eval_kernel", "bound": "hbm", "achieved": ach_eval, "peak": peak, "unit": "GB/s",
                                "frac": ach_eval / peak, "traffic": traffic.get("node_eval_kernel"),
                                "bytes_per_node_eval": BYTES_NODE_EVAL, "ms_per_sweep": ms_eval,
